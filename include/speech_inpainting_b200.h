@@ -1,0 +1,161 @@
+/*
+ * speech_inpainting_b200.h - C-ABI of the B200-native Speech-Inpainting hot path.
+ *
+ * The reference (Fireflies-17/Speech-Inpainting) is pure Python with no FFI of its own;
+ * its "operator boundary" for the north-star path is the nn.Module call surface
+ *   CustomModel.forward / HubertModel.forward        I_ea/model.py:80-89
+ *   HubertFeatureReader.get_feats / extract_features I_da/src/hubert_feature_reader.py:44-67
+ *   Generator.forward                                I_ea/hifi_gan/models.py:107-123, I_da/src/models.py:209-225
+ *   CodeGenerator.forward                            I_da/src/model.py:121-189
+ * plus the glue in I_ea/predict.py:85-207 and I_da/scripts/inpainting.py:181-259.
+ * Each entry point below names the reference lines it replaces.  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless named host_*.
+ *   - no allocation inside the library: outputs and workspaces are caller-owned.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - return 0 (SIB_OK) or a negative/positive error code; sib_last_error() gives the text.
+ *     No error is swallowed and there is NO CPU fallback.
+ *   - activations are "frame-major": [batch][time][channels], channels contiguous.
+ *   - re-entrant across devices: no global mutable state except a thread-local error string.
+ */
+#ifndef SPEECH_INPAINTING_B200_H_
+#define SPEECH_INPAINTING_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIB_ABI_VERSION 1
+#define SIB_MAX_TAPS 128
+
+enum sib_status { SIB_OK = 0, SIB_ERR_INVALID = 1, SIB_ERR_CUDA = 2, SIB_ERR_UNSUPPORTED = 3 };
+enum sib_act { SIB_ACT_NONE = 0, SIB_ACT_GELU = 1, SIB_ACT_LRELU = 2, SIB_ACT_TANH = 3 };
+enum sib_dtype { SIB_F32 = 0, SIB_BF16 = 1 };
+
+typedef void* sib_stream_t; /* cudaStream_t */
+
+int sib_abi_version(void);
+const char* sib_last_error(void);
+/* number of kernels this library has launched from the calling thread (bench `gpu_launches`) */
+long long sib_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic frame-major 1-D convolution / linear layer with fused epilogue.
+ *   y[b,t,co] = post( out_scale * ( bias[co] + sum_j sum_ci pre(x[b, t*stride + tap_offset[j], ci]) * w[g][j][ci][co]
+ *                                    + residual[b,t,co] + (accumulate ? y[b,t,co] : 0) ) )
+ *   (res_after_act=1 moves `+ residual` outside post())
+ * rows outside [0,t_in) read as zero (== zero padding).  Covers
+ *   torch.nn.Conv1d (+dilation/padding/stride/groups)   HF:106-175 conv layers, HF:83-92 pos-conv,
+ *                                                       models.py:36-43 ResBlock convs, :108 conv_pre
+ *   torch.nn.ConvTranspose1d (poly-phase: c_out = stride*Cout)  models.py:110-111 `ups[i]`
+ *   torch.nn.Linear (batch=1, n_taps=1)                 HF:228-229, 320-324, 343, 363-367; model.py:88
+ * w layout: [groups][n_taps][c_in/groups][c_out/groups], c_out contiguous.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sib_conv_desc {
+  int32_t batch, t_in, t_out, c_in, c_out, groups;
+  int32_t n_taps, stride;
+  int32_t tap_offset[SIB_MAX_TAPS];
+  int64_t x_batch_stride, y_batch_stride, r_batch_stride; /* elements */
+  int32_t x_row_stride, y_row_stride, r_row_stride;       /* elements */
+  int32_t pre_act;   /* SIB_ACT_NONE | SIB_ACT_LRELU applied to x on load */
+  float pre_slope;
+  int32_t post_act;  /* sib_act */
+  float post_slope;
+  float out_scale;
+  int32_t accumulate;
+  int32_t res_after_act; /* 0: residual joins the sum before post(); 1: y = post(...) + residual (HF:440-441) */
+} sib_conv_desc;
+
+int sib_conv1d_f32(const sib_conv_desc* d, const float* x, const float* w, const float* bias,
+                   const float* residual, float* y, sib_stream_t stream);
+
+/* conv with a single output channel + activation: models.py:119-121 lrelu(0.01) -> conv_post -> tanh.
+ * x [B,T,C] frame-major, w [k][C], y [B,T].  */
+int sib_conv1d_cout1_f32(const float* x, const float* w, const float* bias, float* y, int batch, int t,
+                         int c, int k, int pad, float pre_slope, int post_act, sib_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HuBERT conv0 (Conv1d 1->C, k=10, s=5) fused with its norm (HF:154-175 / HF:127-151).
+ *   mode 0: GroupNorm statistics only -> partial[b][tile][c][2] (sum, sumsq); tile = 64 frames
+ *   mode 1: recompute conv0, GroupNorm(C groups) with mean/rstd[b][c], affine, exact GELU -> y[B,T0,C]
+ *   mode 2: conv0 + bias only (feat_extract_norm == "layer"; LayerNorm+GELU follow as sib_layernorm)
+ * sib_gn_finalize reduces the partials to mean / rstd (double accumulation, eps 1e-5).
+ * ------------------------------------------------------------------------------------------ */
+int sib_conv0_f32(int mode, const float* wave, int batch, int n_samples, int64_t wave_batch_stride,
+                  const float* w /*[C][k]*/, const float* bias /*nullable*/, int c, int k, int stride, int t0,
+                  float* partial, const float* mean, const float* rstd, const float* gamma,
+                  const float* beta, float* y, sib_stream_t stream);
+int sib_conv0_num_tiles(int t0);
+int sib_gn_finalize_f32(const float* partial, int batch, int n_tiles, int c, int t0, float eps, float* mean,
+                        float* rstd, sib_stream_t stream);
+
+/* LayerNorm over the channel axis of `rows` rows (HF:396,398,442,613,147,228; model.py:87):
+ *   y = act( LN(x + residual) * gamma + beta ), residual nullable, act in {NONE, GELU}. In-place allowed. */
+int sib_layernorm_f32(const float* x, const float* residual, const float* gamma, const float* beta, float* y,
+                      int64_t rows, int c, float eps, int post_act, sib_stream_t stream);
+
+/* Multi-head self-attention (HF:234-259 eager path): qkv packed [B,T,3H] (q|k|v), softmax in fp32,
+ * scale d^-1/2, keys >= key_len[b] masked (key_len nullable => no padding). out [B,T,H]. head_dim = 64. */
+int sib_attention_f32(const float* qkv, const int32_t* key_len, float* out, int batch, int t, int heads,
+                      int head_dim, sib_stream_t stream);
+
+/* zero frames t >= key_len[b] of h[B,T,C] (HF:429-432). */
+int sib_zero_padded_frames_f32(float* h, const int32_t* key_len, int batch, int t, int c, sib_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ glue */
+/* a1: wave[b, lo[b]:hi[b]] = 0 (numpy slice semantics; I_ea/predict.py:133, dataset.py:82).
+ * add_eps != 0 first adds it to every sample: y_inp = (y + 1e-6) * mask (I_da inpainting.py:187-191). */
+int sib_zero_ranges_f32(float* wave, int batch, int n, const int32_t* lo, const int32_t* hi, float add_eps,
+                        sib_stream_t stream);
+/* a2: per-utterance (x-mean)/sqrt(var+eps); lengths nullable (HF feature_extraction_wav2vec2.py:78-97,
+ * eps 1e-7, tail -> 0) ; eps 1e-5 reproduces F.layer_norm(x, x.shape) (hubert_feature_reader.py:53-54). */
+int sib_znorm_f32(const float* x, float* y, int batch, int n, const int32_t* lengths, float eps,
+                  sib_stream_t stream);
+/* a11: ragged gather of masked frames: out[off[b]+i, :] = src[b, pos[b]+i, :], i < len[b] (predict.py:164-168) */
+int sib_gather_frames_f32(const float* src, int batch, int t, int d, const int32_t* pos, const int32_t* len,
+                          const int32_t* off, float* out, sib_stream_t stream);
+/* a12: labels[m] = argmax_k cos(v[m], cc[k]) (loss_fn.py:44-46), cc = centred codebook [K,D]; ties -> lowest k */
+int sib_cos_argmax_f32(const float* v, const float* cc, int m, int k, int d, int64_t* labels, sib_stream_t stream);
+/* a17: labels[m] = argmin_k ||f[m]-mu[k]||^2 (sklearn KMeans.predict, inpainting.py:204-205) */
+int sib_l2_argmin_f32(const float* f, const float* mu, int m, int k, int d, int64_t* labels, sib_stream_t stream);
+/* a13: mel[b,:,pos[b]+i] = cc[labels[off[b]+i]] + center, i < len[b]; mel is channels-first [B,D,T] (predict.py:184-187) */
+int sib_paste_centroids_f32(float* mel, int batch, int d, int t, const float* cc, const float* center,
+                            const int64_t* labels, const int32_t* pos, const int32_t* len, const int32_t* off,
+                            sib_stream_t stream);
+/* a14: extend_mel (inference_modified.py:16-19): linear resize along time by 441/256, align_corners=False.
+ * in channels-first [B,D,T]; out channels-first [B,D,Tm] (frame_major=0) or frame-major [B,Tm,D] (1). */
+int sib_extend_mel_f32(const float* in, float* out, int batch, int d, int t, int tm, int frame_major,
+                       sib_stream_t stream);
+/* [B,C,T] <-> [B,T,C] */
+int sib_transpose_f32(const float* in, float* out, int batch, int rows, int cols, sib_stream_t stream);
+/* a18 front (I_da/src/model.py:141-172): out[b,t,:] = emb_c[code[b,t]] | emb_p[zp[b,t/rep]] | spk[b]  (frame-major) */
+int sib_embed_concat_f32(const int64_t* code, const int64_t* zp, const float* spk, const float* emb_c,
+                         const float* emb_p, float* out, int batch, int t, int t_p, int e, int e_spk,
+                         sib_stream_t stream);
+/* a19: int16 = (int16)(int32)trunc(y*32768) (dataset.py:241-243, predict.py:125-127) */
+int sib_pack_int16_f32(const float* y, int16_t* out, int64_t n, sib_stream_t stream);
+
+/* a20: log-mel spectrogram (meldataset.py:49-79 / mel_dump.py:40-98): reflect pad, hann-1024 STFT,
+ * sqrt(re^2+im^2+1e-9), mel basis [n_mels][513] (sparse rows), log(clamp(.,1e-5)). out [B,n_mels,frames]. */
+int sib_mel_spectrogram_f32(const float* wave, int batch, int n, int hop, int pad, const float* mel_basis,
+                            int n_mels, float* out, int frames, sib_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * bf16 tensor-core path (tcgen05 + TMA), see DESIGN.md.  Same contract as sib_conv1d_f32 with
+ * bf16 x / w / y / residual, fp32 bias and accumulation.  w layout: [groups][c_out/g][n_taps][c_in/g]
+ * (K-major).  Requires c_in/groups % 16 == 0.
+ * ------------------------------------------------------------------------------------------ */
+int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void* w, const float* bias,
+                    const void* residual, void* y, void* y_act /* nullable 2nd output = lrelu(y) */,
+                    sib_stream_t stream);
+int sib_cast_f32_to_bf16(const float* in, void* out, int64_t n, sib_stream_t stream);
+int sib_cast_bf16_to_f32(const void* in, float* out, int64_t n, sib_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEECH_INPAINTING_B200_H_ */

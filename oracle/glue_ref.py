@@ -63,6 +63,17 @@ def ida_trim(n_samples: int, hop: int = 320):
     return to_remove, to_remove // hop, to_remove // 80
 
 
+def ida_matched_frames(n_samples: int, n_code: int, n_f0: int, hop: int = 320) -> int:
+    """`match_length([(audio,1),(mask,1),(code,320),(f0,80)])` (I_da/src/multiseries.py:5-73: unit =
+    lcm(1,1,320,80) = 320 samples, n_unit = min over series) followed by the 1280-sample tail trim of
+    I_da/scripts/inpainting.py:243-256 -> number of code frames fed to the generator."""
+    lcm = int(np.lcm.reduce([1, 1, hop, 80]))
+    fpu = [lcm // 1, lcm // 1, lcm // hop, lcm // 80]
+    n_unit = min(n_samples // fpu[0], n_samples // fpu[1], n_code // fpu[2], n_f0 // fpu[3])
+    to_remove, rm_code, _ = ida_trim(n_unit * lcm, hop)
+    return n_unit * fpu[2] - rm_code
+
+
 # ----------------------------------------------------------------------------- a2 z-norm
 def processor_znorm(x: torch.Tensor, lengths=None, padding_value: float = 0.0) -> torch.Tensor:
     """HF wav2vec2/feature_extraction_wav2vec2.py:78-97 `zero_mean_unit_var_norm`:

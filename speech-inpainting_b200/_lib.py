@@ -1,0 +1,91 @@
+"""ctypes binding of the C-ABI in include/speech_inpainting_b200.h.
+
+There is no CPU fallback: if `libsib_b200.so` is missing the import fails loudly
+(build it with `python speech-inpainting_b200/build.py` or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsib_b200.so")
+
+SIB_MAX_TAPS = 128
+ACT_NONE, ACT_GELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+
+
+class ConvDesc(C.Structure):
+    """mirror of `sib_conv_desc`"""
+    _fields_ = [
+        ("batch", C.c_int32), ("t_in", C.c_int32), ("t_out", C.c_int32), ("c_in", C.c_int32),
+        ("c_out", C.c_int32), ("groups", C.c_int32), ("n_taps", C.c_int32), ("stride", C.c_int32),
+        ("tap_offset", C.c_int32 * SIB_MAX_TAPS),
+        ("x_batch_stride", C.c_int64), ("y_batch_stride", C.c_int64), ("r_batch_stride", C.c_int64),
+        ("x_row_stride", C.c_int32), ("y_row_stride", C.c_int32), ("r_row_stride", C.c_int32),
+        ("pre_act", C.c_int32), ("pre_slope", C.c_float), ("post_act", C.c_int32), ("post_slope", C.c_float),
+        ("out_scale", C.c_float), ("accumulate", C.c_int32), ("res_after_act", C.c_int32),
+    ]
+
+
+class SibError(RuntimeError):
+    pass
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_SIGS = {
+    "sib_abi_version": ([], C.c_int),
+    "sib_last_error": ([], C.c_char_p),
+    "sib_launch_count": ([], C.c_longlong),
+    "sib_conv1d_f32": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P], _I),
+    "sib_conv1d_cout1_f32": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P], _I),
+    "sib_conv0_f32": ([_I, _P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], _I),
+    "sib_conv0_num_tiles": ([_I], _I),
+    "sib_gn_finalize_f32": ([_P, _I, _I, _I, _I, _F, _P, _P, _P], _I),
+    "sib_layernorm_f32": ([_P, _P, _P, _P, _P, _L, _I, _F, _I, _P], _I),
+    "sib_attention_f32": ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
+    "sib_zero_padded_frames_f32": ([_P, _P, _I, _I, _I, _P], _I),
+    "sib_zero_ranges_f32": ([_P, _I, _I, _P, _P, _F, _P], _I),
+    "sib_znorm_f32": ([_P, _P, _I, _I, _P, _F, _P], _I),
+    "sib_gather_frames_f32": ([_P, _I, _I, _I, _P, _P, _P, _P, _P], _I),
+    "sib_cos_argmax_f32": ([_P, _P, _I, _I, _I, _P, _P], _I),
+    "sib_l2_argmin_f32": ([_P, _P, _I, _I, _I, _P, _P], _I),
+    "sib_paste_centroids_f32": ([_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], _I),
+    "sib_extend_mel_f32": ([_P, _P, _I, _I, _I, _I, _I, _P], _I),
+    "sib_transpose_f32": ([_P, _P, _I, _I, _I, _P], _I),
+    "sib_embed_concat_f32": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
+    "sib_pack_int16_f32": ([_P, _P, _L, _P], _I),
+    "sib_mel_spectrogram_f32": ([_P, _I, _I, _I, _I, _P, _I, _P, _I, _P], _I),
+    "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
+    "sib_cast_f32_to_bf16": ([_P, _P, _L, _P], _I),
+    "sib_cast_bf16_to_f32": ([_P, _P, _L, _P], _I),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises if it has not been built - no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SibError(f"{LIB_PATH} is missing: build it with `python speech-inpainting_b200/build.py` "
+                           "(there is no CPU / PyTorch fallback for this path)")
+        l = C.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(l, name)  # AttributeError if the .so is stale
+            fn.argtypes = args
+            fn.restype = res
+        if l.sib_abi_version() != 1:
+            raise SibError("libsib_b200.so ABI version mismatch; rebuild")
+        _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS)
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise SibError(f"{what} failed (status {rc}): {lib().sib_last_error().decode()}")

@@ -1,0 +1,244 @@
+// Glue kernels between the two models: ragged mask-frame gather,
+// cosine / L2 codebook assignment, centroid paste, extend_mel, embedding concat, int16 pack, casts.
+// All are HBM/latency-bound index work: coalesced rows, one warp per row where a reduction is needed.
+#include "common.cuh"
+
+namespace {
+
+__global__ void gather_frames_kernel(const float* __restrict__ src, int T, int Dm, const int32_t* __restrict__ pos,
+                                     const int32_t* __restrict__ len, const int32_t* __restrict__ off,
+                                     float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int L = len[b];
+  const int64_t total = (int64_t)L * Dm;
+  const float* s = src + ((int64_t)b * T + pos[b]) * Dm;
+  float* o = out + (int64_t)off[b] * Dm;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    o[i] = s[i];
+}
+
+// One warp per query row.  MODE 0: argmax cosine similarity (torch.cosine_similarity, eps 1e-8);
+// MODE 1: argmin squared L2 distance.  Ties resolve to the lowest index (torch.argmax / np.argmin).
+template <int MODE>
+__global__ void __launch_bounds__(256) assign_kernel(const float* __restrict__ v, const float* __restrict__ cb, int M,
+                                                     int K, int Dm, int64_t* __restrict__ labels) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const float* vr = v + (int64_t)m * Dm;
+  float vn = 0.f;
+  for (int c = lane; c < Dm; c += 32) vn += vr[c] * vr[c];
+  vn = sqrtf(sib::warp_sum(vn));
+  float best = MODE == 0 ? -INFINITY : INFINITY;
+  int best_k = 0;
+  for (int k = 0; k < K; ++k) {
+    const float* cr = cb + (int64_t)k * Dm;
+    float dot = 0.f, cn = 0.f;
+    for (int c = lane; c < Dm; c += 32) {
+      const float a = vr[c], bb = cr[c];
+      if (MODE == 0) {
+        dot = fmaf(a, bb, dot);
+        cn = fmaf(bb, bb, cn);
+      } else {
+        const float dlt = a - bb;
+        dot = fmaf(dlt, dlt, dot);
+      }
+    }
+    dot = sib::warp_sum(dot);
+    float score;
+    if (MODE == 0) {
+      cn = sqrtf(sib::warp_sum(cn));
+      score = dot / (fmaxf(vn, 1e-8f) * fmaxf(cn, 1e-8f));
+      if (score > best) { best = score; best_k = k; }
+    } else {
+      score = dot;
+      if (score < best) { best = score; best_k = k; }
+    }
+  }
+  if (lane == 0) labels[m] = best_k;
+}
+
+__global__ void paste_centroids_kernel(float* __restrict__ mel, int Dm, int T, const float* __restrict__ cc,
+                                       const float* __restrict__ center, const int64_t* __restrict__ labels,
+                                       const int32_t* __restrict__ pos, const int32_t* __restrict__ len,
+                                       const int32_t* __restrict__ off) {
+  const int b = blockIdx.y;
+  const int L = len[b], p0 = pos[b];
+  float* mb = mel + (int64_t)b * Dm * T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L * Dm; i += gridDim.x * blockDim.x) {
+    const int c = i / L, f = i - c * L;
+    if (p0 + f < 0 || p0 + f >= T) continue;
+    const int64_t lab = labels[off[b] + f];
+    mb[(int64_t)c * T + p0 + f] = cc[lab * Dm + c] + center[c];
+  }
+}
+
+// F.interpolate(bilinear, scale_factor=(1, 441/256), align_corners=False) along time:
+// src = max(0, (dst + 0.5) * (256/441) - 0.5); i0 = floor(src); i1 = min(i0+1, T-1).
+__global__ void extend_mel_kernel(const float* __restrict__ in, float* __restrict__ out, int Dm, int T, int Tm,
+                                  int frame_major) {
+  const int b = blockIdx.y;
+  const float scale = (float)(1.0 / (441.0 / 256.0));
+  const float* ib = in + (int64_t)b * Dm * T;
+  float* ob = out + (int64_t)b * Dm * Tm;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Dm * Tm; i += gridDim.x * blockDim.x) {
+    int c, t;
+    if (frame_major) { t = i / Dm; c = i - t * Dm; } else { c = i / Tm; t = i - c * Tm; }
+    float src = ((float)t + 0.5f) * scale - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    int i0 = (int)src;
+    i0 = min(i0, T - 1);
+    const int i1 = min(i0 + 1, T - 1);
+    const float w1 = src - (float)i0, w0 = 1.f - w1;
+    const float* row = ib + (int64_t)c * T;
+    ob[i] = w0 * row[i0] + w1 * row[i1];
+  }
+}
+
+// 32x32 smem-tiled transpose: in [B][R][Cc] -> out [B][Cc][R]
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* ib = in + (int64_t)b * R * Cc;
+  float* ob = out + (int64_t)b * R * Cc;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? ib[(int64_t)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) ob[(int64_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void embed_concat_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ zp,
+                                    const float* __restrict__ spk, const float* __restrict__ emb_c,
+                                    const float* __restrict__ emb_p, float* __restrict__ out, int T, int Tp, int E,
+                                    int Es) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  const int W = 2 * E + Es;
+  const int rep = T / Tp;  // _upsample repeats each pitch step T // Tp times (model.py:104)
+  const int64_t ci = code[(int64_t)b * T + t];
+  const int64_t pi = zp[(int64_t)b * Tp + min(t / rep, Tp - 1)];
+  float* o = out + ((int64_t)b * T + t) * W;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    float v;
+    if (i < E) v = emb_c[ci * E + i];
+    else if (i < 2 * E) v = emb_p[pi * E + (i - E)];
+    else v = spk[(int64_t)b * Es + (i - 2 * E)];
+    o[i] = v;
+  }
+}
+
+__global__ void pack_int16_kernel(const float* __restrict__ y, int16_t* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // numpy float32 -> int16 astype: C conversion through a wider int, truncation toward zero
+    out[i] = (int16_t)(int32_t)(y[i] * 32768.0f);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+inline unsigned ew_grid(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+}  // namespace
+
+extern "C" int sib_gather_frames_f32(const float* src, int batch, int t, int d, const int32_t* pos,
+                                     const int32_t* len, const int32_t* off, float* out, sib_stream_t stream) {
+  SIB_REQUIRE(src && pos && len && off && out && batch > 0 && batch <= 65535 && t > 0 && d > 0,
+              "sib_gather_frames_f32: bad argument");
+  gather_frames_kernel<<<dim3(8, batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, t, d, pos, len, off, out);
+  SIB_CHECK_LAUNCH("sib_gather_frames_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_cos_argmax_f32(const float* v, const float* cc, int m, int k, int d, int64_t* labels,
+                                  sib_stream_t stream) {
+  SIB_REQUIRE(v && cc && labels && m > 0 && k > 0 && d > 0, "sib_cos_argmax_f32: bad argument");
+  assign_kernel<0><<<sib::ceil_div(m, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(v, cc, m, k, d, labels);
+  SIB_CHECK_LAUNCH("sib_cos_argmax_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_l2_argmin_f32(const float* f, const float* mu, int m, int k, int d, int64_t* labels,
+                                 sib_stream_t stream) {
+  SIB_REQUIRE(f && mu && labels && m > 0 && k > 0 && d > 0, "sib_l2_argmin_f32: bad argument");
+  assign_kernel<1><<<sib::ceil_div(m, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(f, mu, m, k, d, labels);
+  SIB_CHECK_LAUNCH("sib_l2_argmin_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_paste_centroids_f32(float* mel, int batch, int d, int t, const float* cc, const float* center,
+                                       const int64_t* labels, const int32_t* pos, const int32_t* len,
+                                       const int32_t* off, sib_stream_t stream) {
+  SIB_REQUIRE(mel && cc && center && labels && pos && len && off && batch > 0 && batch <= 65535 && d > 0 && t > 0,
+              "sib_paste_centroids_f32: bad argument");
+  paste_centroids_kernel<<<dim3(8, batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(mel, d, t, cc, center, labels,
+                                                                                        pos, len, off);
+  SIB_CHECK_LAUNCH("sib_paste_centroids_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_extend_mel_f32(const float* in, float* out, int batch, int d, int t, int tm, int frame_major,
+                                  sib_stream_t stream) {
+  SIB_REQUIRE(in && out && batch > 0 && batch <= 65535 && d > 0 && t > 0 && tm > 0, "sib_extend_mel_f32: bad argument");
+  extend_mel_kernel<<<dim3(sib::ceil_div((int64_t)d * tm, 256), batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, out, d, t, tm, frame_major);
+  SIB_CHECK_LAUNCH("sib_extend_mel_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_transpose_f32(const float* in, float* out, int batch, int rows, int cols, sib_stream_t stream) {
+  SIB_REQUIRE(in && out && batch > 0 && batch <= 65535 && rows > 0 && cols > 0, "sib_transpose_f32: bad argument");
+  SIB_REQUIRE(sib::ceil_div(rows, 32) <= 65535, "sib_transpose_f32: rows too large");
+  dim3 grid(sib::ceil_div(cols, 32), sib::ceil_div(rows, 32), batch);
+  transpose_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(in, out, rows, cols);
+  SIB_CHECK_LAUNCH("sib_transpose_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_embed_concat_f32(const int64_t* code, const int64_t* zp, const float* spk, const float* emb_c,
+                                    const float* emb_p, float* out, int batch, int t, int t_p, int e, int e_spk,
+                                    sib_stream_t stream) {
+  SIB_REQUIRE(code && zp && spk && emb_c && emb_p && out && batch > 0 && batch <= 65535 && t > 0 && t_p > 0 && e > 0,
+              "sib_embed_concat_f32: bad argument");
+  SIB_REQUIRE(t >= t_p && (t - t_p * (t / t_p)) / (t / t_p) == 0,
+              "sib_embed_concat_f32: misaligned condition lengths t=%d t_p=%d (model.py:110-114)", t, t_p);
+  embed_concat_kernel<<<dim3(t, batch), 128, 0, static_cast<cudaStream_t>(stream)>>>(code, zp, spk, emb_c, emb_p, out,
+                                                                                     t, t_p, e, e_spk);
+  SIB_CHECK_LAUNCH("sib_embed_concat_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_pack_int16_f32(const float* y, int16_t* out, int64_t n, sib_stream_t stream) {
+  SIB_REQUIRE(y && out && n > 0, "sib_pack_int16_f32: bad argument");
+  pack_int16_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, out, n);
+  SIB_CHECK_LAUNCH("sib_pack_int16_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_cast_f32_to_bf16(const float* in, void* out, int64_t n, sib_stream_t stream) {
+  SIB_REQUIRE(in && out && n > 0, "sib_cast_f32_to_bf16: bad argument");
+  cast_f32_bf16_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, (__nv_bfloat16*)out, n);
+  SIB_CHECK_LAUNCH("sib_cast_f32_to_bf16");
+  return SIB_OK;
+}
+
+extern "C" int sib_cast_bf16_to_f32(const void* in, float* out, int64_t n, sib_stream_t stream) {
+  SIB_REQUIRE(in && out && n > 0, "sib_cast_bf16_to_f32: bad argument");
+  cast_bf16_f32_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)in, out, n);
+  SIB_CHECK_LAUNCH("sib_cast_bf16_to_f32");
+  return SIB_OK;
+}

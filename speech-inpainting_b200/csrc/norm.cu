@@ -1,0 +1,273 @@
+// Bandwidth-bound normalisation kernels of the HuBERT front: processor z-norm (a2), conv0 fused with
+// GroupNorm/GELU (a3), LayerNorm (a4, a8, a10).  Warp-shuffle reductions, vectorised row access.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row; the row lives in registers (C <= 32*MAXV) so x is read exactly once.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float* __restrict__ y, int64_t rows, int C, float eps,
+                                                        int post_act) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * C;
+  const float* rr = res ? res + row * C : nullptr;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    float t = 0.f;
+    if (c < C) {
+      t = xr[c];
+      if (rr) t += rr[c];
+    }
+    v[i] = t;
+    s += t;
+  }
+  const float mean = sib::warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    const float dlt = (c < C) ? v[i] - mean : 0.f;
+    q += dlt * dlt;
+  }
+  const float rstd = rsqrtf(sib::warp_sum(q) / C + eps);
+  float* yr = y + row * C;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      if (post_act == SIB_ACT_GELU) o = sib::gelu_erf(o);
+      yr[c] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ conv0
+// HuBERT conv0: Conv1d(1 -> C, k, stride) over the raw waveform (HF:154-175).  10 MACs per output, so
+// it is recomputed in both GroupNorm passes instead of materialising [B,C,N/5] twice.
+// CTA = (64-frame tile, batch); 256 threads; thread owns channels tid, tid+256, ...
+constexpr int C0_TILE = 64;
+constexpr int C0_MAXK = 16;
+
+template <int MODE>
+__global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ wave, int n, int64_t wave_bs,
+                                                    const float* __restrict__ w, const float* __restrict__ bias,
+                                                    int C, int K, int S, int T0, float* __restrict__ partial,
+                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    float* __restrict__ y) {
+  extern __shared__ float xs[];  // (C0_TILE-1)*S + K samples
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int t_begin = tile * C0_TILE;
+  const int nt = min(C0_TILE, T0 - t_begin);
+  const int span = (nt - 1) * S + K;
+  const float* wb = wave + (int64_t)b * wave_bs + (int64_t)t_begin * S;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) xs[i] = wb[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float wr[C0_MAXK];
+#pragma unroll
+    for (int j = 0; j < C0_MAXK; ++j) wr[j] = j < K ? w[c * K + j] : 0.f;
+    const float bs = bias ? bias[c] : 0.f;
+    float s = 0.f, q = 0.f;
+    float m = 0.f, r = 0.f, ga = 0.f, be = 0.f;
+    if (MODE == 1) {
+      m = mean[b * C + c]; r = rstd[b * C + c]; ga = gamma[c]; be = beta[c];
+    }
+    for (int t = 0; t < nt; ++t) {
+      float acc = bs;
+#pragma unroll
+      for (int j = 0; j < C0_MAXK; ++j)
+        if (j < K) acc = fmaf(wr[j], xs[t * S + j], acc);
+      if (MODE == 0) {
+        s += acc; q += acc * acc;
+      } else if (MODE == 1) {
+        y[((int64_t)b * T0 + t_begin + t) * C + c] = sib::gelu_erf((acc - m) * r * ga + be);
+      } else {
+        y[((int64_t)b * T0 + t_begin + t) * C + c] = acc;
+      }
+    }
+    if (MODE == 0) {
+      float* pp = partial + (((int64_t)b * gridDim.x + tile) * C + c) * 2;
+      pp[0] = s; pp[1] = q;
+    }
+  }
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int n_tiles, int C, int T0, float eps,
+                                   float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int t = 0; t < n_tiles; ++t) {
+    const float* pp = partial + (((int64_t)b * n_tiles + t) * C + c) * 2;
+    s += pp[0]; q += pp[1];
+  }
+  const double m = s / T0;
+  double var = q / T0 - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[b * C + c] = (float)m;
+  rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ------------------------------------------------------------------------------------------ z-norm
+// One CTA per utterance: mean, then centred sum of squares (two passes; the second hits L2), then apply.
+__global__ void __launch_bounds__(1024) znorm_kernel(const float* __restrict__ x, float* __restrict__ y, int n,
+                                                     const int32_t* __restrict__ lengths, float eps) {
+  __shared__ float red[32];
+  __shared__ float bc;
+  const int b = blockIdx.x;
+  const float* xb = x + (int64_t)b * n;
+  float* yb = y + (int64_t)b * n;
+  const int len = lengths ? min(max(lengths[b], 0), n) : n;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  auto block_sum = [&](float v) {
+    v = sib::warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      float t = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+      t = sib::warp_sum(t);
+      if (lane == 0) bc = t;
+    }
+    __syncthreads();
+    return bc;
+  };
+  float s = 0.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) s += xb[i];
+  const float mean = block_sum(s) / (float)max(len, 1);
+  float q = 0.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const float dlt = xb[i] - mean;
+    q += dlt * dlt;
+  }
+  const float rstd = rsqrtf(block_sum(q) / (float)max(len, 1) + eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) yb[i] = i < len ? (xb[i] - mean) * rstd : 0.f;
+}
+
+__global__ void zero_ranges_kernel(float* __restrict__ wave, int n, const int32_t* __restrict__ lo,
+                                   const int32_t* __restrict__ hi, float add_eps) {
+  const int b = blockIdx.y;
+  // numpy slice semantics: negative indices count from the end, then clamp to [0, n]
+  int l = lo[b], h = hi[b];
+  if (l < 0) l += n;
+  if (h < 0) h += n;
+  l = min(max(l, 0), n);
+  h = min(max(h, 0), n);
+  float* wb = wave + (int64_t)b * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i >= l && i < h)
+      wb[i] = 0.f;
+    else if (add_eps != 0.f)
+      wb[i] = wb[i] + add_eps;
+  }
+}
+
+__global__ void zero_padded_frames_kernel(float* __restrict__ h, const int32_t* __restrict__ key_len, int T, int C) {
+  const int b = blockIdx.y;
+  const int kl = key_len[b];
+  const int64_t total = (int64_t)(T - kl) * C;
+  if (total <= 0) return;
+  float* hb = h + ((int64_t)b * T + kl) * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    hb[i] = 0.f;
+}
+
+}  // namespace
+
+extern "C" int sib_layernorm_f32(const float* x, const float* residual, const float* gamma, const float* beta,
+                                 float* y, int64_t rows, int c, float eps, int post_act, sib_stream_t stream) {
+  SIB_REQUIRE(x && gamma && beta && y && rows > 0 && c > 0, "sib_layernorm_f32: bad argument");
+  SIB_REQUIRE(c <= 4096, "sib_layernorm_f32: c=%d > 4096 unsupported", c);
+  SIB_REQUIRE(post_act == SIB_ACT_NONE || post_act == SIB_ACT_GELU, "sib_layernorm_f32: unsupported post_act");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  if (c <= 256)
+    layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, residual, gamma, beta, y, rows, c, eps, post_act);
+  else if (c <= 512)
+    layernorm_kernel<16><<<grid, wpb * 32, 0, s>>>(x, residual, gamma, beta, y, rows, c, eps, post_act);
+  else if (c <= 1024)
+    layernorm_kernel<32><<<grid, wpb * 32, 0, s>>>(x, residual, gamma, beta, y, rows, c, eps, post_act);
+  else
+    layernorm_kernel<128><<<grid, wpb * 32, 0, s>>>(x, residual, gamma, beta, y, rows, c, eps, post_act);
+  SIB_CHECK_LAUNCH("sib_layernorm_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_conv0_num_tiles(int t0) { return (t0 + C0_TILE - 1) / C0_TILE; }
+
+extern "C" int sib_conv0_f32(int mode, const float* wave, int batch, int n_samples, int64_t wave_batch_stride,
+                             const float* w, const float* bias, int c, int k, int stride, int t0, float* partial,
+                             const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
+                             sib_stream_t stream) {
+  SIB_REQUIRE(wave && w && batch > 0 && c > 0 && t0 > 0, "sib_conv0_f32: bad argument");
+  SIB_REQUIRE(k > 0 && k <= C0_MAXK && stride > 0, "sib_conv0_f32: k=%d stride=%d unsupported", k, stride);
+  SIB_REQUIRE((int64_t)(t0 - 1) * stride + k <= n_samples, "sib_conv0_f32: t0=%d does not fit n_samples=%d", t0, n_samples);
+  SIB_REQUIRE(batch <= 65535, "sib_conv0_f32: batch too large");
+  dim3 grid(sib_conv0_num_tiles(t0), batch);
+  const size_t smem = ((size_t)(C0_TILE - 1) * stride + k) * sizeof(float);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (mode == 0) {
+    SIB_REQUIRE(partial, "sib_conv0_f32: mode 0 needs partial");
+    conv0_kernel<0><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0, partial,
+                                            nullptr, nullptr, nullptr, nullptr, nullptr);
+  } else if (mode == 1) {
+    SIB_REQUIRE(mean && rstd && gamma && beta && y, "sib_conv0_f32: mode 1 needs mean/rstd/gamma/beta/y");
+    conv0_kernel<1><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0, nullptr,
+                                            mean, rstd, gamma, beta, y);
+  } else if (mode == 2) {
+    SIB_REQUIRE(y, "sib_conv0_f32: mode 2 needs y");
+    conv0_kernel<2><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0, nullptr,
+                                            nullptr, nullptr, nullptr, nullptr, y);
+  } else {
+    SIB_REQUIRE(false, "sib_conv0_f32: unknown mode %d", mode);
+  }
+  SIB_CHECK_LAUNCH("sib_conv0_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_gn_finalize_f32(const float* partial, int batch, int n_tiles, int c, int t0, float eps,
+                                   float* mean, float* rstd, sib_stream_t stream) {
+  SIB_REQUIRE(partial && mean && rstd && batch > 0 && n_tiles > 0 && c > 0 && t0 > 0, "sib_gn_finalize_f32: bad argument");
+  dim3 grid(sib::ceil_div(c, 128), batch);
+  gn_finalize_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(partial, n_tiles, c, t0, eps, mean, rstd);
+  SIB_CHECK_LAUNCH("sib_gn_finalize_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_znorm_f32(const float* x, float* y, int batch, int n, const int32_t* lengths, float eps,
+                             sib_stream_t stream) {
+  SIB_REQUIRE(x && y && batch > 0 && n > 0, "sib_znorm_f32: bad argument");
+  znorm_kernel<<<batch, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, lengths, eps);
+  SIB_CHECK_LAUNCH("sib_znorm_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_zero_ranges_f32(float* wave, int batch, int n, const int32_t* lo, const int32_t* hi,
+                                   float add_eps, sib_stream_t stream) {
+  SIB_REQUIRE(wave && lo && hi && batch > 0 && n > 0 && batch <= 65535, "sib_zero_ranges_f32: bad argument");
+  dim3 grid(min(sib::ceil_div(n, 256), 64), batch);
+  zero_ranges_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(wave, n, lo, hi, add_eps);
+  SIB_CHECK_LAUNCH("sib_zero_ranges_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_zero_padded_frames_f32(float* h, const int32_t* key_len, int batch, int t, int c,
+                                          sib_stream_t stream) {
+  SIB_REQUIRE(h && key_len && batch > 0 && t > 0 && c > 0 && batch <= 65535, "sib_zero_padded_frames_f32: bad argument");
+  dim3 grid(32, batch);
+  zero_padded_frames_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h, key_len, t, c);
+  SIB_CHECK_LAUNCH("sib_zero_padded_frames_f32");
+  return SIB_OK;
+}

@@ -1,0 +1,262 @@
+"""HiFi-GAN generators on the B200 kernels, behind the reference's module surface.
+
+Drop-in for:
+  * `Generator(h).forward(x[B, in_dim, Tm]) -> [B, 1, Tm*prod(rates)]`   I_ea/hifi_gan/models.py:76-132,
+                                                                          I_da/src/models.py:156-233
+  * `CodeGenerator(h).forward(code=, f0=, emb=, spkr=)`                  I_da/src/model.py:42-189
+`load_state_dict` takes the reference checkpoints (`ckpt['generator']`) with weight-norm tensors
+(`weight_g/weight_v`) or after `remove_weight_norm()` (`weight`).  Weight-norm folding, the poly-phase
+re-layout of ConvTranspose1d and the transposition into kernel layouts happen once, on first use.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+from .hubert import _StateHolder
+from .ops import ACT_NONE, ACT_TANH, Plan, SibError
+
+LRELU_SLOPE = 0.1  # models.py:9
+
+
+def get_padding(kernel_size: int, dilation: int = 1) -> int:
+    """I_ea/hifi_gan/utils.py:47-48."""
+    return int((kernel_size * dilation - dilation) / 2)
+
+
+class AttrDict(dict):
+    """I_ea/hifi_gan/env.py:5-8."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.__dict__ = self
+
+
+def _hget(h, name, default=None):
+    if isinstance(h, dict):
+        return h.get(name, default)
+    return getattr(h, name, default)
+
+
+class Generator(_StateHolder):
+    def __init__(self, h, precision: str = "fp32"):
+        super().__init__()
+        self.h = h
+        self.precision = precision
+        self.upsample_rates = list(_hget(h, "upsample_rates"))
+        self.upsample_kernel_sizes = list(_hget(h, "upsample_kernel_sizes"))
+        self.c0 = int(_hget(h, "upsample_initial_channel"))
+        self.rb_kernels = list(_hget(h, "resblock_kernel_sizes"))
+        self.rb_dilations = [list(d) for d in _hget(h, "resblock_dilation_sizes")]
+        self.resblock = str(_hget(h, "resblock", "1"))
+        # I_ea hard-codes 80 mel bins (models.py:86); I_da reads model_in_dim (src/models.py:171)
+        self.in_dim = int(_hget(h, "model_in_dim", 80) or 80)
+        self.num_kernels = len(self.rb_kernels)
+        self.num_upsamples = len(self.upsample_rates)
+        self.total_upsample = math.prod(self.upsample_rates)
+        self._weight_norm_removed = False
+        self._plans = {}
+        self.use_cuda_graph = False
+
+    # ---- state
+    def _conv_names(self):
+        names = ["conv_pre"] + [f"ups.{i}" for i in range(self.num_upsamples)]
+        for i in range(self.num_upsamples):
+            for j in range(self.num_kernels):
+                n = i * self.num_kernels + j
+                if self.resblock == "1":
+                    for m in range(len(self.rb_dilations[j])):
+                        names += [f"resblocks.{n}.convs1.{m}", f"resblocks.{n}.convs2.{m}"]
+                else:
+                    names += [f"resblocks.{n}.convs.{m}" for m in range(len(self.rb_dilations[j]))]
+        return names + ["conv_post"]
+
+    def _extra_keys(self):
+        return []
+
+    def _expected_keys(self):
+        keys = []
+        for n in self._conv_names():
+            keys += [n + ".bias", n + ".weight_g", n + ".weight_v"]
+        return keys + self._extra_keys()
+
+    def load_state_dict(self, sd, strict: bool = True):
+        folded = {k for k in sd if k.endswith(".weight") and not k.startswith("emb_")}
+        if folded:  # checkpoint saved after remove_weight_norm()
+            exp = {n + s for n in self._conv_names() for s in (".bias", ".weight")} | set(self._extra_keys())
+            if strict and set(sd.keys()) != exp:
+                raise RuntimeError(f"Error(s) in loading state_dict: missing {sorted(exp - set(sd))[:8]} "
+                                   f"unexpected {sorted(set(sd) - exp)[:8]}")
+            self._sd = {k: v.detach().to(self._device, torch.float32).contiguous() for k, v in sd.items()}
+            self._packed = None
+            return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+        return super().load_state_dict(sd, strict)
+
+    def remove_weight_norm(self):
+        """models.py:125-132.  Folding happens at pack time; this only records the call."""
+        self._weight_norm_removed = True
+
+    def _weight(self, name):
+        """weight = g * v / ||v|| with the norm over all dims but 0 (torch weight_norm dim=0)."""
+        if name + ".weight" in self._sd:
+            return self._sd[name + ".weight"]
+        g, v = self._sd[name + ".weight_g"], self._sd[name + ".weight_v"]
+        return g * v / v.pow(2).sum(dim=(1, 2), keepdim=True).sqrt()
+
+    def _pack(self):
+        if self._packed is not None:
+            return self._packed
+        self._require_cuda()
+        P = {}
+        P["conv_pre.w"] = ops.pack_conv_weight(self._weight("conv_pre"))
+        for i, (u, k) in enumerate(zip(self.upsample_rates, self.upsample_kernel_sizes)):
+            w, b, offs = ops.pack_conv_transpose(self._weight(f"ups.{i}"), self._sd[f"ups.{i}.bias"], u, (k - u) // 2)
+            P[f"ups.{i}.w"], P[f"ups.{i}.b"], P[f"ups.{i}.taps"] = w, b, offs
+        for n in self._conv_names():
+            if n.startswith("resblocks."):
+                P[n + ".w"] = ops.pack_conv_weight(self._weight(n))
+        wp = self._weight("conv_post")  # [1, C, 7] -> [k][C]
+        P["conv_post.w"] = wp[0].t().contiguous()
+        self._packed = P
+        self._plans = {}
+        return P
+
+    # ---- plan
+    def _build_plan(self, B: int, Tm: int, frame_major_in: bool):
+        P, dev = self._pack(), self._device
+        f32 = dict(device=dev, dtype=torch.float32)
+        io = SimpleNamespace()
+        io.x_cf = None if frame_major_in else torch.empty(B, self.in_dim, Tm, **f32)
+        io.x = torch.empty(B, Tm, self.in_dim, **f32)
+        chans = [self.c0 // (2 ** (i + 1)) for i in range(self.num_upsamples)]
+        lens, L = [], Tm
+        for u in self.upsample_rates:
+            L *= u
+            lens.append(L)
+        big = max(l * c for l, c in zip(lens, chans))
+        pool = [torch.empty(B * big, **f32) for _ in range(6)]
+
+        def view(i, L_, C_):
+            return pool[i][: B * L_ * C_].view(B, L_, C_)
+
+        plan = Plan()
+        with plan.record():
+            if not frame_major_in:
+                ops.transpose(io.x_cf, io.x)  # [B,C,T] -> [B,T,C]
+            cur = torch.empty(B, Tm, self.c0, **f32)
+            ops.conv1d(io.x, P["conv_pre.w"], self._sd["conv_pre.bias"], cur, ops.conv_taps(7, 1, 3))  # models.py:108
+            t_in = Tm
+            for i, u in enumerate(self.upsample_rates):
+                C_, L_ = chans[i], lens[i]
+                # xs alternates between two slots so that the next stage can read it while writing its own
+                up, xs = view(0, L_, C_), view(1 if i % 2 == 0 else 5, L_, C_)
+                # lrelu(0.1) -> ConvTranspose1d as poly-phase conv: y[B, t_in, u*C] == [B, t_in*u, C]  (models.py:110-111)
+                ops.conv1d(cur, P[f"ups.{i}.w"], P[f"ups.{i}.b"], up.view(B, t_in, u * C_), P[f"ups.{i}.taps"],
+                           pre_slope=LRELU_SLOPE)
+                for j, (rk, dils) in enumerate(zip(self.rb_kernels, self.rb_dilations)):
+                    n = i * self.num_kernels + j
+                    last_j = j == self.num_kernels - 1
+                    xcur = up
+                    for m, dl in enumerate(dils):
+                        last_m = m == len(dils) - 1
+                        # MRF sum / num_kernels folded into the last residual epilogue of each block (models.py:113-118)
+                        dst = xs if last_m else view(2 + (m & 1), L_, C_)
+                        kw = dict(accumulate=last_m and j > 0, out_scale=(1.0 / self.num_kernels) if (last_m and last_j) else 1.0)
+                        if self.resblock == "1":  # models.py:36-43
+                            t1 = view(4, L_, C_)
+                            ops.conv1d(xcur, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
+                                       t1, ops.conv_taps(rk, dl, get_padding(rk, dl)), pre_slope=LRELU_SLOPE)
+                            ops.conv1d(t1, P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
+                                       dst, ops.conv_taps(rk, 1, get_padding(rk, 1)), pre_slope=LRELU_SLOPE,
+                                       residual=xcur, **kw)
+                        else:  # models.py:66-71
+                            ops.conv1d(xcur, P[f"resblocks.{n}.convs.{m}.w"], self._sd[f"resblocks.{n}.convs.{m}.bias"],
+                                       dst, ops.conv_taps(rk, dl, get_padding(rk, dl)), pre_slope=LRELU_SLOPE,
+                                       residual=xcur, **kw)
+                        xcur = dst
+                cur = xs
+                t_in = L_
+            io.y = torch.empty(B, 1, lens[-1], **f32)
+            # lrelu(default 0.01) -> conv_post -> tanh (models.py:119-121)
+            ops.conv1d_cout1(cur, P["conv_post.w"], self._sd["conv_post.bias"], io.y.view(B, lens[-1]), 7, 3, 0.01, ACT_TANH)
+        io.plan = plan
+        if self.use_cuda_graph:
+            plan.capture()
+        return io
+
+    def _run(self, x, frame_major_in=False):
+        self._require_cuda()
+        if x.dim() != 3:
+            raise SibError(f"Generator input must be 3-D, got {tuple(x.shape)}")
+        if frame_major_in:
+            B, Tm, Cin = x.shape
+        else:
+            B, Cin, Tm = x.shape
+        if Cin != self.in_dim:
+            raise RuntimeError(f"expected input with {self.in_dim} channels, got {Cin}")  # torch conv1d raises RuntimeError too
+        key = (B, Tm, frame_major_in)
+        self._pack()
+        io = self._plans.get(key)
+        if io is None:
+            io = self._plans[key] = self._build_plan(B, Tm, frame_major_in)
+        (io.x if frame_major_in else io.x_cf).copy_(x.to(self._device, torch.float32), non_blocking=True)
+        io.plan.run()
+        return io
+
+    def forward(self, x):
+        """x [B, in_dim, Tm] (channels-first, as the reference) -> [B, 1, Tm*prod(rates)]."""
+        return self._run(x).y.clone()
+
+    def forward_frame_major(self, x):
+        """x [B, Tm, in_dim] frame-major (what extend_mel / embed_concat kernels emit) -> same output."""
+        return self._run(x, frame_major_in=True).y.clone()
+
+    __call__ = forward
+
+
+class CodeGenerator(Generator):
+    """I_da/src/model.py:42-189 for the shipped config (no code VQ; f0_stats and multispkr set).
+
+    The frozen f0 VQ-VAE encoder (model.py:148-153, Jukebox convs, `.cuda()` hard-coded in vq.py:22) is
+    SURVEY 8f "next" row 2: this class takes its output `z_p` (bin indices [B, T/4]) through the extra
+    keyword `f0_code`; passing raw `f0` without `f0_code` raises."""
+
+    def __init__(self, h, precision: str = "fp32"):
+        super().__init__(h, precision)
+        self.num_embeddings = int(_hget(h, "num_embeddings"))
+        self.embedding_dim = int(_hget(h, "embedding_dim"))
+        fq = _hget(h, "f0_quantizer") or {}
+        self.f0_bins = int(fq.get("f0_vq_params", {}).get("l_bins", 20)) if isinstance(fq, dict) else 20
+
+    def _extra_keys(self):
+        return ["emb_c.weight", "emb_p.weight", "emb_s.weight"]
+
+    def load_state_dict(self, sd, strict: bool = True):
+        # the reference checkpoint also carries the frozen fo_vqvae.*; it is not on this path
+        sd = {k: v for k, v in sd.items() if not k.startswith("fo_vqvae.")}
+        return super().load_state_dict(sd, strict)
+
+    def forward(self, **kwargs):
+        self._require_cuda()
+        code = kwargs["code"]
+        if "f0_code" not in kwargs:
+            raise SibError("CodeGenerator needs f0_code= (quantised f0 bins [B, T/4]); the f0 VQ-VAE encoder is "
+                           "outside the hot path (SURVEY 8f row 2)")
+        zp, emb = kwargs["f0_code"], kwargs["emb"]
+        dev = self._device
+        code = code.to(dev, torch.int64).contiguous()
+        zp = zp.to(dev, torch.int64).contiguous()
+        emb = emb.to(dev, torch.float32).contiguous()
+        B, T = code.shape
+        E = self.embedding_dim
+        Tmax = max(T, zp.shape[1])
+        if Tmax != T:
+            raise SibError("pitch series longer than the code series is not produced by the reference pipeline")
+        x = torch.empty(B, T, 2 * E + emb.shape[1], device=dev, dtype=torch.float32)
+        ops.embed_concat(code, zp, emb, self._sd["emb_c.weight"], self._sd["emb_p.weight"], x)
+        return self.forward_frame_major(x)
+
+    __call__ = forward

@@ -1,0 +1,394 @@
+"""HuBERT encoder on the B200 kernels, behind the reference's module surface.
+
+Drop-in for:
+  * HF `HubertModel.forward(input_values, attention_mask) -> .last_hidden_state`  HF:889-958
+  * `CustomModel.forward` (HubertModel -> LayerNorm -> Linear(H,80))               I_ea/model.py:80-89
+  * fairseq-style `extract_features(source, padding_mask, mask, output_layer)`       I_da/src/hubert_feature_reader.py:60-65
+Checkpoint key names are the reference's (HF state dict, old or new weight-norm names).
+All arithmetic runs in libsib_b200.so; there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+from .ops import ACT_GELU, ACT_NONE, Plan, SibError
+
+
+@dataclass
+class HubertConfig:
+    """The HF `HubertConfig` fields that change the arithmetic (same names, same defaults)."""
+
+    hidden_size: int = 768
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 12
+    intermediate_size: int = 3072
+    feat_extract_norm: str = "group"
+    conv_bias: bool = False
+    do_stable_layer_norm: bool = False
+    conv_dim: tuple = (512,) * 7
+    conv_kernel: tuple = (10, 3, 3, 3, 3, 2, 2)
+    conv_stride: tuple = (5, 2, 2, 2, 2, 2, 2)
+    num_conv_pos_embeddings: int = 128
+    num_conv_pos_embedding_groups: int = 16
+    layer_norm_eps: float = 1e-5
+    # SpecAugment knobs the reference zeroes (I_ea/model.py:58-63); eval-only path ignores them
+    mask_time_prob: float = 0.0
+    mask_feature_prob: float = 0.0
+    mask_feature_length: int = 0
+    mask_feature_min_masks: int = 0
+    mask_time_length: int = 0
+    mask_time_min_masks: int = 0
+
+    @staticmethod
+    def base():
+        return HubertConfig()
+
+    @staticmethod
+    def large():
+        return HubertConfig(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+                            intermediate_size=4096, feat_extract_norm="layer", conv_bias=True,
+                            do_stable_layer_norm=True)
+
+    @classmethod
+    def from_any(cls, cfg):
+        """Accepts this class, an HF HubertConfig or any object/dict with the same attribute names."""
+        if isinstance(cls, type) and isinstance(cfg, cls):
+            return cfg
+        get = (lambda k, d: cfg.get(k, d)) if isinstance(cfg, dict) else (lambda k, d: getattr(cfg, k, d))
+        base = cls()
+        kw = {f: get(f, getattr(base, f)) for f in base.__dataclass_fields__}
+        for f in ("conv_dim", "conv_kernel", "conv_stride"):
+            kw[f] = tuple(kw[f])
+        return cls(**kw)
+
+    def feat_extract_output_length(self, n: int) -> int:
+        """HF:675-688."""
+        for k, s in zip(self.conv_kernel, self.conv_stride):
+            n = (n - k) // s + 1
+        return n
+
+
+def expected_hubert_keys(cfg: HubertConfig, prefix: str = "", new_wn_names: bool = True):
+    keys = []
+    for i in range(len(cfg.conv_dim)):
+        b = f"feature_extractor.conv_layers.{i}."
+        keys.append(b + "conv.weight")
+        if cfg.conv_bias:
+            keys.append(b + "conv.bias")
+        if cfg.feat_extract_norm == "layer" or i == 0:
+            keys += [b + "layer_norm.weight", b + "layer_norm.bias"]
+    keys += ["feature_projection.layer_norm.weight", "feature_projection.layer_norm.bias",
+             "feature_projection.projection.weight", "feature_projection.projection.bias",
+             "encoder.pos_conv_embed.conv.bias", "encoder.layer_norm.weight", "encoder.layer_norm.bias"]
+    if new_wn_names:
+        keys += ["encoder.pos_conv_embed.conv.parametrizations.weight.original0",
+                 "encoder.pos_conv_embed.conv.parametrizations.weight.original1"]
+    else:
+        keys += ["encoder.pos_conv_embed.conv.weight_g", "encoder.pos_conv_embed.conv.weight_v"]
+    for l in range(cfg.num_hidden_layers):
+        b = f"encoder.layers.{l}."
+        for n in ("attention.q_proj", "attention.k_proj", "attention.v_proj", "attention.out_proj", "layer_norm",
+                  "feed_forward.intermediate_dense", "feed_forward.output_dense", "final_layer_norm"):
+            keys += [b + n + ".weight", b + n + ".bias"]
+    keys.append("masked_spec_embed")
+    return [prefix + k for k in keys]
+
+
+class _StateHolder:
+    """Minimal nn.Module-like surface: load_state_dict / state_dict / parameters / to / eval."""
+
+    def __init__(self):
+        self._sd = {}
+        self._device = torch.device("cpu")
+        self._packed = None
+        self.training = False
+
+    def load_state_dict(self, sd, strict: bool = True):
+        exp = set(self._expected_keys())
+        got = set(sd.keys())
+        alt = {k.replace("parametrizations.weight.original0", "weight_g").replace(
+            "parametrizations.weight.original1", "weight_v") for k in exp}
+        if strict and got != exp and got != alt:
+            missing, extra = sorted((exp - got) & (alt - got)), sorted(got - exp - alt)
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:8]} unexpected {extra[:8]}")
+        self._sd = {k: v.detach().to(self._device, torch.float32).contiguous() for k, v in sd.items()}
+        self._packed = None
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    def state_dict(self):
+        return dict(self._sd)
+
+    def parameters(self):
+        return iter(self._sd.values())
+
+    def to(self, device=None, *a, **k):
+        if device is not None and not isinstance(device, torch.dtype):
+            self._device = torch.device(device)
+            self._sd = {k_: v.to(self._device) for k_, v in self._sd.items()}
+            self._packed = None
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise SibError("this is an inference-only path (SURVEY 2: training is out of scope)")
+        return self
+
+    def _require_cuda(self):
+        if self._device.type != "cuda":
+            raise SibError("module must be moved to a CUDA device before forward (no CPU fallback)")
+
+
+class HubertModel(_StateHolder):
+    """HF `HubertModel` surface over the sm_100a kernels (eval mode, SpecAugment off)."""
+
+    def __init__(self, config=None, precision: str = "fp32", key_prefix: str = ""):
+        super().__init__()
+        self.config = HubertConfig.from_any(config) if config is not None else HubertConfig()
+        self.precision = precision
+        self._prefix = key_prefix
+        self._plans = {}
+        self.use_cuda_graph = False
+
+    # ---- state
+    def _expected_keys(self):
+        return expected_hubert_keys(self.config, "")
+
+    def _w(self, name):
+        return self._sd[name]
+
+    def _pos_conv_weight(self):
+        """weight_norm(dim=2) folded: w = g * v / ||v||_(0,1)  (HF:59-78)."""
+        b = "encoder.pos_conv_embed.conv."
+        if b + "weight" in self._sd:
+            return self._sd[b + "weight"]
+        if b + "weight_g" in self._sd:
+            g, v = self._sd[b + "weight_g"], self._sd[b + "weight_v"]
+        else:
+            g, v = self._sd[b + "parametrizations.weight.original0"], self._sd[b + "parametrizations.weight.original1"]
+        return g * v / v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()
+
+    def _pack(self):
+        """One-time weight packing into kernel layouts (fold weight-norm, transpose, fuse QKV)."""
+        if self._packed is not None:
+            return self._packed
+        self._require_cuda()
+        cfg, P = self.config, {}
+        w0 = self._w("feature_extractor.conv_layers.0.conv.weight")
+        P["conv0.w"] = w0.reshape(w0.shape[0], -1).contiguous()
+        for i in range(len(cfg.conv_dim)):
+            b = f"feature_extractor.conv_layers.{i}."
+            if i > 0:
+                P[f"conv{i}.w"] = ops.pack_conv_weight(self._w(b + "conv.weight"))
+            P[f"conv{i}.b"] = self._sd.get(b + "conv.bias")
+            if b + "layer_norm.weight" in self._sd:
+                P[f"conv{i}.g"], P[f"conv{i}.beta"] = self._w(b + "layer_norm.weight"), self._w(b + "layer_norm.bias")
+        P["proj.w"] = ops.pack_linear_weight(self._w("feature_projection.projection.weight"))
+        P["pos.w"] = ops.pack_conv_weight(self._pos_conv_weight(), cfg.num_conv_pos_embedding_groups)
+        for l in range(cfg.num_hidden_layers):
+            b = f"encoder.layers.{l}.attention."
+            qkv_w = torch.cat([self._w(b + "q_proj.weight"), self._w(b + "k_proj.weight"), self._w(b + "v_proj.weight")], 0)
+            P[f"l{l}.qkv.w"] = ops.pack_linear_weight(qkv_w)
+            P[f"l{l}.qkv.b"] = torch.cat([self._w(b + "q_proj.bias"), self._w(b + "k_proj.bias"), self._w(b + "v_proj.bias")]).contiguous()
+            P[f"l{l}.o.w"] = ops.pack_linear_weight(self._w(b + "out_proj.weight"))
+            f = f"encoder.layers.{l}.feed_forward."
+            P[f"l{l}.ff1.w"] = ops.pack_linear_weight(self._w(f + "intermediate_dense.weight"))
+            P[f"l{l}.ff2.w"] = ops.pack_linear_weight(self._w(f + "output_dense.weight"))
+        self._packed = P
+        self._plans = {}
+        return P
+
+    # ---- plan
+    def _build_plan(self, B: int, N: int, padded: bool, n_layers: int):
+        cfg, P, dev = self.config, self._pack(), self._device
+        f32 = dict(device=dev, dtype=torch.float32)
+        lens = [N]
+        for k, s in zip(cfg.conv_kernel, cfg.conv_stride):
+            lens.append((lens[-1] - k) // s + 1)
+        if lens[-1] < 1:
+            raise SibError(f"input of {N} samples is shorter than the receptive field of the feature encoder")
+        T, H, C = lens[-1], cfg.hidden_size, cfg.conv_dim[0]
+        eps = cfg.layer_norm_eps
+        io = SimpleNamespace(wave=torch.empty(B, N, **f32), key_len=torch.empty(B, dtype=torch.int32, device=dev) if padded else None)
+        plan = Plan()
+        with plan.record():
+            # ---- feature encoder (HF:203-213)
+            t0 = lens[1]
+            a = torch.empty(B, t0, C, **f32)
+            k0, s0 = cfg.conv_kernel[0], cfg.conv_stride[0]
+            if cfg.feat_extract_norm == "group":
+                nt = ops.conv0_num_tiles(t0)
+                part = torch.empty(B, nt, C, 2, **f32)
+                mean, rstd = torch.empty(B, C, **f32), torch.empty(B, C, **f32)
+                ops.conv0(0, io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, partial=part)
+                ops.gn_finalize(part, B, nt, C, t0, 1e-5, mean, rstd)
+                ops.conv0(1, io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, mean=mean, rstd=rstd,
+                          gamma=P["conv0.g"], beta=P["conv0.beta"], y=a)
+            else:
+                ops.conv0(2, io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, y=a)
+                ops.layernorm(a, P["conv0.g"], P["conv0.beta"], a, 1e-5, post_act=ACT_GELU)
+            for i in range(1, len(cfg.conv_dim)):
+                y = torch.empty(B, lens[i + 1], cfg.conv_dim[i], **f32)
+                k, s = cfg.conv_kernel[i], cfg.conv_stride[i]
+                if cfg.feat_extract_norm == "layer":
+                    ops.conv1d(a, P[f"conv{i}.w"], P[f"conv{i}.b"], y, list(range(k)), stride=s)
+                    ops.layernorm(y, P[f"conv{i}.g"], P[f"conv{i}.beta"], y, 1e-5, post_act=ACT_GELU)
+                else:
+                    ops.conv1d(a, P[f"conv{i}.w"], P[f"conv{i}.b"], y, list(range(k)), stride=s, post_act=ACT_GELU)
+                a = y
+            # ---- feature projection (HF:225-231)
+            ln = torch.empty(B, T, cfg.conv_dim[-1], **f32)
+            ops.layernorm(a, self._w("feature_projection.layer_norm.weight"), self._w("feature_projection.layer_norm.bias"), ln, eps)
+            h = torch.empty(B, T, H, **f32)
+            ops.linear(ln.view(B * T, -1), P["proj.w"], self._w("feature_projection.projection.bias"), h.view(B * T, H))
+            if padded:
+                ops.zero_padded_frames(h, io.key_len)  # HF:429-432
+            # ---- positional conv embedding (HF:83-92, 440-442)
+            kp = cfg.num_conv_pos_embeddings
+            taps = [j - kp // 2 for j in range(kp)]  # pad k//2; the dropped last step is simply not computed
+            h2 = torch.empty(B, T, H, **f32)
+            tmp = torch.empty(B, T, H, **f32)
+            if cfg.do_stable_layer_norm:
+                ops.conv1d(h, P["pos.w"], self._w("encoder.pos_conv_embed.conv.bias"), h2, taps,
+                           groups=cfg.num_conv_pos_embedding_groups, post_act=ACT_GELU, residual=h, res_after_act=True)
+            else:
+                ops.conv1d(h, P["pos.w"], self._w("encoder.pos_conv_embed.conv.bias"), tmp, taps,
+                           groups=cfg.num_conv_pos_embedding_groups, post_act=ACT_GELU)
+                ops.layernorm(tmp, self._w("encoder.layer_norm.weight"), self._w("encoder.layer_norm.bias"), h2, eps, residual=h)
+            h = h2
+            # ---- transformer layers
+            qkv = torch.empty(B, T, 3 * H, **f32)
+            att = torch.empty(B, T, H, **f32)
+            ff = torch.empty(B, T, cfg.intermediate_size, **f32)
+            nrm = torch.empty(B, T, H, **f32)
+            M = B * T
+            for l in range(n_layers):
+                b = f"encoder.layers.{l}."
+                ob, f2b = self._w(b + "attention.out_proj.bias"), self._w(b + "feed_forward.output_dense.bias")
+                f1b = self._w(b + "feed_forward.intermediate_dense.bias")
+                ln1 = (self._w(b + "layer_norm.weight"), self._w(b + "layer_norm.bias"))
+                ln2 = (self._w(b + "final_layer_norm.weight"), self._w(b + "final_layer_norm.bias"))
+                if cfg.do_stable_layer_norm:  # HF:525-548
+                    ops.layernorm(h, ln1[0], ln1[1], nrm, eps)
+                    ops.linear(nrm.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
+                    ops.attention(qkv, io.key_len, att, cfg.num_attention_heads)
+                    ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, h.view(M, H), residual=h.view(M, H))
+                    ops.layernorm(h, ln2[0], ln2[1], nrm, eps)
+                    ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
+                    ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, h.view(M, H), residual=h.view(M, H))
+                else:  # HF:388-405
+                    ops.linear(h.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
+                    ops.attention(qkv, io.key_len, att, cfg.num_attention_heads)
+                    ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, tmp.view(M, H))
+                    ops.layernorm(tmp, ln1[0], ln1[1], nrm, eps, residual=h)
+                    ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
+                    ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, tmp.view(M, H))
+                    ops.layernorm(tmp, ln2[0], ln2[1], h, eps, residual=nrm)
+            if cfg.do_stable_layer_norm and n_layers == cfg.num_hidden_layers:
+                ops.layernorm(h, self._w("encoder.layer_norm.weight"), self._w("encoder.layer_norm.bias"), h, eps)  # HF:613
+        io.out = h
+        io.T = T
+        io.plan = plan
+        if self.use_cuda_graph:
+            plan.capture()
+        return io
+
+    def _key_len(self, attention_mask, N):
+        """HF:690-700: valid frames per utterance from the sample-level attention mask."""
+        lens = attention_mask.sum(-1).to(torch.int64)
+        out = lens.clone()
+        for k, s in zip(self.config.conv_kernel, self.config.conv_stride):
+            out = torch.div(out - k, s, rounding_mode="floor") + 1
+        return out.to(torch.int32)
+
+    def _run(self, input_values, attention_mask=None, n_layers=None):
+        self._require_cuda()
+        if input_values.dim() != 2:
+            raise SibError(f"input_values must be [batch, samples], got {tuple(input_values.shape)}")
+        B, N = input_values.shape
+        L = self.config.num_hidden_layers if n_layers is None else n_layers
+        padded = attention_mask is not None and not bool(attention_mask.to(torch.bool).all())
+        key = (B, N, padded, L)
+        self._pack()
+        io = self._plans.get(key)
+        if io is None:
+            io = self._plans[key] = self._build_plan(B, N, padded, L)
+        io.wave.copy_(input_values.to(self._device, torch.float32), non_blocking=True)
+        if padded:
+            io.key_len.copy_(self._key_len(attention_mask.to(self._device), N))
+        io.plan.run()
+        return io
+
+    # ---- reference surface
+    def forward(self, input_values, attention_mask=None, **_unused):
+        io = self._run(input_values, attention_mask)
+        return SimpleNamespace(last_hidden_state=io.out.clone())
+
+    __call__ = forward
+
+    def extract_features(self, source, padding_mask=None, mask=False, output_layer=None):
+        """fairseq HuBERT surface used by I_da (hubert_feature_reader.py:60-65); output_layer is 1-based,
+        None / -1 / 0 => all layers.  fairseq-vs-HF equivalence: parity unpinned (fairseq absent)."""
+        if mask:
+            raise SibError("mask=True (SpecAugment) is a training feature; the reference calls mask=False")
+        n_layers = None if (output_layer is None or output_layer <= 0) else min(output_layer, self.config.num_hidden_layers)
+        am = None if padding_mask is None else (~padding_mask.to(torch.bool)).to(torch.int64)
+        io = self._run(source, am, n_layers)
+        return io.out.clone(), padding_mask
+
+
+class CustomModel(_StateHolder):
+    """I_ea/model.py:22-89 `CustomModel`: HubertModel + final_layers = LayerNorm(H) -> Linear(H, codebook_dim).
+    Constructed from a config instead of `from_pretrained` (no network on the path); state-dict keys are
+    `base_model.*` and `final_layers.{0,1}.*`."""
+
+    def __init__(self, codebook_dim=80, type="large", load_pretrained=False, train_encoder=False, loss_function="",
+                 config=None, precision: str = "fp32"):
+        super().__init__()
+        if config is None:
+            config = HubertConfig.base() if type == "base" else HubertConfig.large()
+        self.base_model = HubertModel(config, precision=precision)
+        self.last_hidden_dim = self.base_model.config.hidden_size
+        self.codebook_dim = 100 if loss_function == "softmax" else codebook_dim
+        self._head = None
+
+    def _expected_keys(self):
+        return (expected_hubert_keys(self.base_model.config, "base_model.") +
+                ["final_layers.0.weight", "final_layers.0.bias", "final_layers.1.weight", "final_layers.1.bias"])
+
+    def load_state_dict(self, sd, strict: bool = True):
+        r = super().load_state_dict(sd, strict)
+        self.base_model._device = self._device
+        self.base_model.load_state_dict({k[len("base_model."):]: v for k, v in self._sd.items() if k.startswith("base_model.")}, strict)
+        self._head = None
+        return r
+
+    def to(self, device=None, *a, **k):
+        super().to(device, *a, **k)
+        self.base_model.to(device)
+        self._head = None
+        return self
+
+    def forward(self, input_values, attention_mask=None):
+        io = self.base_model._run(input_values, attention_mask)
+        h = io.out
+        B, T, H = h.shape
+        if self._head is None:
+            self._head = ops.pack_linear_weight(self._sd["final_layers.1.weight"])
+        nrm = torch.empty_like(h)
+        ops.layernorm(h, self._sd["final_layers.0.weight"], self._sd["final_layers.0.bias"], nrm, 1e-5)
+        out = torch.empty(B, T, self.codebook_dim, device=h.device, dtype=torch.float32)
+        ops.linear(nrm.view(B * T, H), self._head, self._sd["final_layers.1.bias"], out.view(B * T, -1))
+        return out
+
+    __call__ = forward

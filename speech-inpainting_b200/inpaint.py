@@ -1,0 +1,187 @@
+"""Batched inpainting pipelines = the reference's driver glue replayed on the device.
+
+  * `InformedInpainter` - I_ea/predict.py:85-207 (mask -> z-norm -> CustomModel -> gather -> cos-sim argmax
+    -> centroid paste -> extend_mel -> Generator), batched, ragged mask lengths allowed.
+  * `BlindInpainter`    - I_da/scripts/inpainting.py:181-259 (mask -> get_feats x2 -> k-means units ->
+    optional splice -> trim -> CodeGenerator).
+Integer index arithmetic is done on the host with Python ints exactly as the reference does; everything
+that touches samples / frames runs in libsib_b200.so.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+from .ops import SibError
+
+
+# ----------------------------------------------------------------------------- a1 (host integers)
+def iea_mask_indices(start_sec: float, end_sec: float, sr16: int = 16000, sr22: int = 22050):
+    """I_ea/predict.py:85-90, 99-100, 133."""
+    mask_ms = int((end_sec - start_sec) * 1000)
+    mask_len = mask_ms // 20
+    start_mask, end_mask = int(start_sec * sr16), int(end_sec * sr16)
+    mask_pos = start_mask // 320
+    return dict(mask_len=mask_len, mask_pos=mask_pos, zero16=iea_zero_range(mask_pos, mask_len),
+                zero22=(start_mask * sr22 // sr16, end_mask * sr22 // sr16))
+
+
+def iea_zero_range(mask_pos: int, mask_len: int):
+    """I_ea/predict.py:133 / I_ea/dataset/dataset.py:82: [pos*320+80, (pos+L)*320+79-80)."""
+    return mask_pos * 320 + 80, (mask_pos + mask_len) * 320 + 79 - 80
+
+
+def extend_mel(spec: torch.Tensor) -> torch.Tensor:
+    """I_ea/hifi_gan/inference_modified.py:16-19: [B,80,T] -> [B,80,floor(T*441/256)] on the device."""
+    if not spec.is_cuda:
+        raise SibError("extend_mel: CUDA tensor required (no CPU fallback)")
+    spec = spec.to(torch.float32).contiguous()
+    B, Dm, T = spec.shape
+    out = torch.empty(B, Dm, ops.extend_mel_len(T), device=spec.device, dtype=torch.float32)
+    ops.extend_mel(spec, out, frame_major=False)
+    return out
+
+
+def shard_batch(n_items: int, world_size: int, rank: int):
+    """Contiguous utterance shard of rank `rank`: [rank*n/W, (rank+1)*n/W) with the remainder
+    spread over the first ranks.  No data-path collective: replicas only."""
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def ida_matched_frames(n_samples: int, n_code: int, n_f0: int, hop: int = 320) -> int:
+    """Code frames that survive `match_length` (I_da/src/multiseries.py:5-73; hops 1/320/80 => unit = 320
+    samples) and the 1280-sample tail trim (I_da/scripts/inpainting.py:243-256)."""
+    n_unit = min(n_samples // hop, n_code, n_f0 // (hop // 80))
+    to_remove = (n_unit * hop) % (16 * 80)
+    if to_remove % hop != 0:
+        raise SibError("to_remove % code_hop_size != 0 (inpainting.py:245 assert)")
+    return n_unit - to_remove // hop
+
+
+def _i32(v, dev):
+    return torch.as_tensor(v, dtype=torch.int32).to(dev)
+
+
+class InformedInpainter:
+    """I_ea informed inpainting for a batch of utterances (predict.py:85-207)."""
+
+    def __init__(self, model, generator, codebook: torch.Tensor):
+        """codebook = ApplyKmeans.C, shape [80, K] (I_ea/dataset/km_label.py:10-34, loss_fn.py:10-14)."""
+        self.model, self.generator = model, generator
+        dev = model._device
+        C = codebook.to(dev, torch.float32)
+        all_t = C.t().contiguous()                     # all_embeds_t [K, 80]
+        self.center = all_t.mean(dim=0).contiguous()   # center_
+        self.cc = (all_t - self.center[None, :]).contiguous()  # all_embeds_t_c
+        self.device = dev
+
+    def __call__(self, wave16, mel, mask_pos, mask_len, apply_mask: bool = True, normalize: bool = True,
+                 attention_mask=None, return_int16: bool = False):
+        """wave16 [B,N] float32 (host or device), mel [B,80,T'] (hop-441 log-mel of the masked 22 kHz wave),
+        mask_pos/mask_len: per-utterance frame index / length (ints or sequences).
+        Returns namespace(wave [B,1,S], labels [sum L] int64, mel [B,80,T'] inpainted, offsets)."""
+        dev = self.device
+        B, N = wave16.shape
+        pos = [int(p) for p in (mask_pos if hasattr(mask_pos, "__len__") else [mask_pos] * B)]
+        ln = [int(l) for l in (mask_len if hasattr(mask_len, "__len__") else [mask_len] * B)]
+        if len(pos) != B or len(ln) != B:
+            raise SibError("mask_pos / mask_len must have one entry per utterance")
+        x = wave16.to(dev, torch.float32, non_blocking=True).clone() if wave16.is_cuda else wave16.to(dev, torch.float32, non_blocking=True)
+        x = x.contiguous()
+        if apply_mask:  # predict.py:133
+            rng = [iea_zero_range(p, l) for p, l in zip(pos, ln)]
+            ops.zero_ranges(x, _i32([r[0] for r in rng], dev), _i32([r[1] for r in rng], dev))
+        if normalize:   # predict.py:136-141 (processor: do_normalize=True, eps 1e-7)
+            lengths = None if attention_mask is None else attention_mask.sum(-1).to(dev, torch.int32)
+            xn = torch.empty_like(x)
+            ops.znorm(x, xn, lengths, 1e-7)
+            x = xn
+        outputs = self.model(x, attention_mask)  # [B,T,80]  predict.py:163
+        T = outputs.shape[1]
+        for p, l in zip(pos, ln):
+            if p < 0 or p + l > T:
+                raise SibError(f"mask frames [{p},{p + l}) outside the {T} encoder frames")
+        off, acc = [], 0
+        for l in ln:
+            off.append(acc)
+            acc += l
+        M = acc
+        mel_dev = mel.to(dev, torch.float32, non_blocking=True).clone() if mel.is_cuda else mel.to(dev, torch.float32, non_blocking=True).contiguous()
+        labels = torch.empty(max(M, 1), dtype=torch.int64, device=dev)[:M]
+        if M > 0:
+            pos_t, len_t, off_t = _i32(pos, dev), _i32(ln, dev), _i32(off, dev)
+            values = torch.empty(M, outputs.shape[-1], device=dev, dtype=torch.float32)
+            ops.gather_frames(outputs, pos_t, len_t, off_t, values)       # predict.py:164-168
+            ops.cos_argmax(values, self.cc, labels)                        # loss_fn.py:44-46
+            ops.paste_centroids(mel_dev, self.cc, self.center, labels, pos_t, len_t, off_t)  # predict.py:184-187
+        Tp = mel_dev.shape[2]
+        feats = torch.empty(B, ops.extend_mel_len(Tp), mel_dev.shape[1], device=dev, dtype=torch.float32)
+        ops.extend_mel(mel_dev, feats, frame_major=True)                   # predict.py:189
+        y = self.generator.forward_frame_major(feats)                      # predict.py:203
+        res = SimpleNamespace(wave=y, labels=labels, mel=mel_dev, offsets=off, outputs=outputs)
+        if return_int16:                                                   # predict.py:204-206
+            res.int16 = torch.empty(y.shape, dtype=torch.int16, device=dev)
+            ops.pack_int16(y, res.int16)
+        return res
+
+
+class BlindInpainter:
+    """I_da inpainting for a batch of equal-length utterances (scripts/inpainting.py:181-259)."""
+
+    def __init__(self, hubert, code_generator, kmeans_centers: torch.Tensor, layer: int = -1, normalize: bool = False,
+                 code_hop_size: int = 320, sampling_rate: int = 16000):
+        self.hubert, self.gen = hubert, code_generator
+        self.device = hubert._device
+        self.mu = kmeans_centers.to(self.device, torch.float32).contiguous()  # [K, H]
+        self.layer, self.normalize = layer, normalize
+        self.hop, self.sr = code_hop_size, sampling_rate
+
+    def get_feats(self, x):
+        """HubertFeatureReader.get_feats (hubert_feature_reader.py:44-67), batched over equal lengths."""
+        if self.normalize:
+            xn = torch.empty_like(x)
+            ops.znorm(x, xn, None, 1e-5)  # F.layer_norm(x, x.shape)
+            x = xn
+        feats = []
+        for s in range(0, x.shape[1], 1_600_000):
+            f, _ = self.hubert.extract_features(x[:, s:s + 1_600_000].contiguous(), padding_mask=None, mask=False,
+                                                output_layer=self.layer)
+            feats.append(f)
+        return feats[0] if len(feats) == 1 else torch.cat(feats, 1)
+
+    def units(self, feats):
+        B, T, H = feats.shape
+        labels = torch.empty(B * T, dtype=torch.int64, device=self.device)
+        ops.l2_argmin(feats.reshape(B * T, H), self.mu, labels)  # kmeans_model.predict (inpainting.py:204-205)
+        return labels.view(B, T)
+
+    def __call__(self, wave, mask_size: int, f0_code, emb, informed: bool = True, return_int16: bool = False):
+        dev = self.device
+        y = wave.to(dev, torch.float32).contiguous()
+        B, N = y.shape
+        frame_start = int(self.sr * 3 / 2)                                  # inpainting.py:187
+        y_inp = y.clone()
+        ops.zero_ranges(y_inp, _i32([frame_start] * B, dev), _i32([frame_start + mask_size] * B, dev), add_eps=1e-6)  # :188-191
+        code = self.units(self.get_feats(y))                                # :195-205
+        code_inp = self.units(self.get_feats(y_inp))
+        if informed:                                                         # :207-214
+            a, b = frame_start // self.hop, (frame_start + mask_size) // self.hop
+            code_inp[:, :a] = code[:, :a]
+            code_inp[:, b:] = code[:, b:]
+        # match_length over (audio hop 1, code hop 320, f0 hop 80) then drop the tail so that the audio is a
+        # multiple of 1280 samples (multiseries.py:5-73, inpainting.py:217-256)
+        n_code = ida_matched_frames(N, code.shape[1], 4 * f0_code.shape[1], self.hop)
+        code, code_inp = code[:, :n_code].contiguous(), code_inp[:, :n_code].contiguous()
+        zp = f0_code.to(dev)[:, : n_code // 4].contiguous()
+        wav_gen = self.gen(code=code, f0_code=zp, emb=emb)                   # :258
+        wav_inp = self.gen(code=code_inp, f0_code=zp, emb=emb)               # :259
+        res = SimpleNamespace(audio_gen=wav_gen, audio_inp=wav_inp, code=code, code_inpainting=code_inp,
+                              audio_mask=y_inp)
+        if return_int16:
+            res.int16 = torch.empty(wav_inp.shape, dtype=torch.int16, device=dev)
+            ops.pack_int16(wav_inp, res.int16)
+        return res

@@ -1,0 +1,320 @@
+"""Tensor-level wrappers over the C-ABI kernels + launch plans.
+
+PyTorch is plumbing here (device memory, streams); every op below is a call into
+`libsib_b200.so` on the current CUDA stream.  A `Plan` records the launches of one forward pass
+over static buffers so that it can be replayed with ~2 us of host time per kernel or captured
+into a CUDA graph (no tracing compiler involved).
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_TANH, ConvDesc, SibError  # noqa: F401
+
+_active_plan = None
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise SibError(f"{name} must be a CUDA tensor (no CPU fallback on this path)")
+    if dtype is not None and t.dtype != dtype:
+        raise SibError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class Plan:
+    """Recorded launch list of one forward pass over static buffers."""
+
+    def __init__(self):
+        self.steps = []   # (cfunc, args-without-stream, name)
+        self.keep = []    # tensors / descs that must outlive the plan
+        self.graph = None
+
+    @contextlib.contextmanager
+    def record(self):
+        global _active_plan
+        prev, _active_plan = _active_plan, self
+        try:
+            yield self
+        finally:
+            _active_plan = prev
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return
+        s = _stream()
+        for fn, args, name in self.steps:
+            rc = fn(*args, s)
+            if rc:
+                _lib.check(rc, name)
+
+    def capture(self):
+        """Capture the launch list into a CUDA graph (launch-bound inner loops, one replay per forward)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.run()  # warm-up outside capture (sets func attributes)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            s = _stream()
+            for fn, args, name in self.steps:
+                rc = fn(*args, s)
+                if rc:
+                    _lib.check(rc, name)
+        self.graph = g
+
+    def __len__(self):
+        return len(self.steps)
+
+
+def _emit(name, args, keep=()):
+    fn = getattr(_lib.lib(), name)
+    if _active_plan is not None:
+        _active_plan.steps.append((fn, args, name))
+        _active_plan.keep.extend(keep)
+        return
+    rc = fn(*args, _stream())
+    if rc:
+        _lib.check(rc, name)
+
+
+def launch_count() -> int:
+    return int(_lib.lib().sib_launch_count())
+
+
+# ----------------------------------------------------------------------------- weight packing
+def pack_conv_weight(w: torch.Tensor, groups: int = 1) -> torch.Tensor:
+    """torch Conv1d weight [Cout, Cin/g, k] -> [g][k][Cin/g][Cout/g] (fp32 SIMT layout)."""
+    cout, cin_g, k = w.shape
+    return w.view(groups, cout // groups, cin_g, k).permute(0, 3, 2, 1).contiguous()
+
+
+def pack_linear_weight(w: torch.Tensor) -> torch.Tensor:
+    """torch Linear weight [out, in] -> [1][1][in][out]."""
+    return w.t().contiguous().view(1, 1, w.shape[1], w.shape[0])
+
+
+def conv_taps(k: int, dilation: int, padding: int):
+    return [j * dilation - padding for j in range(k)]
+
+
+def pack_conv_transpose(w: torch.Tensor, bias, stride: int, padding: int):
+    """ConvTranspose1d weight [Cin, Cout, k] -> poly-phase conv over the *input* grid:
+    output row q holds the `stride` phases of samples q*stride+p, so y[B, T, stride*Cout] is
+    bit-for-bit the frame-major [B, T*stride, Cout].  Returns (w_packed[1][taps][Cin][s*Cout],
+    bias[s*Cout], tap_offsets).  For o = q*s+p: j = r + m*s, r = (p+pad) % s, i = q + (p+pad)//s - m."""
+    cin, cout, k = w.shape
+    entries = []
+    for p in range(stride):
+        r, delta = (p + padding) % stride, (p + padding) // stride
+        m = 0
+        while r + m * stride < k:
+            entries.append((delta - m, p, r + m * stride))
+            m += 1
+    offs = sorted({e[0] for e in entries})
+    packed = torch.zeros(len(offs), cin, stride * cout, dtype=w.dtype, device=w.device)
+    for off, p, j in entries:
+        packed[offs.index(off), :, p * cout:(p + 1) * cout] = w[:, :, j]
+    b = None if bias is None else bias.repeat(stride)
+    return packed.unsqueeze(0).contiguous(), b, offs
+
+
+# ----------------------------------------------------------------------------- conv / linear
+def make_desc(batch, t_in, t_out, c_in, c_out, taps, *, stride=1, groups=1, x_row=None, x_batch=None,
+              y_row=None, y_batch=None, r_row=None, r_batch=None, pre_slope=None, post_act=ACT_NONE,
+              post_slope=0.0, out_scale=1.0, accumulate=False, res_after_act=False) -> ConvDesc:
+    if len(taps) > _lib.SIB_MAX_TAPS:
+        raise SibError(f"{len(taps)} taps > {_lib.SIB_MAX_TAPS}")
+    d = ConvDesc()
+    d.batch, d.t_in, d.t_out, d.c_in, d.c_out, d.groups = batch, t_in, t_out, c_in, c_out, groups
+    d.n_taps, d.stride = len(taps), stride
+    for i, o in enumerate(taps):
+        d.tap_offset[i] = o
+    d.x_row_stride = c_in if x_row is None else x_row
+    d.x_batch_stride = t_in * d.x_row_stride if x_batch is None else x_batch
+    d.y_row_stride = c_out if y_row is None else y_row
+    d.y_batch_stride = t_out * d.y_row_stride if y_batch is None else y_batch
+    d.r_row_stride = c_out if r_row is None else r_row
+    d.r_batch_stride = t_out * d.r_row_stride if r_batch is None else r_batch
+    d.pre_act = ACT_LRELU if pre_slope is not None else ACT_NONE
+    d.pre_slope = 0.0 if pre_slope is None else pre_slope
+    d.post_act, d.post_slope, d.out_scale = post_act, post_slope, out_scale
+    d.accumulate, d.res_after_act = int(accumulate), int(res_after_act)
+    return d
+
+
+def conv1d(x, w, bias, y, taps, *, stride=1, groups=1, residual=None, y_act=None, **kw):
+    """x [B,T_in,Cin], y [B,T_out,Cout] frame-major (fp32 or bf16, chosen by x.dtype)."""
+    B, t_in, c_in = x.shape
+    _, t_out, c_out = y.shape
+    d = make_desc(B, t_in, t_out, c_in, c_out, taps, stride=stride, groups=groups,
+                  x_row=x.stride(1), x_batch=x.stride(0), y_row=y.stride(1), y_batch=y.stride(0),
+                  r_row=None if residual is None else residual.stride(1),
+                  r_batch=None if residual is None else residual.stride(0), **kw)
+    if x.dtype == torch.float32:
+        _chk(w, torch.float32, "w"); _chk(y, torch.float32, "y"); _chk(bias, torch.float32, "bias")
+        _chk(residual, torch.float32, "residual")
+        if y_act is not None:
+            raise SibError("y_act is a bf16-path feature")
+        _emit("sib_conv1d_f32", (C.byref(d), _p(x), _p(w), _p(bias), _p(residual), _p(y)), keep=(d, x, w, bias, residual, y))
+    elif x.dtype == torch.bfloat16:
+        _chk(w, torch.bfloat16, "w"); _chk(y, torch.bfloat16, "y"); _chk(bias, torch.float32, "bias")
+        _chk(residual, torch.bfloat16, "residual"); _chk(y_act, torch.bfloat16, "y_act")
+        _emit("sib_conv1d_bf16", (C.byref(d), _p(x), _p(w), _p(bias), _p(residual), _p(y), _p(y_act)),
+              keep=(d, x, w, bias, residual, y, y_act))
+    else:
+        raise SibError(f"unsupported dtype {x.dtype}")
+
+
+def linear(x2d, w, bias, y2d, *, residual=None, **kw):
+    """x2d [M,K] @ packed w [1][1][K][N] (+bias) -> y2d [M,N]."""
+    conv1d(x2d.unsqueeze(0), w, bias, y2d.unsqueeze(0), [0],
+           residual=None if residual is None else residual.unsqueeze(0), **kw)
+
+
+def conv1d_cout1(x, w, bias, y, k, pad, pre_slope, post_act):
+    B, T, Cc = x.shape
+    _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y")
+    _emit("sib_conv1d_cout1_f32", (_p(x), _p(w), _p(bias), _p(y), B, T, Cc, k, pad, pre_slope, post_act),
+          keep=(x, w, bias, y))
+
+
+# ----------------------------------------------------------------------------- norms / attention
+def conv0(mode, wave, w, bias, c, k, stride, t0, *, partial=None, mean=None, rstd=None, gamma=None, beta=None, y=None):
+    B, n = wave.shape
+    _chk(wave, torch.float32, "wave")
+    _emit("sib_conv0_f32", (mode, _p(wave), B, n, wave.stride(0), _p(w), _p(bias), c, k, stride, t0, _p(partial),
+                            _p(mean), _p(rstd), _p(gamma), _p(beta), _p(y)),
+          keep=(wave, w, bias, partial, mean, rstd, gamma, beta, y))
+
+
+def conv0_num_tiles(t0: int) -> int:
+    return int(_lib.lib().sib_conv0_num_tiles(t0))
+
+
+def gn_finalize(partial, batch, n_tiles, c, t0, eps, mean, rstd):
+    _emit("sib_gn_finalize_f32", (_p(partial), batch, n_tiles, c, t0, eps, _p(mean), _p(rstd)), keep=(partial, mean, rstd))
+
+
+def layernorm(x, gamma, beta, y, eps=1e-5, residual=None, post_act=ACT_NONE):
+    c = x.shape[-1]
+    rows = x.numel() // c
+    _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y")
+    _emit("sib_layernorm_f32", (_p(x), _p(residual), _p(gamma), _p(beta), _p(y), rows, c, eps, post_act),
+          keep=(x, residual, gamma, beta, y))
+
+
+def attention(qkv, key_len, out, heads):
+    B, T, H3 = qkv.shape
+    _chk(qkv, torch.float32, "qkv"); _chk(out, torch.float32, "out"); _chk(key_len, torch.int32, "key_len")
+    _emit("sib_attention_f32", (_p(qkv), _p(key_len), _p(out), B, T, heads, H3 // 3 // heads), keep=(qkv, key_len, out))
+
+
+def zero_padded_frames(h, key_len):
+    B, T, Cc = h.shape
+    _emit("sib_zero_padded_frames_f32", (_p(h), _p(_chk(key_len, torch.int32, "key_len")), B, T, Cc), keep=(h, key_len))
+
+
+# ----------------------------------------------------------------------------- glue
+def zero_ranges(wave, lo, hi, add_eps=0.0):
+    B, n = wave.shape
+    _chk(wave, torch.float32, "wave"); _chk(lo, torch.int32, "lo"); _chk(hi, torch.int32, "hi")
+    if not wave.is_contiguous():
+        raise SibError("wave must be contiguous")
+    _emit("sib_zero_ranges_f32", (_p(wave), B, n, _p(lo), _p(hi), add_eps), keep=(wave, lo, hi))
+
+
+def znorm(x, y, lengths=None, eps=1e-7):
+    B, n = x.shape
+    _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y"); _chk(lengths, torch.int32, "lengths")
+    _emit("sib_znorm_f32", (_p(x), _p(y), B, n, _p(lengths), eps), keep=(x, y, lengths))
+
+
+def gather_frames(src, pos, length, off, out):
+    B, T, Dm = src.shape
+    _chk(src, torch.float32, "src"); _chk(out, torch.float32, "out")
+    for t, nme in ((pos, "pos"), (length, "len"), (off, "off")):
+        _chk(t, torch.int32, nme)
+    _emit("sib_gather_frames_f32", (_p(src), B, T, Dm, _p(pos), _p(length), _p(off), _p(out)), keep=(src, pos, length, off, out))
+
+
+def cos_argmax(v, cc, labels):
+    M, Dm = v.shape
+    _chk(v, torch.float32, "v"); _chk(cc, torch.float32, "cc"); _chk(labels, torch.int64, "labels")
+    _emit("sib_cos_argmax_f32", (_p(v), _p(cc), M, cc.shape[0], Dm, _p(labels)), keep=(v, cc, labels))
+
+
+def l2_argmin(f, mu, labels):
+    M, Dm = f.shape
+    _chk(f, torch.float32, "f"); _chk(mu, torch.float32, "mu"); _chk(labels, torch.int64, "labels")
+    _emit("sib_l2_argmin_f32", (_p(f), _p(mu), M, mu.shape[0], Dm, _p(labels)), keep=(f, mu, labels))
+
+
+def paste_centroids(mel, cc, center, labels, pos, length, off):
+    B, Dm, T = mel.shape
+    _chk(mel, torch.float32, "mel"); _chk(labels, torch.int64, "labels")
+    _emit("sib_paste_centroids_f32", (_p(mel), B, Dm, T, _p(cc), _p(center), _p(labels), _p(pos), _p(length), _p(off)),
+          keep=(mel, cc, center, labels, pos, length, off))
+
+
+def extend_mel_len(t: int) -> int:
+    """floor(T * 441/256) with the float arithmetic F.interpolate uses."""
+    import math
+    return int(math.floor(float(t) * (441 / 256)))
+
+
+def extend_mel(mel, out, frame_major: bool):
+    B, Dm, T = mel.shape
+    tm = out.shape[1] if frame_major else out.shape[2]
+    _chk(mel, torch.float32, "mel"); _chk(out, torch.float32, "out")
+    _emit("sib_extend_mel_f32", (_p(mel), _p(out), B, Dm, T, tm, int(frame_major)), keep=(mel, out))
+
+
+def transpose(x, out):
+    """[B,R,C] -> [B,C,R]"""
+    B, R, Cc = x.shape
+    _chk(x, torch.float32, "x"); _chk(out, torch.float32, "out")
+    _emit("sib_transpose_f32", (_p(x), _p(out), B, R, Cc), keep=(x, out))
+
+
+def embed_concat(code, zp, spk, emb_c, emb_p, out):
+    B, T = code.shape
+    _chk(code, torch.int64, "code"); _chk(zp, torch.int64, "zp"); _chk(spk, torch.float32, "spk")
+    _emit("sib_embed_concat_f32", (_p(code), _p(zp), _p(spk), _p(emb_c), _p(emb_p), _p(out), B, T, zp.shape[1],
+                                   emb_c.shape[1], spk.shape[1]), keep=(code, zp, spk, emb_c, emb_p, out))
+
+
+def pack_int16(y, out):
+    _chk(y, torch.float32, "y"); _chk(out, torch.int16, "out")
+    _emit("sib_pack_int16_f32", (_p(y), _p(out), y.numel()), keep=(y, out))
+
+
+def mel_spectrogram(wave, basis, out, hop, pad):
+    B, n = wave.shape
+    _chk(wave, torch.float32, "wave"); _chk(basis, torch.float32, "basis"); _chk(out, torch.float32, "out")
+    _emit("sib_mel_spectrogram_f32", (_p(wave), B, n, hop, pad, _p(basis), basis.shape[0], _p(out), out.shape[2]),
+          keep=(wave, basis, out))
+
+
+def cast_to_bf16(x, out):
+    _emit("sib_cast_f32_to_bf16", (_p(x), _p(out), x.numel()), keep=(x, out))
+
+
+def cast_to_f32(x, out):
+    _emit("sib_cast_bf16_to_f32", (_p(x), _p(out), x.numel()), keep=(x, out))

@@ -1,0 +1,263 @@
+"""-m gpu: every C-ABI kernel against a plain PyTorch fp32 statement of the same op (through ctypes)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import max_abs, snr_db, to_frame_major
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sib():
+    import speech_inpainting_b200 as m
+    m._load_lib()
+    return m
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale)
+
+
+CONV_CASES = [
+    # B, T, Cin, Cout, k, stride, dil, pad, groups
+    (2, 300, 64, 96, 3, 1, 1, 1, 1),
+    (1, 517, 128, 128, 7, 1, 3, 9, 1),
+    (3, 130, 32, 32, 11, 1, 5, 25, 1),
+    (2, 401, 512, 512, 3, 2, 1, 0, 1),   # HuBERT conv1-4 shape
+    (2, 200, 512, 512, 2, 2, 1, 0, 1),   # HuBERT conv5-6 shape
+    (2, 99, 768, 768, 128, 1, 1, 64, 16),  # pos-conv (k=128, groups=16) - output trimmed to T
+    (1, 50, 80, 512, 7, 1, 1, 3, 1),     # conv_pre
+    (2, 77, 20, 36, 5, 1, 2, 4, 2),      # odd sizes -> scalar path
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv1d_f32(sib, case):
+    B, T, Cin, Cout, k, s, d, p, g = case
+    x = _rand(B, Cin, T, seed=1)
+    w = _rand(Cout, Cin // g, k, seed=2, scale=1.0 / math.sqrt(Cin // g * k))
+    b = _rand(Cout, seed=3, scale=0.1)
+    ref = F.conv1d(F.leaky_relu(x, 0.1), w, b, stride=s, dilation=d, padding=p, groups=g)
+    t_out = min(ref.shape[-1], T) if (k == 128) else ref.shape[-1]
+    ref = ref[..., :t_out]
+    res = _rand(B, Cout, t_out, seed=4)
+    ref = torch.tanh(ref + res) if Cout == 96 else F.gelu(ref + res)
+    xd, wd = to_frame_major(x).cuda(), sib.ops.pack_conv_weight(w.cuda(), g)
+    y = torch.empty(B, t_out, Cout, device="cuda")
+    sib.ops.conv1d(xd, wd, b.cuda(), y, sib.ops.conv_taps(k, d, p), stride=s, groups=g, pre_slope=0.1,
+                   residual=to_frame_major(res).cuda(), post_act=sib.ops.ACT_TANH if Cout == 96 else sib.ops.ACT_GELU)
+    assert max_abs(to_frame_major(ref), y.cpu()) < 2e-4
+    assert snr_db(to_frame_major(ref), y.cpu()) > 80
+
+
+def test_conv1d_accumulate_scale_and_res_after_act(sib):
+    B, T, Cc = 2, 150, 64
+    x, w, b = _rand(B, Cc, T, seed=5), _rand(Cc, Cc, 3, seed=6, scale=0.1), _rand(Cc, seed=7)
+    y0 = _rand(B, T, Cc, seed=8)
+    y = y0.clone().cuda()
+    sib.ops.conv1d(to_frame_major(x).cuda(), sib.ops.pack_conv_weight(w.cuda()), b.cuda(), y, sib.ops.conv_taps(3, 1, 1),
+                   accumulate=True, out_scale=1.0 / 3)
+    ref = (to_frame_major(F.conv1d(x, w, b, padding=1)) + y0) / 3
+    assert max_abs(ref, y.cpu()) < 1e-5
+    res = _rand(B, T, Cc, seed=9)
+    y2 = torch.empty(B, T, Cc, device="cuda")
+    sib.ops.conv1d(to_frame_major(x).cuda(), sib.ops.pack_conv_weight(w.cuda()), b.cuda(), y2, sib.ops.conv_taps(3, 1, 1),
+                   post_act=sib.ops.ACT_GELU, residual=res.cuda(), res_after_act=True)
+    ref2 = F.gelu(to_frame_major(F.conv1d(x, w, b, padding=1))) + res
+    assert max_abs(ref2, y2.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("ks", [(16, 8), (4, 2), (11, 5), (8, 4)])
+def test_conv_transpose_polyphase(sib, ks):
+    k, s = ks
+    B, T, Cin, Cout = 2, 37, 64, 32
+    x, w, b = _rand(B, Cin, T, seed=1), _rand(Cin, Cout, k, seed=2, scale=0.1), _rand(Cout, seed=3)
+    ref = F.conv_transpose1d(F.leaky_relu(x, 0.1), w, b, stride=s, padding=(k - s) // 2)
+    assert ref.shape[-1] == T * s
+    wp, bp, taps = sib.ops.pack_conv_transpose(w.cuda(), b.cuda(), s, (k - s) // 2)
+    y = torch.empty(B, T * s, Cout, device="cuda")
+    sib.ops.conv1d(to_frame_major(x).cuda(), wp, bp, y.view(B, T, s * Cout), taps, pre_slope=0.1)
+    assert max_abs(to_frame_major(ref), y.cpu()) < 1e-5
+
+
+def test_linear_f32(sib):
+    M, K, N = 333, 768, 80
+    x, w, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=0.05), _rand(N, seed=3)
+    y = torch.empty(M, N, device="cuda")
+    sib.ops.linear(x.cuda(), sib.ops.pack_linear_weight(w.cuda()), b.cuda(), y)
+    assert max_abs(F.linear(x, w, b), y.cpu()) < 1e-4
+
+
+def test_conv_cout1_tanh(sib):
+    B, T, Cc = 2, 1000, 32
+    x, w, b = _rand(B, Cc, T, seed=1), _rand(1, Cc, 7, seed=2, scale=0.1), _rand(1, seed=3)
+    ref = torch.tanh(F.conv1d(F.leaky_relu(x), w, b, padding=3))
+    y = torch.empty(B, T, device="cuda")
+    sib.ops.conv1d_cout1(to_frame_major(x).cuda(), w[0].t().contiguous().cuda(), b.cuda(), y, 7, 3, 0.01, sib.ops.ACT_TANH)
+    assert max_abs(ref[:, 0], y.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("c", [80, 512, 768, 1024, 1500])
+def test_layernorm(sib, c):
+    x, r = _rand(37, 5, c, seed=1, scale=2.0), _rand(37, 5, c, seed=2)
+    g, b = 1 + 0.1 * _rand(c, seed=3), _rand(c, seed=4)
+    y = torch.empty(37, 5, c, device="cuda")
+    sib.ops.layernorm(x.cuda(), g.cuda(), b.cuda(), y, 1e-5, residual=r.cuda(), post_act=sib.ops.ACT_GELU)
+    ref = F.gelu(F.layer_norm(x + r, (c,), g, b, 1e-5))
+    assert max_abs(ref, y.cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("T,padded", [(99, False), (199, True), (64, False), (130, True)])
+def test_attention(sib, T, padded):
+    B, nh, d = 3, 4, 64
+    H = nh * d
+    qkv = _rand(B, T, 3 * H, seed=T)
+    kl = torch.tensor([T, T - 17, 5], dtype=torch.int32) if padded else None
+    q, k, v = [t.view(B, T, nh, d).transpose(1, 2) for t in qkv.split(H, dim=-1)]
+    s = torch.matmul(q, k.transpose(2, 3)) * d ** -0.5
+    if padded:
+        km = torch.arange(T)[None, :] < kl[:, None]
+        s = s.masked_fill(~km[:, None, None, :], torch.finfo(torch.float32).min)
+    ref = torch.matmul(F.softmax(s, -1), v).transpose(1, 2).reshape(B, T, H)
+    out = torch.empty(B, T, H, device="cuda")
+    sib.ops.attention(qkv.cuda(), None if kl is None else kl.cuda(), out, nh)
+    assert max_abs(ref, out.cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["group", "layer"])
+def test_conv0(sib, mode):
+    B, N, Cc = 2, 4000, 512
+    x = _rand(B, N, seed=1)
+    w, g, be = _rand(Cc, 1, 10, seed=2, scale=0.4), 1 + 0.1 * _rand(Cc, seed=3), 0.1 * _rand(Cc, seed=4)
+    bias = 0.1 * _rand(Cc, seed=5) if mode == "layer" else None
+    h = F.conv1d(x[:, None], w, bias, stride=5)
+    t0 = h.shape[-1]
+    y = torch.empty(B, t0, Cc, device="cuda")
+    wd = w.reshape(Cc, 10).contiguous().cuda()
+    if mode == "group":
+        ref = F.gelu(F.group_norm(h, Cc, g, be, 1e-5))
+        nt = sib.ops.conv0_num_tiles(t0)
+        part = torch.empty(B, nt, Cc, 2, device="cuda")
+        mean, rstd = torch.empty(B, Cc, device="cuda"), torch.empty(B, Cc, device="cuda")
+        sib.ops.conv0(0, x.cuda(), wd, None, Cc, 10, 5, t0, partial=part)
+        sib.ops.gn_finalize(part, B, nt, Cc, t0, 1e-5, mean, rstd)
+        sib.ops.conv0(1, x.cuda(), wd, None, Cc, 10, 5, t0, mean=mean, rstd=rstd, gamma=g.cuda(), beta=be.cuda(), y=y)
+    else:
+        ref = F.gelu(F.layer_norm(h.transpose(1, 2), (Cc,), g, be, 1e-5)).transpose(1, 2)
+        sib.ops.conv0(2, x.cuda(), wd, bias.cuda(), Cc, 10, 5, t0, y=y)
+        sib.ops.layernorm(y, g.cuda(), be.cuda(), y, 1e-5, post_act=sib.ops.ACT_GELU)
+    assert max_abs(to_frame_major(ref), y.cpu()) < 3e-5
+
+
+def test_znorm_and_zero_ranges(sib):
+    from oracle import glue_ref
+    B, N = 3, 32000
+    x = 0.1 * _rand(B, N, seed=1) + 0.01
+    lengths = torch.tensor([N, N - 5000, 1234], dtype=torch.int32)
+    y = torch.empty(B, N, device="cuda")
+    sib.ops.znorm(x.cuda(), y, None, 1e-7)
+    assert max_abs(glue_ref.processor_znorm(x), y.cpu()) < 2e-5
+    sib.ops.znorm(x.cuda(), y, lengths.cuda(), 1e-7)
+    assert max_abs(glue_ref.processor_znorm(x, lengths), y.cpu()) < 2e-5
+    sib.ops.znorm(x.cuda(), y, None, 1e-5)
+    assert max_abs(glue_ref.fairseq_layer_norm(x[0]), y[0].cpu()) < 2e-5
+    # zero ranges: bit exact, numpy slice semantics incl. empty / clamped ranges
+    lo, hi = [14480, 31000, 500], [17599, 40000, 400]
+    xd = x.clone().cuda()
+    sib.ops.zero_ranges(xd, torch.tensor(lo, dtype=torch.int32).cuda(), torch.tensor(hi, dtype=torch.int32).cuda())
+    for b in range(B):
+        assert np.array_equal(glue_ref.apply_zero_range(x[b].numpy(), lo[b], hi[b]), xd[b].cpu().numpy())
+    xd = x.clone().cuda()
+    sib.ops.zero_ranges(xd, torch.tensor([24000] * B, dtype=torch.int32).cuda(),
+                        torch.tensor([24000 + 6400] * B, dtype=torch.int32).cuda(), add_eps=1e-6)
+    ref, fs = glue_ref.ida_mask(x[0].numpy(), 6400)
+    assert fs == 24000 and np.array_equal(ref.astype(np.float32), xd[0].cpu().numpy())
+
+
+def test_glue_gather_assign_paste(sib, golden_dir):
+    from oracle import glue_ref
+    from oracle.params import make_codebook
+    gold = np.load(f"{golden_dir}/glue_golden.npz")
+    for K in (100, 500):
+        C = make_codebook(80, K, seed=77)
+        vals = _rand(3, 10, 80, seed=K)
+        cc, center = glue_ref.codebook_center(C)
+        labels = torch.empty(30, dtype=torch.int64, device="cuda")
+        sib.ops.cos_argmax(vals.view(30, 80).cuda(), cc.contiguous().cuda(), labels)
+        assert np.array_equal(labels.cpu().numpy().reshape(3, 10), gold[f"cos_sim_pred_{K}"])  # reference labels, exact
+        mel = _rand(1, 80, 50, seed=5).cuda()
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32).cuda()
+        sib.ops.paste_centroids(mel, cc.contiguous().cuda(), center.cuda(), labels[:10].contiguous(), i32([7]), i32([10]), i32([0]))
+        assert max_abs(torch.from_numpy(gold[f"paste_{K}"]), mel.cpu()) < 1e-6
+    # ragged gather
+    out = _rand(4, 60, 80, seed=3)
+    pos, ln = [0, 13, 59, 20], [5, 20, 1, 0]
+    off = [0, 5, 25, 26]
+    got = torch.empty(26, 80, device="cuda")
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32).cuda()
+    sib.ops.gather_frames(out.cuda(), i32(pos), i32(ln), i32(off), got)
+    ref = torch.cat(glue_ref.gather_mask_frames(out, pos, ln), 0)
+    assert torch.equal(ref, got.cpu())
+    # k-means assignment
+    f, mu = _rand(199, 768, seed=1), _rand(500, 768, seed=2)
+    lab = torch.empty(199, dtype=torch.int64, device="cuda")
+    sib.ops.l2_argmin(f.cuda(), mu.cuda(), lab)
+    assert torch.equal(glue_ref.kmeans_predict(f, mu), lab.cpu())
+
+
+@pytest.mark.parametrize("T", [37, 100, 200])
+def test_extend_mel(sib, golden_dir, T):
+    gold = torch.from_numpy(np.load(f"{golden_dir}/glue_golden.npz")[f"extend_mel_{T}"])
+    spec = _rand(2, 80, T, seed=T)  # same seed as make_golden
+    spec = torch.randn(2, 80, T, generator=torch.Generator().manual_seed(T))
+    out = sib.extend_mel(spec.cuda())
+    assert out.shape == gold.shape
+    assert max_abs(gold, out.cpu()) < 5e-5
+    fm = torch.empty(2, gold.shape[-1], 80, device="cuda")
+    sib.ops.extend_mel(spec.cuda(), fm, frame_major=True)
+    assert torch.equal(fm.transpose(1, 2), out)
+
+
+def test_transpose_embed_pack(sib):
+    from oracle import hifigan_ref
+    x = _rand(3, 45, 70, seed=1)
+    out = torch.empty(3, 70, 45, device="cuda")
+    sib.ops.transpose(x.cuda(), out)
+    assert torch.equal(x.transpose(1, 2), out.cpu())
+    B, T, E = 2, 16, 128
+    code = torch.randint(0, 500, (B, T), generator=torch.Generator().manual_seed(1))
+    zp = torch.randint(0, 20, (B, T // 4), generator=torch.Generator().manual_seed(2))
+    emb = _rand(B, E, seed=3)
+    p = {"emb_c.weight": _rand(500, E, seed=4), "emb_p.weight": _rand(20, E, seed=5)}
+    ref = hifigan_ref.code_generator_front(p, code, zp, emb)
+    got = torch.empty(B, T, 3 * E, device="cuda")
+    sib.ops.embed_concat(code.cuda(), zp.cuda(), emb.cuda(), p["emb_c.weight"].cuda(), p["emb_p.weight"].cuda(), got)
+    assert torch.equal(to_frame_major(ref), got.cpu())
+    y = torch.cat([torch.tanh(_rand(1, 1, 5000, seed=6) * 3), torch.tensor([[[1.0, -1.0, 0.99999, -0.99999, 0.0]]])], -1)
+    out16 = torch.empty(y.shape, dtype=torch.int16, device="cuda")
+    sib.ops.pack_int16(y.cuda(), out16)
+    assert np.array_equal(hifigan_ref.to_int16(y), out16.cpu().numpy().squeeze())
+
+
+@pytest.mark.parametrize("hop,pad,fmax", [(256, None, None), (441, 312, 8000)])
+def test_mel_spectrogram(sib, golden_dir, hop, pad, fmax):
+    gold = torch.from_numpy(np.load(f"{golden_dir}/mel_golden.npz")[f"mel_hop{hop}"])
+    y = 0.3 * torch.randn(2, 22050, generator=torch.Generator().manual_seed(3)).clamp(-3, 3)
+    out = sib.mel_spectrogram(y.cuda(), hop_size=hop, fmax=fmax, pad=pad)
+    assert out.shape == gold.shape
+    assert max_abs(gold, out.cpu()) < 2e-3   # log of fp32 magnitudes; bulk error is ~1e-5
+    assert float((gold - out.cpu()).abs().mean()) < 2e-5
+
+
+def test_errors_are_loud(sib):
+    x = torch.zeros(1, 8, 16)
+    with pytest.raises(sib.SibError):
+        sib.extend_mel(x)  # CPU tensor: no fallback
+    d = sib.ops.make_desc(1, 8, 8, 16, 16, [0], groups=3)
+    xd = torch.zeros(1, 8, 16, device="cuda")
+    with pytest.raises(sib.SibError, match="groups"):
+        sib.ops.conv1d(xd, xd, None, xd.clone(), [0], groups=3)
