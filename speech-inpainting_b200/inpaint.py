@@ -174,7 +174,7 @@ class BlindInpainter:
             code_inp[:, b:] = code[:, b:]
         # match_length over (audio hop 1, code hop 320, f0 hop 80) then drop the tail so that the audio is a
         # multiple of 1280 samples (multiseries.py:5-73, inpainting.py:217-256)
-        n_code = ida_matched_frames(N, code.shape[1], 4 * f0_code.shape[1], self.hop)
+        n_code = ida_matched_frames(N, code.shape[1], 16 * f0_code.shape[1], self.hop)  # one f0 bin = 16 f0 frames
         code, code_inp = code[:, :n_code].contiguous(), code_inp[:, :n_code].contiguous()
         zp = f0_code.to(dev)[:, : n_code // 4].contiguous()
         wav_gen = self.gen(code=code, f0_code=zp, emb=emb)                   # :258
