@@ -68,6 +68,8 @@ typedef struct sib_conv_desc {
   float out_scale;
   int32_t accumulate;
   int32_t res_after_act; /* 0: residual joins the sum before post(); 1: y = post(...) + residual (HF:440-441) */
+  /* bf16 tensor-core path only */
+  float act2_slope;      /* second output y_act = leaky_relu(y, act2_slope) */
 } sib_conv_desc;
 
 int sib_conv1d_f32(const sib_conv_desc* d, const float* x, const float* w, const float* bias,
@@ -146,12 +148,16 @@ int sib_mel_spectrogram_f32(const float* wave, int batch, int n, int hop, int pa
 
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core path (tcgen05 + TMA), see DESIGN.md.  Same contract as sib_conv1d_f32 with
- * bf16 x / w / y / residual, fp32 bias and accumulation.  w layout: [groups][c_out/g][n_taps][c_in/g]
- * (K-major).  Requires c_in/groups % 16 == 0.
+ * bf16 x / w / y / residual, fp32 bias and accumulation, no pre-activation (producers write y_act instead).
+ * w layout (K-major): [groups][c_out/g][c_in/g / cc][n_taps][cc]  (cc from sib_conv1d_bf16_kblock).
+ * Requires c_in/groups % 16 == 0, c_out/groups % 8 == 0.  stride > 1: valid convolution, groups = 1, dense rows, and
+ * x readable up to ceil(t_in/stride)*stride rows in the last batch item.
  * ------------------------------------------------------------------------------------------ */
 int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void* w, const float* bias,
-                    const void* residual, void* y, void* y_act /* nullable 2nd output = lrelu(y) */,
+                    const void* residual, void* y, void* y_act /* nullable 2nd output = lrelu(y, act2_slope) */,
                     sib_stream_t stream);
+/* K-block geometry the kernel uses for c_in/groups: cc channels x tb taps per pipeline stage (cc*tb = 64). */
+int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb);
 int sib_cast_f32_to_bf16(const float* in, void* out, int64_t n, sib_stream_t stream);
 int sib_cast_bf16_to_f32(const void* in, float* out, int64_t n, sib_stream_t stream);
 

@@ -25,6 +25,7 @@ class ConvDesc(C.Structure):
         ("x_row_stride", C.c_int32), ("y_row_stride", C.c_int32), ("r_row_stride", C.c_int32),
         ("pre_act", C.c_int32), ("pre_slope", C.c_float), ("post_act", C.c_int32), ("post_slope", C.c_float),
         ("out_scale", C.c_float), ("accumulate", C.c_int32), ("res_after_act", C.c_int32),
+        ("act2_slope", C.c_float),
     ]
 
 
@@ -57,6 +58,7 @@ _SIGS = {
     "sib_pack_int16_f32": ([_P, _P, _L, _P], _I),
     "sib_mel_spectrogram_f32": ([_P, _I, _I, _I, _I, _P, _I, _P, _I, _P], _I),
     "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
+    "sib_conv1d_bf16_kblock": ([_I, C.POINTER(C.c_int), C.POINTER(C.c_int)], _I),
     "sib_cast_f32_to_bf16": ([_P, _P, _L, _P], _I),
     "sib_cast_bf16_to_f32": ([_P, _P, _L, _P], _I),
 }

@@ -110,6 +110,22 @@ def pack_linear_weight(w: torch.Tensor) -> torch.Tensor:
     return w.t().contiguous().view(1, 1, w.shape[1], w.shape[0])
 
 
+def kblock(c_in_per_group: int):
+    """(cc, tb) K-block geometry of the tcgen05 kernel for this channel count (sib_conv1d_bf16_kblock)."""
+    cc, tb = C.c_int(), C.c_int()
+    _lib.check(_lib.lib().sib_conv1d_bf16_kblock(c_in_per_group, C.byref(cc), C.byref(tb)), "sib_conv1d_bf16_kblock")
+    return cc.value, tb.value
+
+
+def to_kmajor_bf16(w_packed: torch.Tensor) -> torch.Tensor:
+    """fp32 SIMT layout [g][taps][cin_g][cout_g] -> tcgen05 layout [g][cout_g][cin_g/cc][taps][cc] bf16
+    (K-major rows of the B operand)."""
+    g, taps, cin_g, cout_g = w_packed.shape
+    cc, _ = kblock(cin_g)
+    w = w_packed.permute(0, 3, 1, 2).reshape(g, cout_g, taps, cin_g // cc, cc).permute(0, 1, 3, 2, 4)
+    return w.to(torch.bfloat16).contiguous()
+
+
 def conv_taps(k: int, dilation: int, padding: int):
     return [j * dilation - padding for j in range(k)]
 
@@ -138,7 +154,8 @@ def pack_conv_transpose(w: torch.Tensor, bias, stride: int, padding: int):
 # ----------------------------------------------------------------------------- conv / linear
 def make_desc(batch, t_in, t_out, c_in, c_out, taps, *, stride=1, groups=1, x_row=None, x_batch=None,
               y_row=None, y_batch=None, r_row=None, r_batch=None, pre_slope=None, post_act=ACT_NONE,
-              post_slope=0.0, out_scale=1.0, accumulate=False, res_after_act=False) -> ConvDesc:
+              post_slope=0.0, out_scale=1.0, accumulate=False, res_after_act=False,
+              act2_slope=0.0) -> ConvDesc:
     if len(taps) > _lib.SIB_MAX_TAPS:
         raise SibError(f"{len(taps)} taps > {_lib.SIB_MAX_TAPS}")
     d = ConvDesc()
@@ -156,6 +173,7 @@ def make_desc(batch, t_in, t_out, c_in, c_out, taps, *, stride=1, groups=1, x_ro
     d.pre_slope = 0.0 if pre_slope is None else pre_slope
     d.post_act, d.post_slope, d.out_scale = post_act, post_slope, out_scale
     d.accumulate, d.res_after_act = int(accumulate), int(res_after_act)
+    d.act2_slope = act2_slope
     return d
 
 

@@ -1,0 +1,125 @@
+"""-m gpu: the bf16 tcgen05/TMA implicit-GEMM kernel (sib_conv1d_bf16) against torch fp32 run on the same
+bf16-rounded operands.  Accumulation is fp32 in TMEM, so the only differences are summation order and the
+final bf16 rounding of the output: tolerance = 1 bf16 ulp of the result (2^-8 relative) + small absolute."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import max_abs, to_frame_major
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sib():
+    import speech_inpainting_b200 as m
+    m._load_lib()
+    return m
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _close(ref, got, tag=""):
+    err = (ref - got).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2 * float(ref.abs().mean())
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{tag}: {bad} elements out of tolerance, max err {err.max():.4g}, ref max {ref.abs().max():.4g}"
+
+
+def _halo_buf(x_fm, halo):
+    """[B,T,C] -> zero-haloed buffer; returns (buffer, view of the valid rows)."""
+    B, T, C = x_fm.shape
+    buf = torch.zeros(B * (T + 2 * halo) + 256, C, dtype=torch.bfloat16, device="cuda")  # + slack rows at the end
+    v = buf[: B * (T + 2 * halo)].view(B, T + 2 * halo, C)[:, halo:halo + T]
+    v.copy_(x_fm)
+    return buf, v
+
+
+TC_CASES = [
+    # B, T, Cin, Cout, k, stride, dil, pad, groups, halo
+    (1, 333, 768, 768, 1, 1, 1, 0, 1, 0),      # linear
+    (1, 6368, 768, 2304, 1, 1, 1, 0, 1, 0),    # QKV projection at config-2 size
+    (2, 300, 128, 128, 7, 1, 3, 9, 1, 0),      # dilated ResBlock conv, OOB zero padding
+    (2, 517, 256, 256, 11, 1, 5, 25, 1, 0),
+    (3, 401, 512, 512, 3, 2, 1, 0, 1, 0),      # HuBERT conv1-4 (stride 2, odd length)
+    (2, 400, 512, 512, 2, 2, 1, 0, 1, 0),      # HuBERT conv5-6
+    (2, 700, 64, 64, 3, 1, 1, 1, 1, 0),
+    (2, 900, 32, 32, 11, 1, 5, 25, 1, 32),     # tap-blocked (cc=32, tb=2), halo
+    (2, 900, 32, 32, 3, 1, 3, 3, 1, 32),
+    (2, 500, 16, 16, 7, 1, 1, 3, 1, 32),       # I_da last stage (cc=16, tb=4)
+    (2, 99, 768, 768, 128, 1, 1, 64, 16, 64),  # pos-conv: 48 ch / group -> cc=16, tb=4
+    (1, 120, 1024, 1024, 128, 1, 1, 64, 16, 64),  # large pos-conv: 64 ch / group -> cc=64
+    (2, 50, 80, 512, 7, 1, 1, 3, 1, 8),        # conv_pre (80 = 5 x 16)
+    (1, 200, 512, 80, 1, 1, 1, 0, 1, 0),       # head: N tail (80 = 64 + 16)
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv1d_bf16_tc(sib, case):
+    B, T, Cin, Cout, k, s, d, p, g, halo = case
+    x = _bf(_rand(B, Cin, T, seed=1))
+    w = _bf(_rand(Cout, Cin // g, k, seed=2, scale=1.0 / math.sqrt(Cin // g * k)))
+    b = _rand(Cout, seed=3, scale=0.1)
+    ref = F.conv1d(x, w, b, stride=s, dilation=d, padding=p, groups=g)
+    t_out = min(ref.shape[-1], T) if k == 128 else ref.shape[-1]
+    ref = to_frame_major(ref[..., :t_out])
+    wk = sib.ops.to_kmajor_bf16(sib.ops.pack_conv_weight(w.cuda(), g))
+    xfm = to_frame_major(x).to(torch.bfloat16).cuda()
+    if halo:
+        keep, xd = _halo_buf(xfm, halo)
+    else:
+        keep = torch.zeros(xfm.numel() + 4096, dtype=torch.bfloat16, device="cuda")  # slack for the stride-s view
+        xd = keep[: xfm.numel()].view_as(xfm)
+        xd.copy_(xfm)
+    y = torch.full((B, t_out, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    sib.ops.conv1d(xd, wk, b.cuda(), y, sib.ops.conv_taps(k, d, p), stride=s, groups=g)
+    torch.cuda.synchronize()
+    _close(ref, y.float().cpu(), f"case {case}")
+
+
+def test_conv1d_bf16_epilogue_variants(sib):
+    B, T, Cc = 2, 300, 128
+    x, w, b = _bf(_rand(B, Cc, T, seed=5)), _bf(_rand(Cc, Cc, 3, seed=6, scale=0.1)), _rand(Cc, seed=7)
+    res, y0 = _bf(_rand(B, T, Cc, seed=8)), _bf(_rand(B, T, Cc, seed=9))
+    conv = to_frame_major(F.conv1d(x, w, b, padding=1))
+    xd = to_frame_major(x).to(torch.bfloat16).cuda()
+    wk = sib.ops.to_kmajor_bf16(sib.ops.pack_conv_weight(w.cuda()))
+    taps = sib.ops.conv_taps(3, 1, 1)
+    # residual + accumulate + scale, second (activated) output
+    y = y0.to(torch.bfloat16).cuda()
+    y2 = torch.empty_like(y)
+    sib.ops.conv1d(xd, wk, b.cuda(), y, taps, residual=res.to(torch.bfloat16).cuda(), accumulate=True, out_scale=1 / 3,
+                   y_act=y2, act2_slope=0.1)
+    ref = (conv + res + y0) / 3
+    _close(ref, y.float().cpu(), "acc")
+    _close(F.leaky_relu(_bf(ref), 0.1), y2.float().cpu(), "y_act")
+    # gelu then residual (pos-conv wiring), lrelu post-act, tanh
+    for act, fn in ((sib.ops.ACT_GELU, F.gelu), (sib.ops.ACT_TANH, torch.tanh)):
+        y = torch.empty(B, T, Cc, dtype=torch.bfloat16, device="cuda")
+        sib.ops.conv1d(xd, wk, b.cuda(), y, taps, post_act=act, residual=res.to(torch.bfloat16).cuda(), res_after_act=True)
+        _close(fn(conv) + res, y.float().cpu(), f"act{act}")
+    y = torch.empty(B, T, Cc, dtype=torch.bfloat16, device="cuda")
+    sib.ops.conv1d(xd, wk, b.cuda(), y, taps, post_act=sib.ops.ACT_LRELU, post_slope=0.1)
+    _close(F.leaky_relu(conv, 0.1), y.float().cpu(), "lrelu")
+
+
+@pytest.mark.parametrize("ks,cin,cout", [((16, 8), 512, 256), ((4, 2), 128, 64), ((4, 2), 64, 32), ((11, 5), 512, 256),
+                                         ((4, 2), 32, 16)])
+def test_conv_transpose_bf16_tc(sib, ks, cin, cout):
+    k, s = ks
+    B, T = 2, 45
+    x, w, b = _bf(_rand(B, cin, T, seed=1)), _bf(_rand(cin, cout, k, seed=2, scale=1 / math.sqrt(cin * k / s))), _rand(cout, seed=3)
+    ref = to_frame_major(F.conv_transpose1d(x, w, b, stride=s, padding=(k - s) // 2))
+    wp, bp, taps = sib.ops.pack_conv_transpose(w.cuda(), b.cuda(), s, (k - s) // 2)
+    keep, xd = _halo_buf(to_frame_major(x).to(torch.bfloat16).cuda(), 8)
+    y = torch.empty(B, T * s, cout, dtype=torch.bfloat16, device="cuda")
+    sib.ops.conv1d(xd, sib.ops.to_kmajor_bf16(wp), bp, y.view(B, T, s * cout), taps)
+    _close(ref, y.float().cpu(), f"convT {ks}")
