@@ -158,6 +158,21 @@ int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void* w, const 
                     sib_stream_t stream);
 /* K-block geometry the kernel uses for c_in/groups: cc channels x tb taps per pipeline stage (cc*tb = 64). */
 int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb);
+
+/* dtype-generic variants of the bandwidth-bound kernels for the bf16 plans (dtypes are sib_dtype; statistics,
+ * softmax and accumulation stay fp32).  Same reference lines as their _f32 counterparts above. */
+int sib_layernorm(const void* x, int x_dtype, const void* residual, int r_dtype, const float* gamma, const float* beta,
+                  void* y, int y_dtype, int64_t rows, int c, float eps, int post_act, sib_stream_t stream);
+int sib_attention(const void* qkv, int dtype, const int32_t* key_len, void* out, int batch, int t, int heads,
+                  int head_dim, sib_stream_t stream);
+int sib_conv0(int mode, const float* wave, int batch, int n_samples, int64_t wave_batch_stride, const float* w,
+              const float* bias, int c, int k, int stride, int t0, float* partial, const float* mean, const float* rstd,
+              const float* gamma, const float* beta, void* y, int y_dtype, sib_stream_t stream);
+int sib_zero_padded_frames(void* h, int dtype, const int32_t* key_len, int batch, int t, int c, sib_stream_t stream);
+int sib_conv1d_cout1(const void* x, int x_dtype, const float* w, const float* bias, float* y, int batch, int t, int c,
+                     int k, int pad, float pre_slope, int post_act, sib_stream_t stream);
+int sib_extend_mel(const float* in, void* out, int out_dtype, int batch, int d, int t, int tm, int frame_major,
+                   sib_stream_t stream);
 int sib_cast_f32_to_bf16(const float* in, void* out, int64_t n, sib_stream_t stream);
 int sib_cast_bf16_to_f32(const void* in, float* out, int64_t n, sib_stream_t stream);
 

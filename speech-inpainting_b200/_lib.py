@@ -59,6 +59,12 @@ _SIGS = {
     "sib_mel_spectrogram_f32": ([_P, _I, _I, _I, _I, _P, _I, _P, _I, _P], _I),
     "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_conv1d_bf16_kblock": ([_I, C.POINTER(C.c_int), C.POINTER(C.c_int)], _I),
+    "sib_layernorm": ([_P, _I, _P, _I, _P, _P, _P, _I, _L, _I, _F, _I, _P], _I),
+    "sib_attention": ([_P, _I, _P, _P, _I, _I, _I, _I, _P], _I),
+    "sib_conv0": ([_I, _P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P], _I),
+    "sib_zero_padded_frames": ([_P, _I, _P, _I, _I, _I, _P], _I),
+    "sib_conv1d_cout1": ([_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P], _I),
+    "sib_extend_mel": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "sib_cast_f32_to_bf16": ([_P, _P, _L, _P], _I),
     "sib_cast_bf16_to_f32": ([_P, _P, _L, _P], _I),
 }

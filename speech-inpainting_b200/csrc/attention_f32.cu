@@ -19,9 +19,25 @@ struct Smem {
   float linv[TQ];
 };
 
-__global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restrict__ qkv,
-                                                            const int32_t* __restrict__ key_len,
-                                                            float* __restrict__ out, int T, int heads) {
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  uint2 r;
+  *reinterpret_cast<__nv_bfloat162*>(&r.x) = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<__nv_bfloat162*>(&r.y) = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+template <typename TE>
+__global__ void __launch_bounds__(256) attention_kernel(const TE* __restrict__ qkv,
+                                                        const int32_t* __restrict__ key_len,
+                                                        TE* __restrict__ out, int T, int heads) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int H = heads * D;
@@ -30,16 +46,16 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
   const int h = blockIdx.y, b = blockIdx.z;
   const int kl = key_len ? min(key_len[b], T) : T;
   const float scale = rsqrtf((float)D);
-  const float* base = qkv + (int64_t)b * T * 3 * H + h * D;
+  const TE* base = qkv + (int64_t)b * T * 3 * H + h * D;
 
   // load Q^T (scaled)
   {
     const int i = tid & 63, dq = tid >> 6;
     const bool ok = q0 + i < T;
-    const float* src = base + (int64_t)(q0 + i) * 3 * H + dq * 16;
+    const TE* src = base + (int64_t)(q0 + i) * 3 * H + dq * 16;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      float4 v = ok ? __ldg(reinterpret_cast<const float4*>(src + m * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 v = ok ? ld4(src + m * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       const int dd = dq * 16 + m * 4;
       sm.Qt[dd + 0][i] = v.x * scale; sm.Qt[dd + 1][i] = v.y * scale;
       sm.Qt[dd + 2][i] = v.z * scale; sm.Qt[dd + 3][i] = v.w * scale;
@@ -59,13 +75,13 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
     {
       const int j = tid & 63, dq = tid >> 6;
       const bool ok = k0 + j < kl;
-      const float* ksrc = base + (int64_t)(k0 + j) * 3 * H + H + dq * 16;
-      const float* vsrc = ksrc + H;
+      const TE* ksrc = base + (int64_t)(k0 + j) * 3 * H + H + dq * 16;
+      const TE* vsrc = ksrc + H;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 kv = ok ? __ldg(reinterpret_cast<const float4*>(ksrc + m * 4)) : z;
-        const float4 vv = ok ? __ldg(reinterpret_cast<const float4*>(vsrc + m * 4)) : z;
+        const float4 kv = ok ? ld4(ksrc + m * 4) : z;
+        const float4 vv = ok ? ld4(vsrc + m * 4) : z;
         const int dd = dq * 16 + m * 4;
         sm.Kt[dd + 0][j] = kv.x; sm.Kt[dd + 1][j] = kv.y; sm.Kt[dd + 2][j] = kv.z; sm.Kt[dd + 3][j] = kv.w;
         *reinterpret_cast<float4*>(&sm.Vs[j][dd]) = vv;
@@ -153,28 +169,38 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
     if (t >= T) continue;
     const float li = sm.linv[ty * 4 + i];
     float4 v = make_float4(o[i][0] * li, o[i][1] * li, o[i][2] * li, o[i][3] * li);
-    *reinterpret_cast<float4*>(out + ((int64_t)b * T + t) * H + h * D + tx * 4) = v;
+    st4(out + ((int64_t)b * T + t) * H + h * D + tx * 4, v);
   }
 }
 
 }  // namespace
 
-extern "C" int sib_attention_f32(const float* qkv, const int32_t* key_len, float* out, int batch, int t, int heads,
-                                 int head_dim, sib_stream_t stream) {
-  SIB_REQUIRE(qkv && out && batch > 0 && t > 0 && heads > 0, "sib_attention_f32: bad argument");
-  SIB_REQUIRE(head_dim == D, "sib_attention_f32: head_dim=%d unsupported (64 only)", head_dim);
+extern "C" int sib_attention(const void* qkv, int dtype, const int32_t* key_len, void* out, int batch, int t, int heads,
+                             int head_dim, sib_stream_t stream) {
+  SIB_REQUIRE(qkv && out && batch > 0 && t > 0 && heads > 0, "sib_attention: bad argument");
+  SIB_REQUIRE(head_dim == D, "sib_attention: head_dim=%d unsupported (64 only)", head_dim);
   SIB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-              "sib_attention_f32: pointers must be 16B aligned");
-  SIB_REQUIRE(batch <= 65535 && heads <= 65535, "sib_attention_f32: grid too large");
+              "sib_attention: pointers must be 16B aligned");
+  SIB_REQUIRE(batch <= 65535 && heads <= 65535, "sib_attention: grid too large");
   static_assert(sizeof(Smem) <= 100 * 1024, "attention smem");
-  cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(Smem));
+  const void* fn = dtype == SIB_BF16 ? (const void*)attention_kernel<__nv_bfloat16> : (const void*)attention_kernel<float>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   if (e != cudaSuccess) {
-    sib::set_error("sib_attention_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    sib::set_error("sib_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return SIB_ERR_CUDA;
   }
   dim3 grid(sib::ceil_div(t, TQ), heads, batch);
-  attention_f32_kernel<<<grid, 256, sizeof(Smem), static_cast<cudaStream_t>(stream)>>>(qkv, key_len, out, t, heads);
-  SIB_CHECK_LAUNCH("sib_attention_f32");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == SIB_BF16)
+    attention_kernel<__nv_bfloat16><<<grid, 256, sizeof(Smem), s>>>((const __nv_bfloat16*)qkv, key_len,
+                                                                    (__nv_bfloat16*)out, t, heads);
+  else
+    attention_kernel<float><<<grid, 256, sizeof(Smem), s>>>((const float*)qkv, key_len, (float*)out, t, heads);
+  SIB_CHECK_LAUNCH("sib_attention");
   return SIB_OK;
+}
+
+extern "C" int sib_attention_f32(const float* qkv, const int32_t* key_len, float* out, int batch, int t, int heads,
+                                 int head_dim, sib_stream_t stream) {
+  return sib_attention(qkv, SIB_F32, key_len, out, batch, t, heads, head_dim, stream);
 }

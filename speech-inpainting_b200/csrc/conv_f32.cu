@@ -175,7 +175,11 @@ __global__ void __launch_bounds__(NT) conv1d_f32_kernel(const __grid_constant__ 
 }
 
 // One output channel: each thread owns one time step; the k*C weights sit in shared memory.
-__global__ void __launch_bounds__(256) conv1d_cout1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__device__ __forceinline__ float ldx(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldx(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename TX>
+__global__ void __launch_bounds__(256) conv1d_cout1_kernel(const TX* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ y,
                                                            int T, int C, int K, int pad, float pre_slope,
                                                            int post_act) {
@@ -185,14 +189,14 @@ __global__ void __launch_bounds__(256) conv1d_cout1_kernel(const float* __restri
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  const float* xb = x + (int64_t)b * T * C;
+  const TX* xb = x + (int64_t)b * T * C;
   float acc = bias ? bias[0] : 0.f;
   for (int j = 0; j < K; ++j) {
     const int ti = t + j - pad;
     if (ti < 0 || ti >= T) continue;
-    const float* xr = xb + (int64_t)ti * C;
+    const TX* xr = xb + (int64_t)ti * C;
     const float* wr = ws + j * C;
-    if ((C & 3) == 0) {
+    if (sizeof(TX) == 4 && (C & 3) == 0) {
       for (int c = 0; c < C; c += 4) {
         float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
         v.x = v.x > 0.f ? v.x : v.x * pre_slope; v.y = v.y > 0.f ? v.y : v.y * pre_slope;
@@ -200,9 +204,20 @@ __global__ void __launch_bounds__(256) conv1d_cout1_kernel(const float* __restri
         acc = fmaf(v.x, wr[c], acc); acc = fmaf(v.y, wr[c + 1], acc);
         acc = fmaf(v.z, wr[c + 2], acc); acc = fmaf(v.w, wr[c + 3], acc);
       }
+    } else if (sizeof(TX) == 2 && (C & 7) == 0) {
+      for (int c = 0; c < C; c += 8) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + c));
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 f = __bfloat1622float2(h2[i]);
+          f.x = f.x > 0.f ? f.x : f.x * pre_slope; f.y = f.y > 0.f ? f.y : f.y * pre_slope;
+          acc = fmaf(f.x, wr[c + 2 * i], acc); acc = fmaf(f.y, wr[c + 2 * i + 1], acc);
+        }
+      }
     } else {
       for (int c = 0; c < C; ++c) {
-        float v = __ldg(xr + c);
+        float v = ldx(xr + c);
         v = v > 0.f ? v : v * pre_slope;
         acc = fmaf(v, wr[c], acc);
       }
@@ -243,14 +258,23 @@ extern "C" int sib_conv1d_f32(const sib_conv_desc* d, const float* x, const floa
   return SIB_OK;
 }
 
+extern "C" int sib_conv1d_cout1(const void* x, int x_dtype, const float* w, const float* bias, float* y, int batch, int t,
+                                int c, int k, int pad, float pre_slope, int post_act, sib_stream_t stream) {
+  SIB_REQUIRE(x && w && y && batch > 0 && t > 0 && c > 0 && k > 0, "sib_conv1d_cout1: bad argument");
+  SIB_REQUIRE((size_t)k * c * sizeof(float) <= 48 * 1024, "sib_conv1d_cout1: k*c too large");
+  SIB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "sib_conv1d_cout1: x must be 16B aligned");
+  dim3 grid(sib::ceil_div(t, 256), batch);
+  const size_t smem = (size_t)k * c * sizeof(float);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (x_dtype == SIB_BF16)
+    conv1d_cout1_kernel<<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, w, bias, y, t, c, k, pad, pre_slope, post_act);
+  else
+    conv1d_cout1_kernel<<<grid, 256, smem, s>>>((const float*)x, w, bias, y, t, c, k, pad, pre_slope, post_act);
+  SIB_CHECK_LAUNCH("sib_conv1d_cout1");
+  return SIB_OK;
+}
+
 extern "C" int sib_conv1d_cout1_f32(const float* x, const float* w, const float* bias, float* y, int batch, int t,
                                     int c, int k, int pad, float pre_slope, int post_act, sib_stream_t stream) {
-  SIB_REQUIRE(x && w && y && batch > 0 && t > 0 && c > 0 && k > 0, "sib_conv1d_cout1_f32: bad argument");
-  SIB_REQUIRE((size_t)k * c * sizeof(float) <= 48 * 1024, "sib_conv1d_cout1_f32: k*c too large");
-  SIB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "sib_conv1d_cout1_f32: x must be 16B aligned");
-  dim3 grid(sib::ceil_div(t, 256), batch);
-  conv1d_cout1_kernel<<<grid, 256, (size_t)k * c * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      x, w, bias, y, t, c, k, pad, pre_slope, post_act);
-  SIB_CHECK_LAUNCH("sib_conv1d_cout1_f32");
-  return SIB_OK;
+  return sib_conv1d_cout1(x, SIB_F32, w, bias, y, batch, t, c, k, pad, pre_slope, post_act, stream);
 }

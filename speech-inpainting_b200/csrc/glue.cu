@@ -75,12 +75,16 @@ __global__ void paste_centroids_kernel(float* __restrict__ mel, int Dm, int T, c
 
 // F.interpolate(bilinear, scale_factor=(1, 441/256), align_corners=False) along time:
 // src = max(0, (dst + 0.5) * (256/441) - 0.5); i0 = floor(src); i1 = min(i0+1, T-1).
-__global__ void extend_mel_kernel(const float* __restrict__ in, float* __restrict__ out, int Dm, int T, int Tm,
+__device__ __forceinline__ void sto(float* p, float v) { *p = v; }
+__device__ __forceinline__ void sto(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename TY>
+__global__ void extend_mel_kernel(const float* __restrict__ in, TY* __restrict__ out, int Dm, int T, int Tm,
                                   int frame_major) {
   const int b = blockIdx.y;
   const float scale = (float)(1.0 / (441.0 / 256.0));
   const float* ib = in + (int64_t)b * Dm * T;
-  float* ob = out + (int64_t)b * Dm * Tm;
+  TY* ob = out + (int64_t)b * Dm * Tm;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Dm * Tm; i += gridDim.x * blockDim.x) {
     int c, t;
     if (frame_major) { t = i / Dm; c = i - t * Dm; } else { c = i / Tm; t = i - c * Tm; }
@@ -91,7 +95,7 @@ __global__ void extend_mel_kernel(const float* __restrict__ in, float* __restric
     const int i1 = min(i0 + 1, T - 1);
     const float w1 = src - (float)i0, w0 = 1.f - w1;
     const float* row = ib + (int64_t)c * T;
-    ob[i] = w0 * row[i0] + w1 * row[i1];
+    sto(ob + i, w0 * row[i0] + w1 * row[i1]);
   }
 }
 
@@ -191,13 +195,21 @@ extern "C" int sib_paste_centroids_f32(float* mel, int batch, int d, int t, cons
   return SIB_OK;
 }
 
+extern "C" int sib_extend_mel(const float* in, void* out, int out_dtype, int batch, int d, int t, int tm, int frame_major,
+                              sib_stream_t stream) {
+  SIB_REQUIRE(in && out && batch > 0 && batch <= 65535 && d > 0 && t > 0 && tm > 0, "sib_extend_mel: bad argument");
+  dim3 grid(sib::ceil_div((int64_t)d * tm, 256), batch);
+  if (out_dtype == SIB_BF16)
+    extend_mel_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, (__nv_bfloat16*)out, d, t, tm, frame_major);
+  else
+    extend_mel_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, (float*)out, d, t, tm, frame_major);
+  SIB_CHECK_LAUNCH("sib_extend_mel");
+  return SIB_OK;
+}
+
 extern "C" int sib_extend_mel_f32(const float* in, float* out, int batch, int d, int t, int tm, int frame_major,
                                   sib_stream_t stream) {
-  SIB_REQUIRE(in && out && batch > 0 && batch <= 65535 && d > 0 && t > 0 && tm > 0, "sib_extend_mel_f32: bad argument");
-  extend_mel_kernel<<<dim3(sib::ceil_div((int64_t)d * tm, 256), batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, out, d, t, tm, frame_major);
-  SIB_CHECK_LAUNCH("sib_extend_mel_f32");
-  return SIB_OK;
+  return sib_extend_mel(in, out, SIB_F32, batch, d, t, tm, frame_major, stream);
 }
 
 extern "C" int sib_transpose_f32(const float* in, float* out, int batch, int rows, int cols, sib_stream_t stream) {

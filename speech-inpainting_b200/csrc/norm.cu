@@ -6,16 +6,21 @@ namespace {
 
 // ------------------------------------------------------------------------------------------ LayerNorm
 // One warp per row; the row lives in registers (C <= 32*MAXV) so x is read exactly once.
-template <int MAXV>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int MAXV, typename TX, typename TR, typename TY>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TX* __restrict__ x, const TR* __restrict__ res,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float* __restrict__ y, int64_t rows, int C, float eps,
+                                                        TY* __restrict__ y, int64_t rows, int C, float eps,
                                                         int post_act) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const float* xr = x + row * C;
-  const float* rr = res ? res + row * C : nullptr;
+  const TX* xr = x + row * C;
+  const TR* rr = res ? res + row * C : nullptr;
   float v[MAXV];
   float s = 0.f;
 #pragma unroll
@@ -23,8 +28,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const int c = lane + i * 32;
     float t = 0.f;
     if (c < C) {
-      t = xr[c];
-      if (rr) t += rr[c];
+      t = ldf(xr + c);
+      if (rr) t += ldf(rr + c);
     }
     v[i] = t;
     s += t;
@@ -38,14 +43,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     q += dlt * dlt;
   }
   const float rstd = rsqrtf(sib::warp_sum(q) / C + eps);
-  float* yr = y + row * C;
+  TY* yr = y + row * C;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = lane + i * 32;
     if (c < C) {
       float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
       if (post_act == SIB_ACT_GELU) o = sib::gelu_erf(o);
-      yr[c] = o;
+      stf(yr + c, o);
     }
   }
 }
@@ -57,13 +62,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 constexpr int C0_TILE = 64;
 constexpr int C0_MAXK = 16;
 
-template <int MODE>
+template <int MODE, typename TY>
 __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ wave, int n, int64_t wave_bs,
                                                     const float* __restrict__ w, const float* __restrict__ bias,
                                                     int C, int K, int S, int T0, float* __restrict__ partial,
                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                    float* __restrict__ y) {
+                                                    TY* __restrict__ y) {
   extern __shared__ float xs[];  // (C0_TILE-1)*S + K samples
   const int b = blockIdx.y, tile = blockIdx.x;
   const int t_begin = tile * C0_TILE;
@@ -90,9 +95,9 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ wa
       if (MODE == 0) {
         s += acc; q += acc * acc;
       } else if (MODE == 1) {
-        y[((int64_t)b * T0 + t_begin + t) * C + c] = sib::gelu_erf((acc - m) * r * ga + be);
+        stf(y + ((int64_t)b * T0 + t_begin + t) * C + c, sib::gelu_erf((acc - m) * r * ga + be));
       } else {
-        y[((int64_t)b * T0 + t_begin + t) * C + c] = acc;
+        stf(y + ((int64_t)b * T0 + t_begin + t) * C + c, acc);
       }
     }
     if (MODE == 0) {
@@ -173,45 +178,71 @@ __global__ void zero_ranges_kernel(float* __restrict__ wave, int n, const int32_
   }
 }
 
-__global__ void zero_padded_frames_kernel(float* __restrict__ h, const int32_t* __restrict__ key_len, int T, int C) {
+template <typename TY>
+__global__ void zero_padded_frames_kernel(TY* __restrict__ h, const int32_t* __restrict__ key_len, int T, int C) {
   const int b = blockIdx.y;
   const int kl = key_len[b];
   const int64_t total = (int64_t)(T - kl) * C;
   if (total <= 0) return;
-  float* hb = h + ((int64_t)b * T + kl) * C;
+  TY* hb = h + ((int64_t)b * T + kl) * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    hb[i] = 0.f;
+    stf(hb + i, 0.f);
 }
 
 }  // namespace
 
-extern "C" int sib_layernorm_f32(const float* x, const float* residual, const float* gamma, const float* beta,
-                                 float* y, int64_t rows, int c, float eps, int post_act, sib_stream_t stream) {
-  SIB_REQUIRE(x && gamma && beta && y && rows > 0 && c > 0, "sib_layernorm_f32: bad argument");
-  SIB_REQUIRE(c <= 4096, "sib_layernorm_f32: c=%d > 4096 unsupported", c);
-  SIB_REQUIRE(post_act == SIB_ACT_NONE || post_act == SIB_ACT_GELU, "sib_layernorm_f32: unsupported post_act");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+namespace {
+template <typename TX, typename TR, typename TY>
+int launch_ln(const void* x, const void* residual, const float* gamma, const float* beta, void* y, int64_t rows, int c,
+              float eps, int post_act, cudaStream_t s) {
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const TX* xx = static_cast<const TX*>(x);
+  const TR* rr = static_cast<const TR*>(residual);
+  TY* yy = static_cast<TY*>(y);
   if (c <= 256)
-    layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, residual, gamma, beta, y, rows, c, eps, post_act);
+    layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(xx, rr, gamma, beta, yy, rows, c, eps, post_act);
   else if (c <= 512)
-    layernorm_kernel<16><<<grid, wpb * 32, 0, s>>>(x, residual, gamma, beta, y, rows, c, eps, post_act);
+    layernorm_kernel<16><<<grid, wpb * 32, 0, s>>>(xx, rr, gamma, beta, yy, rows, c, eps, post_act);
   else if (c <= 1024)
-    layernorm_kernel<32><<<grid, wpb * 32, 0, s>>>(x, residual, gamma, beta, y, rows, c, eps, post_act);
+    layernorm_kernel<32><<<grid, wpb * 32, 0, s>>>(xx, rr, gamma, beta, yy, rows, c, eps, post_act);
   else
-    layernorm_kernel<128><<<grid, wpb * 32, 0, s>>>(x, residual, gamma, beta, y, rows, c, eps, post_act);
-  SIB_CHECK_LAUNCH("sib_layernorm_f32");
+    layernorm_kernel<128><<<grid, wpb * 32, 0, s>>>(xx, rr, gamma, beta, yy, rows, c, eps, post_act);
+  return 0;
+}
+}  // namespace
+
+extern "C" int sib_layernorm(const void* x, int x_dtype, const void* residual, int r_dtype, const float* gamma,
+                             const float* beta, void* y, int y_dtype, int64_t rows, int c, float eps, int post_act,
+                             sib_stream_t stream) {
+  SIB_REQUIRE(x && gamma && beta && y && rows > 0 && c > 0, "sib_layernorm: bad argument");
+  SIB_REQUIRE(c <= 4096, "sib_layernorm: c=%d > 4096 unsupported", c);
+  SIB_REQUIRE(post_act == SIB_ACT_NONE || post_act == SIB_ACT_GELU, "sib_layernorm: unsupported post_act");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int key = (x_dtype << 2) | ((residual ? r_dtype : x_dtype) << 1) | y_dtype;
+  switch (key) {
+    case 0: launch_ln<float, float, float>(x, residual, gamma, beta, y, rows, c, eps, post_act, s); break;
+    case 1: launch_ln<float, float, __nv_bfloat16>(x, residual, gamma, beta, y, rows, c, eps, post_act, s); break;
+    case 6: launch_ln<__nv_bfloat16, __nv_bfloat16, float>(x, residual, gamma, beta, y, rows, c, eps, post_act, s); break;
+    case 7: launch_ln<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(x, residual, gamma, beta, y, rows, c, eps, post_act, s); break;
+    default: SIB_REQUIRE(false, "sib_layernorm: unsupported dtype combination x=%d r=%d y=%d", x_dtype, r_dtype, y_dtype);
+  }
+  SIB_CHECK_LAUNCH("sib_layernorm");
   return SIB_OK;
+}
+
+extern "C" int sib_layernorm_f32(const float* x, const float* residual, const float* gamma, const float* beta,
+                                 float* y, int64_t rows, int c, float eps, int post_act, sib_stream_t stream) {
+  return sib_layernorm(x, SIB_F32, residual, SIB_F32, gamma, beta, y, SIB_F32, rows, c, eps, post_act, stream);
 }
 
 extern "C" int sib_conv0_num_tiles(int t0) { return (t0 + C0_TILE - 1) / C0_TILE; }
 
-extern "C" int sib_conv0_f32(int mode, const float* wave, int batch, int n_samples, int64_t wave_batch_stride,
-                             const float* w, const float* bias, int c, int k, int stride, int t0, float* partial,
-                             const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
-                             sib_stream_t stream) {
-  SIB_REQUIRE(wave && w && batch > 0 && c > 0 && t0 > 0, "sib_conv0_f32: bad argument");
+extern "C" int sib_conv0(int mode, const float* wave, int batch, int n_samples, int64_t wave_batch_stride,
+                         const float* w, const float* bias, int c, int k, int stride, int t0, float* partial,
+                         const float* mean, const float* rstd, const float* gamma, const float* beta, void* y,
+                         int y_dtype, sib_stream_t stream) {
+  SIB_REQUIRE(wave && w && batch > 0 && c > 0 && t0 > 0, "sib_conv0: bad argument");
   SIB_REQUIRE(k > 0 && k <= C0_MAXK && stride > 0, "sib_conv0_f32: k=%d stride=%d unsupported", k, stride);
   SIB_REQUIRE((int64_t)(t0 - 1) * stride + k <= n_samples, "sib_conv0_f32: t0=%d does not fit n_samples=%d", t0, n_samples);
   SIB_REQUIRE(batch <= 65535, "sib_conv0_f32: batch too large");
@@ -220,21 +251,37 @@ extern "C" int sib_conv0_f32(int mode, const float* wave, int batch, int n_sampl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (mode == 0) {
     SIB_REQUIRE(partial, "sib_conv0_f32: mode 0 needs partial");
-    conv0_kernel<0><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0, partial,
-                                            nullptr, nullptr, nullptr, nullptr, nullptr);
+    conv0_kernel<0, float><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0, partial,
+                                                   nullptr, nullptr, nullptr, nullptr, nullptr);
   } else if (mode == 1) {
     SIB_REQUIRE(mean && rstd && gamma && beta && y, "sib_conv0_f32: mode 1 needs mean/rstd/gamma/beta/y");
-    conv0_kernel<1><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0, nullptr,
-                                            mean, rstd, gamma, beta, y);
+    if (y_dtype == SIB_BF16)
+      conv0_kernel<1, __nv_bfloat16><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0,
+                                                             nullptr, mean, rstd, gamma, beta, (__nv_bfloat16*)y);
+    else
+      conv0_kernel<1, float><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0,
+                                                     nullptr, mean, rstd, gamma, beta, (float*)y);
   } else if (mode == 2) {
     SIB_REQUIRE(y, "sib_conv0_f32: mode 2 needs y");
-    conv0_kernel<2><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0, nullptr,
-                                            nullptr, nullptr, nullptr, nullptr, y);
+    if (y_dtype == SIB_BF16)
+      conv0_kernel<2, __nv_bfloat16><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0,
+                                                             nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)y);
+    else
+      conv0_kernel<2, float><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0,
+                                                     nullptr, nullptr, nullptr, nullptr, nullptr, (float*)y);
   } else {
     SIB_REQUIRE(false, "sib_conv0_f32: unknown mode %d", mode);
   }
-  SIB_CHECK_LAUNCH("sib_conv0_f32");
+  SIB_CHECK_LAUNCH("sib_conv0");
   return SIB_OK;
+}
+
+extern "C" int sib_conv0_f32(int mode, const float* wave, int batch, int n_samples, int64_t wave_batch_stride,
+                             const float* w, const float* bias, int c, int k, int stride, int t0, float* partial,
+                             const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
+                             sib_stream_t stream) {
+  return sib_conv0(mode, wave, batch, n_samples, wave_batch_stride, w, bias, c, k, stride, t0, partial, mean, rstd, gamma,
+                   beta, y, SIB_F32, stream);
 }
 
 extern "C" int sib_gn_finalize_f32(const float* partial, int batch, int n_tiles, int c, int t0, float eps,
@@ -263,11 +310,19 @@ extern "C" int sib_zero_ranges_f32(float* wave, int batch, int n, const int32_t*
   return SIB_OK;
 }
 
+extern "C" int sib_zero_padded_frames(void* h, int dtype, const int32_t* key_len, int batch, int t, int c,
+                                      sib_stream_t stream) {
+  SIB_REQUIRE(h && key_len && batch > 0 && t > 0 && c > 0 && batch <= 65535, "sib_zero_padded_frames: bad argument");
+  dim3 grid(32, batch);
+  if (dtype == SIB_BF16)
+    zero_padded_frames_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>((__nv_bfloat16*)h, key_len, t, c);
+  else
+    zero_padded_frames_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>((float*)h, key_len, t, c);
+  SIB_CHECK_LAUNCH("sib_zero_padded_frames");
+  return SIB_OK;
+}
+
 extern "C" int sib_zero_padded_frames_f32(float* h, const int32_t* key_len, int batch, int t, int c,
                                           sib_stream_t stream) {
-  SIB_REQUIRE(h && key_len && batch > 0 && t > 0 && c > 0 && batch <= 65535, "sib_zero_padded_frames_f32: bad argument");
-  dim3 grid(32, batch);
-  zero_padded_frames_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h, key_len, t, c);
-  SIB_CHECK_LAUNCH("sib_zero_padded_frames_f32");
-  return SIB_OK;
+  return sib_zero_padded_frames(h, SIB_F32, key_len, batch, t, c, stream);
 }

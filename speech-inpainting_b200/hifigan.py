@@ -120,12 +120,94 @@ class Generator(_StateHolder):
                 P[n + ".w"] = ops.pack_conv_weight(self._weight(n))
         wp = self._weight("conv_post")  # [1, C, 7] -> [k][C]
         P["conv_post.w"] = wp[0].t().contiguous()
+        if self.precision == "bf16":
+            for k in [k for k in P if k.endswith(".w") and k != "conv_post.w"]:
+                P[k] = ops.to_kmajor_bf16(P[k])  # tcgen05 operand layout
+        elif self.precision != "fp32":
+            raise SibError(f"unknown precision {self.precision!r} (fp32 | bf16)")
         self._packed = P
         self._plans = {}
         return P
 
-    # ---- plan
+    # ---- plan (bf16 / tcgen05 arm)
+    def _build_plan_bf16(self, B: int, Tm: int, frame_major_in: bool):
+        """Same graph as `_build_plan`, bf16 activations.  The TMA-fed kernel cannot transform its A operand, so
+        every leaky_relu that precedes a conv (models.py:37,39,109,119) is produced by the PREVIOUS kernel's
+        epilogue: convs1 write only lrelu(y); ConvTranspose / convs2 write y (residual stream) and lrelu(y)."""
+        P, dev = self._pack(), self._device
+        f32 = dict(device=dev, dtype=torch.float32)
+        b16 = dict(device=dev, dtype=torch.bfloat16)
+        io = SimpleNamespace()
+        io.x_cf = None if frame_major_in else torch.empty(B, self.in_dim, Tm, **f32)
+        io.x = torch.empty(B, Tm, self.in_dim, **f32)
+        chans = [self.c0 // (2 ** (i + 1)) for i in range(self.num_upsamples)]
+        lens, L = [], Tm
+        for u in self.upsample_rates:
+            L *= u
+            lens.append(L)
+        big = max(l * c for l, c in zip(lens, chans))
+        pool = [torch.empty(B * big, **b16) for _ in range(11)]
+        UP, UPA, PA, PAA, PB, PBA, T1, XS0, XS0A, XS1, XS1A = range(11)
+
+        def view(i, L_, C_):
+            return pool[i][: B * L_ * C_].view(B, L_, C_)
+
+        plan = Plan()
+        with plan.record():
+            if not frame_major_in:
+                ops.transpose(io.x_cf, io.x)
+            xb = torch.empty(B, Tm, self.in_dim, **b16)
+            ops.cast_to_bf16(io.x, xb)
+            cur_act = torch.empty(B, Tm, self.c0, **b16)
+            ops.conv1d(xb, P["conv_pre.w"], self._sd["conv_pre.bias"], cur_act, ops.conv_taps(7, 1, 3),
+                       post_act=ops.ACT_LRELU, post_slope=LRELU_SLOPE)
+            t_in = Tm
+            for i, u in enumerate(self.upsample_rates):
+                C_, L_ = chans[i], lens[i]
+                last_stage = i == self.num_upsamples - 1
+                up, up_act = view(UP, L_, C_), view(UPA, L_, C_)
+                xs, xs_act = (view(XS0, L_, C_), view(XS0A, L_, C_)) if i % 2 == 0 else (view(XS1, L_, C_), view(XS1A, L_, C_))
+                ops.conv1d(cur_act, P[f"ups.{i}.w"], P[f"ups.{i}.b"], up.view(B, t_in, u * C_), P[f"ups.{i}.taps"],
+                           y_act=up_act.view(B, t_in, u * C_), act2_slope=LRELU_SLOPE)
+                for j, (rk, dils) in enumerate(zip(self.rb_kernels, self.rb_dilations)):
+                    n = i * self.num_kernels + j
+                    last_j = j == self.num_kernels - 1
+                    xcur, xcur_act = up, up_act
+                    for m, dl in enumerate(dils):
+                        last_m = m == len(dils) - 1
+                        if last_m:
+                            dst, dst_act = xs, (xs_act if last_j else None)
+                            # the next consumer of xs is lrelu(0.1)->ups[i+1] or lrelu(0.01)->conv_post
+                            slope2 = 0.01 if last_stage else LRELU_SLOPE
+                        else:
+                            dst, dst_act = (view(PA, L_, C_), view(PAA, L_, C_)) if m % 2 == 0 else (view(PB, L_, C_), view(PBA, L_, C_))
+                            slope2 = LRELU_SLOPE
+                        kw = dict(accumulate=last_m and j > 0, out_scale=(1.0 / self.num_kernels) if (last_m and last_j) else 1.0,
+                                  residual=xcur, y_act=dst_act, act2_slope=slope2)
+                        if self.resblock == "1":
+                            t1 = view(T1, L_, C_)
+                            ops.conv1d(xcur_act, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
+                                       t1, ops.conv_taps(rk, dl, get_padding(rk, dl)), post_act=ops.ACT_LRELU, post_slope=LRELU_SLOPE)
+                            ops.conv1d(t1, P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
+                                       dst, ops.conv_taps(rk, 1, get_padding(rk, 1)), **kw)
+                        else:
+                            ops.conv1d(xcur_act, P[f"resblocks.{n}.convs.{m}.w"], self._sd[f"resblocks.{n}.convs.{m}.bias"],
+                                       dst, ops.conv_taps(rk, dl, get_padding(rk, dl)), **kw)
+                        xcur, xcur_act = dst, dst_act
+                cur_act = xs_act
+                t_in = L_
+            io.y = torch.empty(B, 1, lens[-1], **f32)
+            # cur_act already holds lrelu(x, 0.01): conv_post reads it with an identity pre-activation (slope 1)
+            ops.conv1d_cout1(cur_act, P["conv_post.w"], self._sd["conv_post.bias"], io.y.view(B, lens[-1]), 7, 3, 1.0, ACT_TANH)
+        io.plan = plan
+        if self.use_cuda_graph:
+            plan.capture()
+        return io
+
+    # ---- plan (fp32 arm)
     def _build_plan(self, B: int, Tm: int, frame_major_in: bool):
+        if self.precision == "bf16":
+            return self._build_plan_bf16(B, Tm, frame_major_in)
         P, dev = self._pack(), self._device
         f32 = dict(device=dev, dtype=torch.float32)
         io = SimpleNamespace()

@@ -204,6 +204,12 @@ class HubertModel(_StateHolder):
             f = f"encoder.layers.{l}.feed_forward."
             P[f"l{l}.ff1.w"] = ops.pack_linear_weight(self._w(f + "intermediate_dense.weight"))
             P[f"l{l}.ff2.w"] = ops.pack_linear_weight(self._w(f + "output_dense.weight"))
+        if self.precision == "bf16":
+            # tcgen05 operand layout (K-major bf16); conv0 / norms / biases stay fp32
+            for k in [k for k in P if k.endswith(".w") and k != "conv0.w"]:
+                P[k] = ops.to_kmajor_bf16(P[k])
+        elif self.precision != "fp32":
+            raise SibError(f"unknown precision {self.precision!r} (fp32 | bf16)")
         self._packed = P
         self._plans = {}
         return P
@@ -211,7 +217,14 @@ class HubertModel(_StateHolder):
     # ---- plan
     def _build_plan(self, B: int, N: int, padded: bool, n_layers: int):
         cfg, P, dev = self.config, self._pack(), self._device
-        f32 = dict(device=dev, dtype=torch.float32)
+        bf16 = self.precision == "bf16"
+        f32 = dict(device=dev, dtype=torch.bfloat16 if bf16 else torch.float32)   # activation dtype of this plan
+        real_f32 = dict(device=dev, dtype=torch.float32)
+
+        def act_buf(b_, t_, c_):
+            # + slack: the stride-s TMA view [B, ceil(T/s), s*C] may touch one row past the last frame
+            flat = torch.zeros(b_ * t_ * c_ + 4 * c_, **f32)
+            return flat[: b_ * t_ * c_].view(b_, t_, c_)
         lens = [N]
         for k, s in zip(cfg.conv_kernel, cfg.conv_stride):
             lens.append((lens[-1] - k) // s + 1)
@@ -219,17 +232,17 @@ class HubertModel(_StateHolder):
             raise SibError(f"input of {N} samples is shorter than the receptive field of the feature encoder")
         T, H, C = lens[-1], cfg.hidden_size, cfg.conv_dim[0]
         eps = cfg.layer_norm_eps
-        io = SimpleNamespace(wave=torch.empty(B, N, **f32), key_len=torch.empty(B, dtype=torch.int32, device=dev) if padded else None)
+        io = SimpleNamespace(wave=torch.empty(B, N, **real_f32), key_len=torch.empty(B, dtype=torch.int32, device=dev) if padded else None)
         plan = Plan()
         with plan.record():
             # ---- feature encoder (HF:203-213)
             t0 = lens[1]
-            a = torch.empty(B, t0, C, **f32)
+            a = act_buf(B, t0, C)
             k0, s0 = cfg.conv_kernel[0], cfg.conv_stride[0]
             if cfg.feat_extract_norm == "group":
                 nt = ops.conv0_num_tiles(t0)
-                part = torch.empty(B, nt, C, 2, **f32)
-                mean, rstd = torch.empty(B, C, **f32), torch.empty(B, C, **f32)
+                part = torch.empty(B, nt, C, 2, **real_f32)
+                mean, rstd = torch.empty(B, C, **real_f32), torch.empty(B, C, **real_f32)
                 ops.conv0(0, io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, partial=part)
                 ops.gn_finalize(part, B, nt, C, t0, 1e-5, mean, rstd)
                 ops.conv0(1, io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, mean=mean, rstd=rstd,
@@ -238,7 +251,7 @@ class HubertModel(_StateHolder):
                 ops.conv0(2, io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, y=a)
                 ops.layernorm(a, P["conv0.g"], P["conv0.beta"], a, 1e-5, post_act=ACT_GELU)
             for i in range(1, len(cfg.conv_dim)):
-                y = torch.empty(B, lens[i + 1], cfg.conv_dim[i], **f32)
+                y = act_buf(B, lens[i + 1], cfg.conv_dim[i])
                 k, s = cfg.conv_kernel[i], cfg.conv_stride[i]
                 if cfg.feat_extract_norm == "layer":
                     ops.conv1d(a, P[f"conv{i}.w"], P[f"conv{i}.b"], y, list(range(k)), stride=s)
@@ -296,6 +309,10 @@ class HubertModel(_StateHolder):
                     ops.layernorm(tmp, ln2[0], ln2[1], h, eps, residual=nrm)
             if cfg.do_stable_layer_norm and n_layers == cfg.num_hidden_layers:
                 ops.layernorm(h, self._w("encoder.layer_norm.weight"), self._w("encoder.layer_norm.bias"), h, eps)  # HF:613
+            if bf16:
+                out32 = torch.empty(B, T, H, **real_f32)
+                ops.cast_to_f32(h, out32)
+                h = out32
         io.out = h
         io.T = T
         io.plan = plan

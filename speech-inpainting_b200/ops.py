@@ -36,6 +36,15 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def _dt(t):
+    """sib_dtype code of a tensor (SIB_F32 = 0, SIB_BF16 = 1)."""
+    if t is None or t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise SibError(f"unsupported dtype {t.dtype}")
+
+
 class Plan:
     """Recorded launch list of one forward pass over static buffers."""
 
@@ -208,8 +217,8 @@ def linear(x2d, w, bias, y2d, *, residual=None, **kw):
 
 def conv1d_cout1(x, w, bias, y, k, pad, pre_slope, post_act):
     B, T, Cc = x.shape
-    _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y")
-    _emit("sib_conv1d_cout1_f32", (_p(x), _p(w), _p(bias), _p(y), B, T, Cc, k, pad, pre_slope, post_act),
+    _chk(x, None, "x"); _chk(y, torch.float32, "y")
+    _emit("sib_conv1d_cout1", (_p(x), _dt(x), _p(w), _p(bias), _p(y), B, T, Cc, k, pad, pre_slope, post_act),
           keep=(x, w, bias, y))
 
 
@@ -217,8 +226,8 @@ def conv1d_cout1(x, w, bias, y, k, pad, pre_slope, post_act):
 def conv0(mode, wave, w, bias, c, k, stride, t0, *, partial=None, mean=None, rstd=None, gamma=None, beta=None, y=None):
     B, n = wave.shape
     _chk(wave, torch.float32, "wave")
-    _emit("sib_conv0_f32", (mode, _p(wave), B, n, wave.stride(0), _p(w), _p(bias), c, k, stride, t0, _p(partial),
-                            _p(mean), _p(rstd), _p(gamma), _p(beta), _p(y)),
+    _emit("sib_conv0", (mode, _p(wave), B, n, wave.stride(0), _p(w), _p(bias), c, k, stride, t0, _p(partial),
+                        _p(mean), _p(rstd), _p(gamma), _p(beta), _p(y), _dt(y)),
           keep=(wave, w, bias, partial, mean, rstd, gamma, beta, y))
 
 
@@ -233,20 +242,22 @@ def gn_finalize(partial, batch, n_tiles, c, t0, eps, mean, rstd):
 def layernorm(x, gamma, beta, y, eps=1e-5, residual=None, post_act=ACT_NONE):
     c = x.shape[-1]
     rows = x.numel() // c
-    _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y")
-    _emit("sib_layernorm_f32", (_p(x), _p(residual), _p(gamma), _p(beta), _p(y), rows, c, eps, post_act),
-          keep=(x, residual, gamma, beta, y))
+    _chk(x, None, "x"); _chk(y, None, "y"); _chk(gamma, torch.float32, "gamma")
+    if not (x.is_contiguous() and y.is_contiguous() and (residual is None or residual.is_contiguous())):
+        raise SibError("layernorm: tensors must be contiguous")
+    _emit("sib_layernorm", (_p(x), _dt(x), _p(residual), _dt(residual), _p(gamma), _p(beta), _p(y), _dt(y), rows, c, eps,
+                            post_act), keep=(x, residual, gamma, beta, y))
 
 
 def attention(qkv, key_len, out, heads):
     B, T, H3 = qkv.shape
-    _chk(qkv, torch.float32, "qkv"); _chk(out, torch.float32, "out"); _chk(key_len, torch.int32, "key_len")
-    _emit("sib_attention_f32", (_p(qkv), _p(key_len), _p(out), B, T, heads, H3 // 3 // heads), keep=(qkv, key_len, out))
+    _chk(qkv, None, "qkv"); _chk(out, qkv.dtype, "out"); _chk(key_len, torch.int32, "key_len")
+    _emit("sib_attention", (_p(qkv), _dt(qkv), _p(key_len), _p(out), B, T, heads, H3 // 3 // heads), keep=(qkv, key_len, out))
 
 
 def zero_padded_frames(h, key_len):
     B, T, Cc = h.shape
-    _emit("sib_zero_padded_frames_f32", (_p(h), _p(_chk(key_len, torch.int32, "key_len")), B, T, Cc), keep=(h, key_len))
+    _emit("sib_zero_padded_frames", (_p(h), _dt(h), _p(_chk(key_len, torch.int32, "key_len")), B, T, Cc), keep=(h, key_len))
 
 
 # ----------------------------------------------------------------------------- glue
@@ -300,8 +311,8 @@ def extend_mel_len(t: int) -> int:
 def extend_mel(mel, out, frame_major: bool):
     B, Dm, T = mel.shape
     tm = out.shape[1] if frame_major else out.shape[2]
-    _chk(mel, torch.float32, "mel"); _chk(out, torch.float32, "out")
-    _emit("sib_extend_mel_f32", (_p(mel), _p(out), B, Dm, T, tm, int(frame_major)), keep=(mel, out))
+    _chk(mel, torch.float32, "mel"); _chk(out, None, "out")
+    _emit("sib_extend_mel", (_p(mel), _p(out), _dt(out), B, Dm, T, tm, int(frame_major)), keep=(mel, out))
 
 
 def transpose(x, out):
