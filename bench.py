@@ -145,7 +145,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def profile_plans(sib, plans):
+def profile_plans(sib, plans, detail=None):
     """Per-launch CUDA-event timing of the recorded launch lists, aggregated per C-ABI kernel family.
     Run after the timed region; gives the dominant kernel's share and its achieved FLOP rate."""
     agg = {}
@@ -166,7 +166,15 @@ def profile_plans(sib, plans):
             a["launches"] += 1
             if name in ("sib_conv1d_f32", "sib_conv1d_bf16"):
                 d = args[0]._obj
-                a["flops"] += 2.0 * d.batch * d.t_out * d.c_out * (d.c_in // d.groups) * d.n_taps
+                fl = 2.0 * d.batch * d.t_out * d.c_out * (d.c_in // d.groups) * d.n_taps
+                a["flops"] += fl
+                if detail is not None:
+                    ms_ = e0.elapsed_time(e1)
+                    detail.append({"kernel": name, "B": d.batch, "t_out": d.t_out, "c_in": d.c_in, "c_out": d.c_out,
+                                   "groups": d.groups, "taps": d.n_taps, "stride": d.stride, "ms": round(ms_, 4),
+                                   "tflops": round(fl / ms_ / 1e9, 1) if ms_ > 0 else None})
+            elif detail is not None:
+                detail.append({"kernel": name, "ms": round(e0.elapsed_time(e1), 4)})
     return agg
 
 
@@ -180,6 +188,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-sample-utts", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write the per-launch timing table (JSON) to this path")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,7 +288,12 @@ def main():
     roofline = cpu = None
     if rank == 0:
         plans = [io.plan for io in pipe.model.base_model._plans.values()] + [io.plan for io in pipe.generator._plans.values()]
-        agg = profile_plans(sib, plans)
+        detail = [] if args.breakdown else None
+        agg = profile_plans(sib, plans, detail)
+        if args.breakdown:
+            os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
+            with open(args.breakdown, "w") as f:
+                json.dump(detail, f, indent=0)
         total_ms = sum(a["ms"] for a in agg.values())
         name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         peaks = {}
