@@ -10,9 +10,13 @@
 //   * c_in/groups in {32, 16, 48, 80, ...} (HiFi-GAN C = 32/16, pos-conv 48/group, conv_pre 80): K-block =
 //     TB taps x CC channels (CC = 32 or 16, CC*TB = 64): TB sub-tiles of 128 x CC with 64- / 32-byte swizzle,
 //     one TMA box and CC/16 MMAs each, so a pipeline stage always carries 64 K-elements.
-// Pipeline: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer, warps 2-5 =
-// epilogue (tcgen05.ld -> bias / residual / accumulate / activation -> bf16 stores).  Accumulator
-// 128 x BN fp32 lives in TMEM.  Several CTAs per SM overlap one tile's epilogue with another's mainloop.
+// Persistent kernel, one CTA per SM looping over output tiles (128 time rows x bn channels):
+//   warp 0      TMA producer: shared-memory ring of STAGES K-blocks, runs ahead across tile boundaries
+//   warp 1      TMEM owner + single-thread tcgen05.mma issuer; TWO accumulators (2 x bn TMEM columns) so the
+//               epilogue of tile i overlaps the mainloop of tile i+1
+//   warps 2-5   epilogue, warp q owns TMEM lanes / tile rows [32q, 32q+32): residual and the accumulate input are
+//               prefetched by TMA into a swizzled staging slab, tcgen05.ld -> bias / residual / accumulate /
+//               activation -> bf16 into the slab -> TMA store (coalesced, rows >= t_out clipped by the TMA unit).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -22,23 +26,26 @@ namespace {
 constexpr int BM = 128;      // time rows per CTA == UMMA M == TMEM lanes
 constexpr int BK = 64;       // bf16 elements per K-block == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                 // two per TMEM lane quarter: latency hiding in the epilogue
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 struct TcArgs {
   // epilogue
   const float* bias;
-  const __nv_bfloat16* res;
-  __nv_bfloat16* y;
-  __nv_bfloat16* y2;
-  int64_t y_bs, r_bs;
-  int y_rs, r_rs;
-  int t_out, cout_g, groups;
+  int has_res, has_y2;
+  int t_out, cout_g, groups, batch;
   int post_act, accumulate, res_after_act;
   float post_slope, out_scale, act2_slope;
+  int bn;            // tile width in output channels (multiple of 16, <= 128) == UMMA N
+  int cw, cw_shift;  // staging box width in channels (64 / 32 / 16) and its log2
+  int tiles_m, tiles_n, total_tiles;
+  int acc_stride;    // TMEM columns between the two accumulators
+  int stages, stage_bytes;
   // mainloop
   int n_chunks, n_tapblocks, tb, cc, n_taps, cin_g;
   int a_sub_bytes, b_sub_bytes;  // bytes of one (tap) sub-tile of A / B inside a stage
   uint32_t desc_hi;              // SBO / version / swizzle bits of the smem matrix descriptor (bits 32..63)
+  uint32_t idesc;
   int tap_row[SIB_MAX_TAPS];     // row coordinate delta per tap
   int tap_ch[SIB_MAX_TAPS];      // channel coordinate delta per tap (stride-s view)
 };
@@ -81,6 +88,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
 //   bits [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4 (8 rows of the
 //   swizzle width) | [46,48) version = 1 | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
@@ -108,63 +120,85 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN>
-struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
-};
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h2[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return o;
+}
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS)
+
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB of A per pipeline stage regardless of the sub-tile split
+
+template <int POST_ACT>
+__device__ __forceinline__ float act_t(float v, float slope) {
+  if (POST_ACT == SIB_ACT_GELU) return sib::gelu_erf(v);
+  if (POST_ACT == SIB_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (POST_ACT == SIB_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+template <int POST_ACT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ TcArgs p) {
-  using L = SmemLayout<BN>;
-  constexpr int STAGES = L::STAGES;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+                      const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y2,
+                      const __grid_constant__ CUtensorMap map_r, const __grid_constant__ TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  const int STAGES = p.stages;
+  const int slab_bytes = 32 * p.bn * 2;                       // one epilogue warp's 32 rows x bn bf16
+  uint8_t* stage_y = smem + STAGES * p.stage_bytes;           // 4 slabs: output (and accumulate input)
+  uint8_t* stage_r = stage_y + 4 * slab_bytes;                // 4 slabs: residual input / second output
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_r + 4 * slab_bytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint64_t* res_bar = tmem_empty_bar + 2;         // [4] one per epilogue warp
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
-  const int b = blockIdx.z / p.groups, g = blockIdx.z % p.groups;
   const int iters = p.n_chunks * p.n_tapblocks;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], NUM_EPI_WARPS);  // one arrive per epilogue warp
+    }
+    for (int s = 0; s < 4; ++s) mbar_init(&res_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const uint32_t tmem_cols = 2 * p.acc_stride;  // power of two >= 32 (host guarantees)
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "r"((uint32_t)TMEM_COLS)
+                 "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -173,153 +207,195 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
 
+  // tile -> (n fastest, m, batch*group): CTAs that run concurrently share the same A rows in L2
+  auto decode = [&](int tile, int& t0, int& n0, int& b, int& g) {
+    const int nt = tile % p.tiles_n;
+    const int rest = tile / p.tiles_n;
+    const int mt = rest % p.tiles_m;
+    const int z = rest / p.tiles_m;
+    t0 = mt * BM;
+    n0 = nt * p.bn;
+    b = z / p.groups;
+    g = z - b * p.groups;
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        const int cc = it / p.n_tapblocks, tb = it - cc * p.n_tapblocks;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + L::A_BYTES;
-        const int nsub = min(p.tb, p.n_taps - tb * p.tb);
-        mbar_expect_tx(&full_bar[stage], (uint32_t)nsub * (uint32_t)(p.a_sub_bytes + p.b_sub_bytes));
-        for (int sidx = 0; sidx < nsub; ++sidx) {
-          const int j = tb * p.tb + sidx;
-          tma_load_3d(a_dst + sidx * p.a_sub_bytes, &map_a, &full_bar[stage], g * p.cin_g + cc * p.cc + p.tap_ch[j],
-                      t0 + p.tap_row[j], b);
-          tma_load_2d(b_dst + sidx * p.b_sub_bytes, &map_b, &full_bar[stage], (cc * p.n_taps + j) * p.cc,
-                      g * p.cout_g + n0);
-        }
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int t0, n0, b, g;
+        decode(tile, t0, n0, b, g);
+        for (int it = 0; it < iters; ++it) {
+          const int cc = it / p.n_tapblocks, tb = it - cc * p.n_tapblocks;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * p.stage_bytes;
+          uint8_t* b_dst = a_dst + A_STAGE_BYTES;
+          const int nsub = min(p.tb, p.n_taps - tb * p.tb);
+          mbar_expect_tx(&full_bar[stage], (uint32_t)nsub * (uint32_t)(p.a_sub_bytes + p.b_sub_bytes));
+          for (int sidx = 0; sidx < nsub; ++sidx) {
+            const int j = tb * p.tb + sidx;
+            tma_load_3d(a_dst + sidx * p.a_sub_bytes, &map_a, &full_bar[stage], g * p.cin_g + cc * p.cc + p.tap_ch[j],
+                        t0 + p.tap_row[j], b);
+            tma_load_2d(b_dst + sidx * p.b_sub_bytes, &map_b, &full_bar[stage], (cc * p.n_taps + j) * p.cc,
+                        g * p.cout_g + n0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int ksteps = p.cc / UMMA_K;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + L::A_BYTES;
-        const int tb = it % p.n_tapblocks;
-        const int nsub = min(p.tb, p.n_taps - tb * p.tb);
-        const int ksteps = p.cc / UMMA_K;
-        for (int sidx = 0; sidx < nsub; ++sidx) {
-          const uint64_t adesc = make_smem_desc(a_addr + sidx * p.a_sub_bytes, p.desc_hi);
-          const uint64_t bdesc = make_smem_desc(b_addr + sidx * p.b_sub_bytes, p.desc_hi);
-          for (int k = 0; k < ksteps; ++k) {
-            // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sidx | k) ? 1u : 0u);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const int tb = it % p.n_tapblocks;
+          const int nsub = min(p.tb, p.n_taps - tb * p.tb);
+          for (int sidx = 0; sidx < nsub; ++sidx) {
+            const uint64_t adesc = make_smem_desc(a_addr + sidx * p.a_sub_bytes, p.desc_hi);
+            const uint64_t bdesc = make_smem_desc(b_addr + sidx * p.b_sub_bytes, p.desc_hi);
+            for (int k = 0; k < ksteps; ++k) {
+              // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, (it | sidx | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ===================== epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) =====================
+    // ===================== epilogue: warps (q, q+4) share TMEM lanes / tile rows [32q, 32q+32) ============
+    // and split the 16-column chunks between them (even / odd); warp `half == 0` drives the TMA traffic.
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int t = t0 + row;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool row_ok = t < p.t_out;
-    const int64_t y_off = (int64_t)b * p.y_bs + (int64_t)t * p.y_rs + (int64_t)g * p.cout_g;
-    const int64_t r_off = (int64_t)b * p.r_bs + (int64_t)t * p.r_rs + (int64_t)g * p.cout_g;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);  // warp-collective: no divergence here
-      if (!row_ok) continue;
-#pragma unroll
-      for (int c8 = 0; c8 < 32; c8 += 8) {
-        const int n = n0 + c0 + c8;
-        if (n >= p.cout_g) break;
-        float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c8 + i]);
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (n + i < p.cout_g) f[i] += __ldg(p.bias + g * p.cout_g + n + i);
+    const int half = (warp - 2) >> 2;
+    uint8_t* slab_y = stage_y + q * slab_bytes;
+    uint8_t* slab_r = stage_r + q * slab_bytes;
+    const int row_bytes = p.cw * 2;                  // 128 / 64 / 32: also the TMA swizzle width of the slab boxes
+    const int box_bytes = 32 * row_bytes;
+    const int chunks_per_row = row_bytes >> 4;       // 16-byte chunks per box row
+    const int swz_shift = row_bytes == 128 ? 0 : (row_bytes == 64 ? 1 : 2);
+    const uint32_t swz = ((uint32_t)lane >> swz_shift) & (uint32_t)(chunks_per_row - 1);
+    const int nboxes = p.bn >> p.cw_shift;
+    const bool prefetch = p.has_res || p.accumulate;
+    const uint32_t pre_bytes = (uint32_t)((p.has_res ? 1 : 0) + (p.accumulate ? 1 : 0)) * (uint32_t)slab_bytes;
+    const uint32_t pair_bar = 1 + q;                 // named barrier of the warp pair (64 threads)
+    int acc = 0;
+    uint32_t acc_phase = 0, res_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int t0, n0, b, g;
+      decode(tile, t0, n0, b, g);
+      const int r0 = t0 + q * 32;
+      const int ch0 = g * p.cout_g + n0;
+      if (prefetch && half == 0 && lane == 0) {
+        mbar_expect_tx(&res_bar[q], pre_bytes);
+        for (int bx = 0; bx < nboxes; ++bx) {
+          if (p.has_res) tma_load_3d(slab_r + bx * box_bytes, &map_r, &res_bar[q], ch0 + bx * p.cw, r0, b);
+          if (p.accumulate) tma_load_3d(slab_y + bx * box_bytes, &map_y, &res_bar[q], ch0 + bx * p.cw, r0, b);
         }
-        const bool full8 = (n + 8 <= p.cout_g);
-        float r[8];
-        bool have_r = false;
-        if (p.res) {
-          have_r = true;
-          if (full8) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(p.res + r_off + n);
-            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (prefetch) {
+        mbar_wait(&res_bar[q], res_phase);
+        res_phase ^= 1;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+#pragma unroll 1
+      for (int c0 = half * 16; c0 < p.bn; c0 += 32) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 ff = __bfloat1622float2(r2[i]);
-              r[2 * i] = ff.x;
-              r[2 * i + 1] = ff.y;
-            }
-          } else {
+        for (int h = 0; h < 2; ++h) {
+          const int col = c0 + 8 * h;
+          const int bx = col >> p.cw_shift;
+          const uint32_t chunk = (uint32_t)((col - (bx << p.cw_shift)) >> 3);
+          const uint32_t off = (uint32_t)(bx * box_bytes + lane * row_bytes) + ((chunk ^ swz) << 4);
+          float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = (n + i < p.cout_g) ? __bfloat162float(p.res[r_off + n + i]) : 0.f;
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]);
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + col + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
           }
-          if (!p.res_after_act) {
+          float r[8];
+          if (p.has_res) {
+            unpack8(*reinterpret_cast<const uint4*>(slab_r + off), r);
+            if (!p.res_after_act) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += r[i];
+            }
+          }
+          if (p.accumulate) {
+            float o[8];
+            unpack8(*reinterpret_cast<const uint4*>(slab_y + off), o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += o[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = act_t<POST_ACT>(f[i] * p.out_scale, p.post_slope);
+          if (p.has_res && p.res_after_act) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] += r[i];
           }
-        }
-        if (p.accumulate) {
+          *reinterpret_cast<uint4*>(slab_y + off) = pack8(f);
+          if (p.has_y2) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (n + i < p.cout_g) f[i] += __bfloat162float(p.y[y_off + n + i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          f[i] = sib::apply_act(f[i] * p.out_scale, p.post_act, p.post_slope);
-          if (have_r && p.res_after_act) f[i] += r[i];
-        }
-        if (full8) {
-          uint4 o;
-          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-          *reinterpret_cast<uint4*>(p.y + y_off + n) = o;
-          if (p.y2) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float a0 = f[2 * i] > 0.f ? f[2 * i] : f[2 * i] * p.act2_slope;
-              const float a1 = f[2 * i + 1] > 0.f ? f[2 * i + 1] : f[2 * i + 1] * p.act2_slope;
-              o2[i] = __floats2bfloat162_rn(a0, a1);
-            }
-            *reinterpret_cast<uint4*>(p.y2 + y_off + n) = o;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (n + i >= p.cout_g) break;
-            p.y[y_off + n + i] = __float2bfloat16_rn(f[i]);
-            if (p.y2) p.y2[y_off + n + i] = __float2bfloat16_rn(f[i] > 0.f ? f[i] : f[i] * p.act2_slope);
+            for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * p.act2_slope;
+            *reinterpret_cast<uint4*>(slab_r + off) = pack8(f);
           }
         }
       }
+      // accumulator drained: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+      // slab -> global through the async proxy, once both warps of the pair have written their columns
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      if (half == 0 && lane == 0) {
+        for (int bx = 0; bx < nboxes; ++bx) {
+          tma_store_3d(&map_y, slab_y + bx * box_bytes, ch0 + bx * p.cw, r0, b);
+          if (p.has_y2) tma_store_3d(&map_y2, slab_r + bx * box_bytes, ch0 + bx * p.cw, r0, b);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // slabs reusable for the next tile
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
     }
+    if (half == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -360,22 +436,6 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
   return SIB_OK;
 }
 
-template <int BN>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, dim3 grid, cudaStream_t s) {
-  using L = SmemLayout<BN>;
-  static bool attr_set = false;  // benign race: idempotent
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-    if (e != cudaSuccess) {
-      sib::set_error("sib_conv1d_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return SIB_ERR_CUDA;
-    }
-    attr_set = true;
-  }
-  conv1d_bf16_tc_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, s>>>(ma, mb, a);
-  return SIB_OK;
-}
-
 }  // namespace
 
 extern "C" int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb) {
@@ -395,41 +455,59 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   SIB_REQUIRE(d->n_taps > 0 && d->n_taps <= SIB_MAX_TAPS, "sib_conv1d_bf16: n_taps=%d out of range", d->n_taps);
   SIB_REQUIRE(d->pre_act == SIB_ACT_NONE, "sib_conv1d_bf16: pre-activation is not available on the TMA path; "
                                           "have the producer write the activated tensor (y_act)");
-  SIB_REQUIRE((int64_t)d->batch * d->groups <= 65535, "sib_conv1d_bf16: batch*groups too large for grid.z");
   const int cin_g = d->c_in / d->groups, cout_g = d->c_out / d->groups;
   int cc, tb;
   if (int rc = sib_conv1d_bf16_kblock(cin_g, &cc, &tb)) return rc;
-  SIB_REQUIRE(cout_g % 8 == 0, "sib_conv1d_bf16: c_out/groups=%d must be a multiple of 8", cout_g);
+  SIB_REQUIRE(cout_g % 16 == 0, "sib_conv1d_bf16: c_out/groups=%d must be a multiple of 16", cout_g);
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
   SIB_REQUIRE(d->x_row_stride % 8 == 0 && d->x_batch_stride % 8 == 0 && d->y_row_stride % 8 == 0 &&
-                  d->y_batch_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                  d->y_batch_stride % 8 == 0 && al16(x) && al16(y) && al16(w),
               "sib_conv1d_bf16: x / y / w must be 16-byte aligned with strides that are multiples of 8 elements");
-  SIB_REQUIRE(!residual || ((reinterpret_cast<uintptr_t>(residual) & 15) == 0 && d->r_row_stride % 8 == 0 &&
-                            d->r_batch_stride % 8 == 0),
+  SIB_REQUIRE(!residual || (al16(residual) && d->r_row_stride % 8 == 0 && d->r_batch_stride % 8 == 0),
               "sib_conv1d_bf16: residual must be 16-byte aligned with strides that are multiples of 8 elements");
-  SIB_REQUIRE(!y_act || (reinterpret_cast<uintptr_t>(y_act) & 15) == 0, "sib_conv1d_bf16: y_act must be 16-byte aligned");
+  SIB_REQUIRE(!y_act || al16(y_act), "sib_conv1d_bf16: y_act must be 16-byte aligned (it shares y's strides)");
+  SIB_REQUIRE(!bias || al16(bias), "sib_conv1d_bf16: bias must be 16-byte aligned");
+
+  // tile width: the largest multiple of 16 that is <= 128 and divides c_out/groups (== UMMA N)
+  int bn = 0;
+  for (int cand = 128; cand >= 16; cand -= 16)
+    if (cout_g % cand == 0) { bn = cand; break; }
+  const int cw = bn % 64 == 0 ? 64 : (bn % 32 == 0 ? 32 : 16);
 
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.bias = bias;
-  a.res = static_cast<const __nv_bfloat16*>(residual);
-  a.y = static_cast<__nv_bfloat16*>(y);
-  a.y2 = static_cast<__nv_bfloat16*>(y_act);
-  a.y_bs = d->y_batch_stride; a.r_bs = d->r_batch_stride; a.y_rs = d->y_row_stride; a.r_rs = d->r_row_stride;
-  a.t_out = d->t_out; a.cout_g = cout_g; a.groups = d->groups;
+  a.has_res = residual != nullptr;
+  a.has_y2 = y_act != nullptr;
+  a.t_out = d->t_out; a.cout_g = cout_g; a.groups = d->groups; a.batch = d->batch;
   a.post_act = d->post_act; a.accumulate = d->accumulate; a.res_after_act = d->res_after_act;
   a.post_slope = d->post_slope; a.out_scale = d->out_scale; a.act2_slope = d->act2_slope;
+  a.bn = bn; a.cw = cw; a.cw_shift = cw == 64 ? 6 : (cw == 32 ? 5 : 4);
+  a.tiles_m = sib::ceil_div(d->t_out, BM);
+  a.tiles_n = cout_g / bn;
+  const int64_t total = (int64_t)a.tiles_m * a.tiles_n * d->batch * d->groups;
+  SIB_REQUIRE(total < (1ll << 31), "sib_conv1d_bf16: too many tiles");
+  a.total_tiles = (int)total;
+  a.acc_stride = bn <= 16 ? 16 : (bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
   a.cc = cc; a.tb = tb; a.cin_g = cin_g;
   a.n_chunks = cin_g / cc;
   a.n_tapblocks = (d->n_taps + tb - 1) / tb;
   a.n_taps = d->n_taps;
   const int row_bytes = cc * 2;  // one K-row of a sub-tile == the swizzle width (128 / 64 / 32 bytes)
   a.desc_hi = make_desc_hi(row_bytes);
-  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  const int bn = cout_g >= 128 ? 128 : (cout_g > 32 ? 64 : 32);
+  a.idesc = make_idesc(bn);
+  auto swz_of = [](int rb) {
+    return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  };
   a.a_sub_bytes = BM * row_bytes;
   a.b_sub_bytes = bn * row_bytes;
+  a.stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+  const int slab_total = 2 * 4 * 32 * bn * 2;  // y + r staging, 4 epilogue warps
+  const int max_smem = 227 * 1024 - 2048;
+  a.stages = (max_smem - slab_total - 1024) / a.stage_bytes;
+  if (a.stages > 8) a.stages = 8;
+  SIB_REQUIRE(a.stages >= 2, "sib_conv1d_bf16: shared memory budget too small");
+  const int smem_bytes = a.stages * a.stage_bytes + slab_total + 1024 /*barriers*/ + 1024 /*alignment slack*/;
 
   const int s = d->stride;
   SIB_REQUIRE(s >= 1, "sib_conv1d_bf16: stride must be positive");
@@ -450,29 +528,69 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     a.tap_row[j] = qd;
     a.tap_ch[j] = (off - qd * s) * d->c_in;
   }
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_y, map_y2, map_r;
   {
     // A viewed as [batch][ceil(t_in/s)][s*c_in]; for s>1 the last (partial) row may extend past t_in: the caller
     // guarantees those bytes are readable (see header) - they only feed masked outputs.
     const cuuint64_t dims[3] = {(cuuint64_t)d->c_in * s, (cuuint64_t)((d->t_in + s - 1) / s), (cuuint64_t)d->batch};
     const cuuint64_t strides[3] = {2, (cuuint64_t)d->x_row_stride * s * 2, (cuuint64_t)d->x_batch_stride * 2};
     const cuuint32_t box[3] = {(cuuint32_t)cc, BM, 1};
-    if (int rc = encode_map(&map_a, x, 3, dims, strides, box, swz, "A")) return rc;
+    if (int rc = encode_map(&map_a, x, 3, dims, strides, box, swz_of(row_bytes), "A")) return rc;
   }
   {
     const cuuint64_t ktot = (cuuint64_t)a.n_chunks * d->n_taps * cc;
     const cuuint64_t dims[2] = {ktot, (cuuint64_t)d->c_out};
     const cuuint64_t strides[2] = {2, ktot * 2};
     const cuuint32_t box[2] = {(cuuint32_t)cc, (cuuint32_t)bn};
-    if (int rc = encode_map(&map_b, w, 2, dims, strides, box, swz, "B")) return rc;
+    if (int rc = encode_map(&map_b, w, 2, dims, strides, box, swz_of(row_bytes), "B")) return rc;
   }
-  dim3 grid(sib::ceil_div(d->t_out, BM), sib::ceil_div(cout_g, bn), d->batch * d->groups);
+  {
+    // output / residual slabs: boxes of 32 rows x cw channels, swizzle width = cw*2 bytes
+    const cuuint64_t dims[3] = {(cuuint64_t)d->c_out, (cuuint64_t)d->t_out, (cuuint64_t)d->batch};
+    const cuuint64_t ys[3] = {2, (cuuint64_t)d->y_row_stride * 2, (cuuint64_t)d->y_batch_stride * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)cw, 32, 1};
+    if (int rc = encode_map(&map_y, y, 3, dims, ys, box, swz_of(cw * 2), "Y")) return rc;
+    if (int rc = encode_map(&map_y2, y_act ? y_act : y, 3, dims, ys, box, swz_of(cw * 2), "Y2")) return rc;
+    const cuuint64_t rs[3] = {2, (cuuint64_t)(residual ? d->r_row_stride : d->y_row_stride) * 2,
+                              (cuuint64_t)(residual ? d->r_batch_stride : d->y_batch_stride) * 2};
+    if (int rc = encode_map(&map_r, residual ? residual : y, 3, dims, rs, box, swz_of(cw * 2), "R")) return rc;
+  }
+  static int sm_count[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && sm_count[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    const void* fns[4] = {(const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU>,
+                          (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH>};
+    for (const void* fn : fns) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) {
+        sib::set_error("sib_conv1d_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return SIB_ERR_CUDA;
+      }
+    }
+    sm_count[dev] = n > 0 ? n : 148;
+  }
+  const int nsm = (dev >= 0 && dev < 64) ? sm_count[dev] : 148;
+  const int grid = a.total_tiles < nsm ? a.total_tiles : nsm;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  int rc;
-  if (bn == 128) rc = launch_tc<128>(map_a, map_b, a, grid, cs);
-  else if (bn == 64) rc = launch_tc<64>(map_a, map_b, a, grid, cs);
-  else rc = launch_tc<32>(map_a, map_b, a, grid, cs);
-  if (rc) return rc;
+  switch (d->post_act) {
+    case SIB_ACT_NONE:
+      conv1d_bf16_tc_kernel<SIB_ACT_NONE><<<grid, NUM_THREADS, smem_bytes, cs>>>(map_a, map_b, map_y, map_y2, map_r, a);
+      break;
+    case SIB_ACT_GELU:
+      conv1d_bf16_tc_kernel<SIB_ACT_GELU><<<grid, NUM_THREADS, smem_bytes, cs>>>(map_a, map_b, map_y, map_y2, map_r, a);
+      break;
+    case SIB_ACT_LRELU:
+      conv1d_bf16_tc_kernel<SIB_ACT_LRELU><<<grid, NUM_THREADS, smem_bytes, cs>>>(map_a, map_b, map_y, map_y2, map_r, a);
+      break;
+    case SIB_ACT_TANH:
+      conv1d_bf16_tc_kernel<SIB_ACT_TANH><<<grid, NUM_THREADS, smem_bytes, cs>>>(map_a, map_b, map_y, map_y2, map_r, a);
+      break;
+    default:
+      SIB_REQUIRE(false, "sib_conv1d_bf16: unknown post_act %d", d->post_act);
+  }
   SIB_CHECK_LAUNCH("sib_conv1d_bf16");
   return SIB_OK;
 }
