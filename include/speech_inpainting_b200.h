@@ -149,7 +149,8 @@ int sib_mel_spectrogram_f32(const float* wave, int batch, int n, int hop, int pa
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core path (tcgen05 + TMA), see DESIGN.md.  Same contract as sib_conv1d_f32 with
  * bf16 x / w / y / residual, fp32 bias and accumulation, no pre-activation (producers write y_act instead).
- * w layout (K-major): [groups][c_out/g][c_in/g / cc][n_taps][cc]  (cc from sib_conv1d_bf16_kblock).
+ * w layout: [groups][c_in/g / cc][n_taps][c_out/g][cc] - one K-major slab per (channel chunk, tap); cc from
+ * sib_conv1d_bf16_kblock.
  * Requires c_in/groups % 16 == 0, c_out/groups % 8 == 0.  stride > 1: valid convolution, groups = 1, dense rows, and
  * x readable up to ceil(t_in/stride)*stride rows in the last batch item.
  * ------------------------------------------------------------------------------------------ */

@@ -18,6 +18,7 @@
 //               prefetched by TMA into a swizzled staging slab, tcgen05.ld -> bias / residual / accumulate /
 //               activation -> bf16 into the slab -> TMA store (coalesced, rows >= t_out clipped by the TMA unit).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -27,7 +28,8 @@ constexpr int BM = 128;      // time rows per CTA == UMMA M == TMEM lanes
 constexpr int BK = 64;       // bf16 elements per K-block == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;                 // two per TMEM lane quarter: latency hiding in the epilogue
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int EPI_WARP0 = 4;                     // warps 0-3: A producer, MMA issuer, B producer, spare
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 
 struct TcArgs {
   // epilogue
@@ -40,7 +42,13 @@ struct TcArgs {
   int cw, cw_shift;  // staging box width in channels (64 / 32 / 16) and its log2
   int tiles_m, tiles_n, total_tiles;
   int acc_stride;    // TMEM columns between the two accumulators
-  int stages, stage_bytes;
+  int stages, stage_bytes;        // mode 0: combined A+B ring
+  // mode 1 ("halo"): the A ring holds one (128 + span) x cc halo tile per channel chunk; every tap is a row-shifted
+  // view of it.  B (weights) either streams through its own ring (tg taps per stage) or stays resident.
+  int mode, rows_h, tap_step, off0;
+  int a_stages, a_stage_bytes, b_stages, b_stage_bytes, b_tap_bytes, tg, b_resident, b_region_bytes;
+  int ring_bytes;                 // bytes of all operand rings (slabs start here)
+  int slab_depth;                 // epilogue staging ring depth D: residual prefetched D-1 tiles ahead
   // mainloop
   int n_chunks, n_tapblocks, tb, cc, n_taps, cin_g;
   int a_sub_bytes, b_sub_bytes;  // bytes of one (tap) sub-tile of A / B inside a stage
@@ -87,6 +95,9 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
@@ -149,7 +160,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB of A per pipeline stage regardless of the sub-tile split
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // mode 0: 16 KB of A per pipeline stage regardless of the sub-tile split
+constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 16, MAX_SLAB_DEPTH = 4;
 
 template <int POST_ACT>
 __device__ __forceinline__ float act_t(float v, float slope) {
@@ -166,33 +178,38 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                       const __grid_constant__ CUtensorMap map_r, const __grid_constant__ TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int STAGES = p.stages;
-  const int slab_bytes = 32 * p.bn * 2;                       // one epilogue warp's 32 rows x bn bf16
-  uint8_t* stage_y = smem + STAGES * p.stage_bytes;           // 4 slabs: output (and accumulate input)
-  uint8_t* stage_r = stage_y + 4 * slab_bytes;                // 4 slabs: residual input / second output
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_r + 4 * slab_bytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint64_t* res_bar = tmem_empty_bar + 2;         // [4] one per epilogue warp
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4);
+  const int slab_bytes = 32 * p.bn * 2;                       // one epilogue warp-pair's 32 rows x bn bf16
+  uint8_t* b_region = smem + p.a_stages * p.a_stage_bytes;    // mode 1 only
+  uint8_t* stage_y = smem + p.ring_bytes;                     // D x 4 slabs: output (and accumulate input)
+  uint8_t* stage_r = stage_y + p.slab_depth * 4 * slab_bytes; // D x 4 slabs: residual input / second output
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(stage_r + p.slab_depth * 4 * slab_bytes);
+  uint64_t* a_empty = a_full + MAX_A_STAGES;
+  uint64_t* b_full = a_empty + MAX_A_STAGES;
+  uint64_t* b_empty = b_full + MAX_B_STAGES;
+  uint64_t* tmem_full_bar = b_empty + MAX_B_STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint64_t* res_bar = tmem_empty_bar + 2;            // [4 pairs][MAX_SLAB_DEPTH]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4 * MAX_SLAB_DEPTH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int iters = p.n_chunks * p.n_tapblocks;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < MAX_A_STAGES; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < MAX_B_STAGES; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < 4 * MAX_SLAB_DEPTH; ++s) mbar_init(&res_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t tmem_cols = 2 * p.acc_stride;  // power of two >= 32 (host guarantees)
@@ -218,32 +235,68 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     b = z / p.groups;
     g = z - b * p.groups;
   };
+  const int row_bytes_k = p.cc * 2;        // bytes of one K-row of an operand sub-tile (= its swizzle width)
+  const int ksteps = p.cc / UMMA_K;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== A producer (mode 0: A and B of every K-block) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int t0, n0, b, g;
         decode(tile, t0, n0, b, g);
-        for (int it = 0; it < iters; ++it) {
-          const int cc = it / p.n_tapblocks, tb = it - cc * p.n_tapblocks;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* a_dst = smem + stage * p.stage_bytes;
-          uint8_t* b_dst = a_dst + A_STAGE_BYTES;
-          const int nsub = min(p.tb, p.n_taps - tb * p.tb);
-          mbar_expect_tx(&full_bar[stage], (uint32_t)nsub * (uint32_t)(p.a_sub_bytes + p.b_sub_bytes));
-          for (int sidx = 0; sidx < nsub; ++sidx) {
-            const int j = tb * p.tb + sidx;
-            tma_load_3d(a_dst + sidx * p.a_sub_bytes, &map_a, &full_bar[stage], g * p.cin_g + cc * p.cc + p.tap_ch[j],
-                        t0 + p.tap_row[j], b);
-            tma_load_2d(b_dst + sidx * p.b_sub_bytes, &map_b, &full_bar[stage], (cc * p.n_taps + j) * p.cc,
-                        g * p.cout_g + n0);
+        if (p.mode == 1) {
+          for (int cc = 0; cc < p.n_chunks; ++cc) {
+            mbar_wait(&a_empty[stage], phase ^ 1);
+            mbar_expect_tx(&a_full[stage], (uint32_t)(p.rows_h * row_bytes_k));
+            tma_load_3d(smem + stage * p.a_stage_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc, t0 + p.off0, b);
+            if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+        } else {
+          const int iters = p.n_chunks * p.n_tapblocks;
+          for (int it = 0; it < iters; ++it) {
+            const int cc = it / p.n_tapblocks, tb = it - cc * p.n_tapblocks;
+            mbar_wait(&a_empty[stage], phase ^ 1);
+            uint8_t* a_dst = smem + stage * p.stage_bytes;
+            uint8_t* b_dst = a_dst + A_STAGE_BYTES;
+            const int nsub = min(p.tb, p.n_taps - tb * p.tb);
+            mbar_expect_tx(&a_full[stage], (uint32_t)nsub * (uint32_t)(p.a_sub_bytes + p.b_sub_bytes));
+            for (int sidx = 0; sidx < nsub; ++sidx) {
+              const int j = tb * p.tb + sidx;
+              tma_load_3d(a_dst + sidx * p.a_sub_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc + p.tap_ch[j],
+                          t0 + p.tap_row[j], b);
+              tma_load_3d(b_dst + sidx * p.b_sub_bytes, &map_b, &a_full[stage], 0, n0,
+                          (g * p.n_chunks + cc) * p.n_taps + j);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== B producer (mode 1) =====================
+    if (lane == 0 && p.mode == 1) {
+      if (p.b_resident) {
+        // every tile of this launch uses the same weights: load them once (groups == 1, tiles_n == 1)
+        const int slabs = p.n_chunks * p.n_taps;
+        mbar_expect_tx(&b_full[0], (uint32_t)(((slabs + p.tg - 1) / p.tg) * p.b_stage_bytes));
+        for (int s0 = 0; s0 < slabs; s0 += p.tg)
+          tma_load_3d(b_region + (s0 / p.tg) * p.b_stage_bytes, &map_b, &b_full[0], 0, 0, s0);
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          int t0, n0, b, g;
+          decode(tile, t0, n0, b, g);
+          for (int cc = 0; cc < p.n_chunks; ++cc) {
+            for (int j0 = 0; j0 < p.n_taps; j0 += p.tg) {
+              mbar_wait(&b_empty[stage], phase ^ 1);
+              mbar_expect_tx(&b_full[stage], (uint32_t)p.b_stage_bytes);
+              tma_load_3d(b_region + stage * p.b_stage_bytes, &map_b, &b_full[stage], 0, n0,
+                          (g * p.n_chunks + cc) * p.n_taps + j0);
+              if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -251,34 +304,79 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, bstage = 0;
+      uint32_t phase = 0, bphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const int ksteps = p.cc / UMMA_K;
+      if (p.mode == 1 && p.b_resident) {
+        mbar_wait(&b_full[0], 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-          const int tb = it % p.n_tapblocks;
-          const int nsub = min(p.tb, p.n_taps - tb * p.tb);
-          for (int sidx = 0; sidx < nsub; ++sidx) {
-            const uint64_t adesc = make_smem_desc(a_addr + sidx * p.a_sub_bytes, p.desc_hi);
-            const uint64_t bdesc = make_smem_desc(b_addr + sidx * p.b_sub_bytes, p.desc_hi);
-            for (int k = 0; k < ksteps; ++k) {
-              // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, (it | sidx | k) ? 1u : 0u);
+        if (p.mode == 1) {
+          // descriptor arithmetic is strength-reduced: this single thread paces every MMA of the SM
+          const uint32_t b_base = smem_u32(b_region);
+          const uint64_t a_tap_inc = (uint64_t)((p.tap_step * row_bytes_k) >> 4);   // next tap = shifted rows
+          const uint64_t b_tap_inc = (uint64_t)(p.b_tap_bytes >> 4);
+          uint64_t bdesc_res = make_smem_desc(b_base, p.desc_hi);                    // resident weights: walk the slabs
+          uint32_t accum = 0;
+          for (int cc = 0; cc < p.n_chunks; ++cc) {
+            mbar_wait(&a_full[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint64_t adesc = make_smem_desc(smem_u32(smem + stage * p.a_stage_bytes), p.desc_hi);
+            if (p.b_resident) {
+              for (int j = 0; j < p.n_taps; ++j) {
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_bf16(tmem_d, adesc + 2 * k, bdesc_res + 2 * k, p.idesc, accum);
+                  accum = 1;
+                }
+                adesc += a_tap_inc;
+                bdesc_res += b_tap_inc;
+              }
+            } else {
+              int j = 0;
+              while (j < p.n_taps) {
+                mbar_wait(&b_full[bstage], bphase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint64_t bdesc = make_smem_desc(b_base + (uint32_t)(bstage * p.b_stage_bytes), p.desc_hi);
+                const int jend = min(j + p.tg, p.n_taps);
+                for (; j < jend; ++j) {
+                  for (int k = 0; k < ksteps; ++k) {
+                    umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
+                    accum = 1;
+                  }
+                  adesc += a_tap_inc;
+                  bdesc += b_tap_inc;
+                }
+                umma_commit(&b_empty[bstage]);
+                if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+              }
             }
+            umma_commit(&a_empty[stage]);
+            if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+        } else {
+          const int iters = p.n_chunks * p.n_tapblocks;
+          for (int it = 0; it < iters; ++it) {
+            mbar_wait(&a_full[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
+            const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+            const int tb = it % p.n_tapblocks;
+            const int nsub = min(p.tb, p.n_taps - tb * p.tb);
+            for (int sidx = 0; sidx < nsub; ++sidx) {
+              const uint64_t adesc = make_smem_desc(a_addr + sidx * p.a_sub_bytes, p.desc_hi);
+              const uint64_t bdesc = make_smem_desc(b_addr + sidx * p.b_sub_bytes, p.desc_hi);
+              for (int k = 0; k < ksteps; ++k) {
+                // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+                umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, (it | sidx | k) ? 1u : 0u);
+              }
+            }
+            umma_commit(&a_empty[stage]);  // frees the smem slot when these MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete
@@ -286,13 +384,12 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
+  } else if (warp >= EPI_WARP0) {
     // ===================== epilogue: warps (q, q+4) share TMEM lanes / tile rows [32q, 32q+32) ============
     // and split the 16-column chunks between them (even / odd); warp `half == 0` drives the TMA traffic.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    uint8_t* slab_y = stage_y + q * slab_bytes;
-    uint8_t* slab_r = stage_r + q * slab_bytes;
+    const int half = (warp - EPI_WARP0) >> 2;
+    const int D = p.slab_depth;
     const int row_bytes = p.cw * 2;                  // 128 / 64 / 32: also the TMA swizzle width of the slab boxes
     const int box_bytes = 32 * row_bytes;
     const int chunks_per_row = row_bytes >> 4;       // 16-byte chunks per box row
@@ -302,25 +399,39 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const bool prefetch = p.has_res || p.accumulate;
     const uint32_t pre_bytes = (uint32_t)((p.has_res ? 1 : 0) + (p.accumulate ? 1 : 0)) * (uint32_t)slab_bytes;
     const uint32_t pair_bar = 1 + q;                 // named barrier of the warp pair (64 threads)
-    int acc = 0;
-    uint32_t acc_phase = 0, res_phase = 0;
+    const bool leader = half == 0 && lane == 0;
+    uint64_t* my_res_bar = res_bar + q * MAX_SLAB_DEPTH;
+    // residual / accumulate-input prefetch of one tile into slab slot `slot` (leader lane only)
+    auto issue_prefetch = [&](int tile, int slot) {
+      int t0, n0, b, g;
+      decode(tile, t0, n0, b, g);
+      uint8_t* sy = stage_y + (slot * 4 + q) * slab_bytes;
+      uint8_t* sr = stage_r + (slot * 4 + q) * slab_bytes;
+      mbar_expect_tx(&my_res_bar[slot], pre_bytes);
+      for (int bx = 0; bx < nboxes; ++bx) {
+        if (p.has_res) tma_load_3d(sr + bx * box_bytes, &map_r, &my_res_bar[slot], g * p.cout_g + n0 + bx * p.cw, t0 + q * 32, b);
+        if (p.accumulate) tma_load_3d(sy + bx * box_bytes, &map_y, &my_res_bar[slot], g * p.cout_g + n0 + bx * p.cw, t0 + q * 32, b);
+      }
+    };
+    if (prefetch && leader) {
+      const int ahead = D > 1 ? D - 1 : 1;
+      int tile = blockIdx.x;
+      for (int k = 0; k < ahead && tile < p.total_tiles; ++k, tile += gridDim.x) issue_prefetch(tile, k % D);
+    }
+    int acc = 0, slot = 0;
+    uint32_t acc_phase = 0, res_phase_bits = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int t0, n0, b, g;
       decode(tile, t0, n0, b, g);
       const int r0 = t0 + q * 32;
       const int ch0 = g * p.cout_g + n0;
-      if (prefetch && half == 0 && lane == 0) {
-        mbar_expect_tx(&res_bar[q], pre_bytes);
-        for (int bx = 0; bx < nboxes; ++bx) {
-          if (p.has_res) tma_load_3d(slab_r + bx * box_bytes, &map_r, &res_bar[q], ch0 + bx * p.cw, r0, b);
-          if (p.accumulate) tma_load_3d(slab_y + bx * box_bytes, &map_y, &res_bar[q], ch0 + bx * p.cw, r0, b);
-        }
-      }
+      uint8_t* slab_y = stage_y + (slot * 4 + q) * slab_bytes;
+      uint8_t* slab_r = stage_r + (slot * 4 + q) * slab_bytes;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (prefetch) {
-        mbar_wait(&res_bar[q], res_phase);
-        res_phase ^= 1;
+        mbar_wait(&my_res_bar[slot], (res_phase_bits >> slot) & 1u);
+        res_phase_bits ^= 1u << slot;
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
 #pragma unroll 1
@@ -373,21 +484,30 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       // accumulator drained: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       // slab -> global through the async proxy, once both warps of the pair have written their columns
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      if (half == 0 && lane == 0) {
+      if (leader) {
         for (int bx = 0; bx < nboxes; ++bx) {
           tma_store_3d(&map_y, slab_y + bx * box_bytes, ch0 + bx * p.cw, r0, b);
           if (p.has_y2) tma_store_3d(&map_y2, slab_r + bx * box_bytes, ch0 + bx * p.cw, r0, b);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // slabs reusable for the next tile
+        // the slot written D-1 tiles from now is the one the PREVIOUS tile used (or this one when D == 1):
+        // wait until its stores have left shared memory, then refill it with the residual of tile i + D - 1
+        if (D > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (prefetch) {
+          const int ahead = D > 1 ? D - 1 : 1;
+          const long long nt = (long long)tile + (long long)ahead * gridDim.x;
+          if (nt < p.total_tiles) issue_prefetch((int)nt, D > 1 ? (slot + D - 1) % D : 0);
+        }
       }
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      if (++slot == D) slot = 0;
     }
     if (half == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -501,13 +621,68 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   };
   a.a_sub_bytes = BM * row_bytes;
   a.b_sub_bytes = bn * row_bytes;
-  a.stage_bytes = A_STAGE_BYTES + bn * BK * 2;
-  const int slab_total = 2 * 4 * 32 * bn * 2;  // y + r staging, 4 epilogue warps
-  const int max_smem = 227 * 1024 - 2048;
-  a.stages = (max_smem - slab_total - 1024) / a.stage_bytes;
-  if (a.stages > 8) a.stages = 8;
-  SIB_REQUIRE(a.stages >= 2, "sib_conv1d_bf16: shared memory budget too small");
-  const int smem_bytes = a.stages * a.stage_bytes + slab_total + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  a.b_tap_bytes = bn * row_bytes;
+  // epilogue staging ring: deep enough to hide the residual TMA latency behind D-1 tiles of work; layers whose
+  // tiles carry a long K loop and no residual keep a single slab and give the memory to the operand rings
+  const bool pre = a.has_res || a.accumulate;
+  const int kblocks = a.n_chunks * d->n_taps * cc / BK;
+  a.slab_depth = pre ? (bn <= 32 ? 4 : (bn <= 64 ? 3 : 2)) : (bn <= 64 ? 2 : (kblocks >= 8 ? 1 : 2));
+  const int slab_total = a.slab_depth * 2 * 4 * 32 * bn * 2;  // D x (y + r) staging, 4 epilogue warp pairs
+  const int avail = 227 * 1024 - 2048 - slab_total - 1024;
+
+  // ---- mode selection: "halo" mode whenever all taps are row shifts of one (128 + span)-row tile
+  a.mode = 0;
+  a.tg = 1;
+  int step = 1;
+  bool uniform = d->stride == 1;
+  if (uniform && d->n_taps > 1) {
+    step = d->tap_offset[1] - d->tap_offset[0];
+    uniform = step >= 1;
+    for (int j = 2; uniform && j < d->n_taps; ++j) uniform = (d->tap_offset[j] - d->tap_offset[j - 1]) == step;
+  }
+  const int rows_h = BM + (d->n_taps - 1) * step;
+  static const bool force_mode0 = getenv("SIB_TC_FORCE_PER_TAP") != nullptr;  // A/B switch for profiling
+  // (plain GEMMs, n_taps == 1, have nothing to share between taps: they keep the combined A+B ring of mode 0)
+  if (uniform && d->n_taps > 1 && rows_h <= 256 && !force_mode0) {
+    a.rows_h = rows_h; a.tap_step = step; a.off0 = d->tap_offset[0];
+    a.a_stage_bytes = (rows_h * row_bytes + 1023) / 1024 * 1024;
+    int tg = 16384 / a.b_tap_bytes;
+    if (tg < 1) tg = 1;
+    if (tg > d->n_taps) tg = d->n_taps;
+    const int slabs = a.n_chunks * d->n_taps;
+    const int resident_bytes = (slabs + tg - 1) / tg * tg * a.b_tap_bytes;
+    if (d->groups == 1 && a.tiles_n == 1 && resident_bytes <= 120 * 1024 && resident_bytes + 2 * a.a_stage_bytes <= avail) {
+      a.mode = 1; a.b_resident = 1; a.tg = tg; a.b_stage_bytes = tg * a.b_tap_bytes; a.b_region_bytes = resident_bytes;
+      a.b_stages = 1;
+      a.a_stages = (avail - resident_bytes) / a.a_stage_bytes;
+      if (a.a_stages > MAX_A_STAGES) a.a_stages = MAX_A_STAGES;
+    } else {
+      a.b_stage_bytes = tg * a.b_tap_bytes;
+      // split the operand budget about evenly between the A ring and the B ring
+      int as = (avail / 2) / a.a_stage_bytes;
+      if (as > a.n_chunks * 3) as = a.n_chunks * 3;   // no point in buffering more than ~3 tiles of A
+      if (as > MAX_A_STAGES) as = MAX_A_STAGES;
+      if (as < 2) as = 2;
+      for (; as >= 2 && a.mode == 0; --as) {
+        int bs = (avail - as * a.a_stage_bytes) / a.b_stage_bytes;
+        if (bs > MAX_B_STAGES) bs = MAX_B_STAGES;
+        if (bs >= 2) {
+          a.mode = 1; a.b_resident = 0; a.tg = tg; a.a_stages = as; a.b_stages = bs; a.b_region_bytes = bs * a.b_stage_bytes;
+        }
+      }
+    }
+  }
+  if (a.mode == 1) {
+    a.ring_bytes = a.a_stages * a.a_stage_bytes + a.b_region_bytes;
+  } else {
+    a.stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+    a.stages = avail / a.stage_bytes;
+    if (a.stages > MAX_A_STAGES) a.stages = MAX_A_STAGES;
+    SIB_REQUIRE(a.stages >= 2, "sib_conv1d_bf16: shared memory budget too small");
+    a.ring_bytes = a.stages * a.stage_bytes;
+    a.a_stages = 0;
+  }
+  const int smem_bytes = a.ring_bytes + slab_total + 1024 /*barriers*/ + 1024 /*alignment slack*/;
 
   const int s = d->stride;
   SIB_REQUIRE(s >= 1, "sib_conv1d_bf16: stride must be positive");
@@ -534,15 +709,15 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     // guarantees those bytes are readable (see header) - they only feed masked outputs.
     const cuuint64_t dims[3] = {(cuuint64_t)d->c_in * s, (cuuint64_t)((d->t_in + s - 1) / s), (cuuint64_t)d->batch};
     const cuuint64_t strides[3] = {2, (cuuint64_t)d->x_row_stride * s * 2, (cuuint64_t)d->x_batch_stride * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)cc, BM, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)cc, (cuuint32_t)(a.mode == 1 ? a.rows_h : BM), 1};
     if (int rc = encode_map(&map_a, x, 3, dims, strides, box, swz_of(row_bytes), "A")) return rc;
   }
   {
-    const cuuint64_t ktot = (cuuint64_t)a.n_chunks * d->n_taps * cc;
-    const cuuint64_t dims[2] = {ktot, (cuuint64_t)d->c_out};
-    const cuuint64_t strides[2] = {2, ktot * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)cc, (cuuint32_t)bn};
-    if (int rc = encode_map(&map_b, w, 2, dims, strides, box, swz_of(row_bytes), "B")) return rc;
+    // weights: [groups][c_in/g / cc][n_taps][c_out/g][cc]; one (chunk, tap) slab = the K-major B operand of one MMA group
+    const cuuint64_t dims[3] = {(cuuint64_t)cc, (cuuint64_t)cout_g, (cuuint64_t)d->groups * a.n_chunks * d->n_taps};
+    const cuuint64_t strides[3] = {2, (cuuint64_t)cc * 2, (cuuint64_t)cout_g * cc * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)cc, (cuuint32_t)bn, (cuuint32_t)a.tg};
+    if (int rc = encode_map(&map_b, w, 3, dims, strides, box, swz_of(row_bytes), "B")) return rc;
   }
   {
     // output / residual slabs: boxes of 32 rows x cw channels, swizzle width = cw*2 bytes

@@ -127,11 +127,11 @@ def kblock(c_in_per_group: int):
 
 
 def to_kmajor_bf16(w_packed: torch.Tensor) -> torch.Tensor:
-    """fp32 SIMT layout [g][taps][cin_g][cout_g] -> tcgen05 layout [g][cout_g][cin_g/cc][taps][cc] bf16
-    (K-major rows of the B operand)."""
+    """fp32 SIMT layout [g][taps][cin_g][cout_g] -> tcgen05 layout [g][cin_g/cc][taps][cout_g][cc] bf16:
+    every (channel-chunk, tap) slab is one K-major B operand [cout_g rows x cc]."""
     g, taps, cin_g, cout_g = w_packed.shape
     cc, _ = kblock(cin_g)
-    w = w_packed.permute(0, 3, 1, 2).reshape(g, cout_g, taps, cin_g // cc, cc).permute(0, 1, 3, 2, 4)
+    w = w_packed.permute(0, 1, 3, 2).reshape(g, taps, cout_g, cin_g // cc, cc).permute(0, 3, 1, 2, 4)
     return w.to(torch.bfloat16).contiguous()
 
 
