@@ -13,6 +13,8 @@ import speech_inpainting_b200 as sib  # noqa: E402
 ops = sib.ops
 # name: (B, T, Cin, Cout, k, dil, stride, residual, y_act)
 SHAPES = {
+    "bigk": (1, 16384, 8192, 4096, 1, 1, 1, False, False),
+    "bigconv": (32, 4096, 512, 512, 11, 1, 1, False, False),
     "qkv": (1, 6368, 768, 2304, 1, 1, 1, False, False),
     "ffn1": (1, 6368, 768, 3072, 1, 1, 1, False, False),
     "ffn2": (1, 6368, 3072, 768, 1, 1, 1, False, False),

@@ -172,7 +172,7 @@ __device__ __forceinline__ float act_t(float v, float slope) {
 }
 
 template <int POST_ACT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y2,
                       const __grid_constant__ CUtensorMap map_r, const __grid_constant__ TcArgs p) {
@@ -626,9 +626,13 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   // tiles carry a long K loop and no residual keep a single slab and give the memory to the operand rings
   const bool pre = a.has_res || a.accumulate;
   const int kblocks = a.n_chunks * d->n_taps * cc / BK;
-  a.slab_depth = pre ? (bn <= 32 ? 4 : (bn <= 64 ? 3 : 2)) : (bn <= 64 ? 2 : (kblocks >= 8 ? 1 : 2));
+  a.slab_depth = pre ? (bn <= 64 ? 3 : 2) : (bn <= 64 ? 2 : (kblocks >= 8 ? 1 : 2));
   const int slab_total = a.slab_depth * 2 * 4 * 32 * bn * 2;  // D x (y + r) staging, 4 epilogue warp pairs
-  const int avail = 227 * 1024 - 2048 - slab_total - 1024;
+  // narrow layers (bn <= 32: 8 KB output tiles) are bound by the per-tile latency chain of one CTA, not by any
+  // throughput: run two persistent CTAs per SM on half the shared memory each
+  const int ctas_per_sm = bn <= 32 ? 2 : 1;
+  const int smem_budget = ctas_per_sm == 2 ? 112 * 1024 : 227 * 1024;
+  const int avail = smem_budget - 2048 - slab_total - 1024;
 
   // ---- mode selection: "halo" mode whenever all taps are row shifts of one (128 + span)-row tile
   a.mode = 0;
@@ -650,9 +654,12 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     if (tg < 1) tg = 1;
     if (tg > d->n_taps) tg = d->n_taps;
     const int slabs = a.n_chunks * d->n_taps;
-    const int resident_bytes = (slabs + tg - 1) / tg * tg * a.b_tap_bytes;
+    // resident weights: split the slabs evenly over as few TMA boxes as possible (box depth <= 16 KB worth of taps)
+    const int rloads = (slabs + tg - 1) / tg;
+    const int rtg = (slabs + rloads - 1) / rloads;
+    const int resident_bytes = rloads * rtg * a.b_tap_bytes;
     if (d->groups == 1 && a.tiles_n == 1 && resident_bytes <= 120 * 1024 && resident_bytes + 2 * a.a_stage_bytes <= avail) {
-      a.mode = 1; a.b_resident = 1; a.tg = tg; a.b_stage_bytes = tg * a.b_tap_bytes; a.b_region_bytes = resident_bytes;
+      a.mode = 1; a.b_resident = 1; a.tg = rtg; a.b_stage_bytes = rtg * a.b_tap_bytes; a.b_region_bytes = resident_bytes;
       a.b_stages = 1;
       a.a_stages = (avail - resident_bytes) / a.a_stage_bytes;
       if (a.a_stages > MAX_A_STAGES) a.a_stages = MAX_A_STAGES;
@@ -748,7 +755,7 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     sm_count[dev] = n > 0 ? n : 148;
   }
   const int nsm = (dev >= 0 && dev < 64) ? sm_count[dev] : 148;
-  const int grid = a.total_tiles < nsm ? a.total_tiles : nsm;
+  const int grid = a.total_tiles < nsm * ctas_per_sm ? a.total_tiles : nsm * ctas_per_sm;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   switch (d->post_act) {
     case SIB_ACT_NONE:
