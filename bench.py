@@ -112,7 +112,8 @@ def time_cpu_reference(state, steps, warmup, sample_utts):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML in-process
+    (20 ms period) so that short timed regions still get tens of samples; `nvidia-smi` as the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -120,16 +121,50 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES through the PCI bus id
+            bus = torch.cuda.get_device_properties(index).pci_bus_id
+            self.handle = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                    self.handle = h
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda name: "Active" if r & getattr(n, name, 0) else "Not Active"  # noqa: E731
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = 0.0
+        return [str(sm), str(mx), f"{pw:.1f}", flag("nvmlClocksThrottleReasonHwSlowdown"),
+                flag("nvmlClocksThrottleReasonHwThermalSlowdown"), flag("nvmlClocksThrottleReasonSwThermalSlowdown"),
+                flag("nvmlClocksThrottleReasonSwPowerCap")]
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._halt.set()
@@ -141,8 +176,11 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_mhz_min": sm[0] if sm else None,
+                "sm_max_mhz": mx[0] if mx else None, "power_w_max": max(pw) if pw else None,
+                "reasons": sorted(reasons), "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def profile_plans(sib, plans, detail=None):
@@ -181,7 +219,7 @@ def profile_plans(sib, plans, detail=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SIB_PRECISION", "bf16"), choices=["fp32", "bf16"])
@@ -274,12 +312,14 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     n0 = sib.ops.launch_count()
+    torch.cuda.nvtx.range_push("sib_timed")  # ncu --nvtx --nvtx-include "sib_timed/" profiles exactly these launches
     ms = timed(step_device, args.steps)
+    torch.cuda.nvtx.range_pop()
     launches = sib.ops.launch_count() - n0
-    clocks = sampler.stop()
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
 
     audio_s = args.batch * SECONDS * world
     value = audio_s * args.steps / (ms / 1e3)
