@@ -1,6 +1,8 @@
 // fp32 multi-head self-attention with online softmax (HF:234-259 eager_attention_forward,
 // HF:296-345).  T <= ~500 frames, head_dim 64, additive key-padding mask expressed as key_len[b].
 // CTA = 64 queries of one (batch, head); K/V streamed in 64-key tiles through shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -175,6 +177,10 @@ __global__ void __launch_bounds__(256) attention_kernel(const TE* __restrict__ q
 
 }  // namespace
 
+// tcgen05 arm (attention_tc.cu)
+int sib_attention_bf16_tc(const void* qkv, const int32_t* key_len, void* out, int batch, int t, int heads,
+                          cudaStream_t stream);
+
 extern "C" int sib_attention(const void* qkv, int dtype, const int32_t* key_len, void* out, int batch, int t, int heads,
                              int head_dim, sib_stream_t stream) {
   SIB_REQUIRE(qkv && out && batch > 0 && t > 0 && heads > 0, "sib_attention: bad argument");
@@ -182,6 +188,9 @@ extern "C" int sib_attention(const void* qkv, int dtype, const int32_t* key_len,
   SIB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
               "sib_attention: pointers must be 16B aligned");
   SIB_REQUIRE(batch <= 65535 && heads <= 65535, "sib_attention: grid too large");
+  static const bool force_simt = getenv("SIB_ATTN_SIMT") != nullptr;  // A/B switch for profiling
+  if (dtype == SIB_BF16 && !force_simt)
+    return sib_attention_bf16_tc(qkv, key_len, out, batch, t, heads, static_cast<cudaStream_t>(stream));
   static_assert(sizeof(Smem) <= 100 * 1024, "attention smem");
   const void* fn = dtype == SIB_BF16 ? (const void*)attention_kernel<__nv_bfloat16> : (const void*)attention_kernel<float>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));

@@ -1,0 +1,246 @@
+// bf16 multi-head self-attention on the 5th-gen tensor cores (HF:234-259 eager_attention_forward, HF:296-345):
+//   out = softmax(q k^T * d^-1/2 + key-padding mask) v,   head_dim 64, T up to a few hundred frames.
+// One CTA per (128-query tile, head, utterance); keys stream in blocks of 128 with an online softmax:
+//   warp 4     TMA producer: Q tile once, then (K, V) blocks through a 2-stage ring - all boxes come straight out
+//              of the packed [B, T, 3H] projection output through ONE 3-D tensor map (channel, frame, utterance);
+//              frames past T are TMA zero fill, so no tile ever reads another utterance
+//   warp 5     single-thread tcgen05.mma issuer:  S = Q K^T  (M 128 x N keys x K 64, both operands K-major) into
+//              TMEM columns [0, 128);  O_blk = P V  (M 128 x N 64 x K keys; V is read in place as an MN-major B
+//              operand, no transpose pass) into TMEM columns [128, 192)
+//   warps 0-3  softmax: thread r owns query row r == TMEM lane r.  Two tcgen05.ld passes over S (row max, then
+//              exp2 / row sum), P goes to shared memory as bf16 in the 128-byte-swizzled K-major layout the P V
+//              MMA reads; the running output lives in registers and is rescaled per block (fp32 throughout).
+// Two CTAs fit per SM (112 KB of shared memory, 256 TMEM columns each), so one CTA's softmax overlaps the
+// other's MMAs and loads.
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace sib_tc;
+
+constexpr int HD = 64;     // head dim == one 128-byte swizzle row
+constexpr int QT = 128;    // queries per CTA == UMMA M == TMEM lanes
+constexpr int KB = 128;    // keys per block
+constexpr int KV_STAGES = 2;
+constexpr int TILE_BYTES = 128 * HD * 2;          // 16 KB: Q tile, one K block, one V block, one 64-key P chunk
+constexpr int SM_Q = 0;
+constexpr int SM_K = SM_Q + TILE_BYTES;
+constexpr int SM_V = SM_K + KV_STAGES * TILE_BYTES;
+constexpr int SM_P = SM_V + KV_STAGES * TILE_BYTES;
+constexpr int SM_BAR = SM_P + 2 * TILE_BYTES;     // 112 KB of tiles
+constexpr int SMEM_BYTES = SM_BAR + 128;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 256;               // S: [0,128)  O_blk: [128,192)
+constexpr uint32_t TMEM_O = 128;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out,
+                    const int32_t* __restrict__ key_len, int T, int heads) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* p_empty = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_empty = bars + 9;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
+  const int H = heads * HD;
+  const int kl = key_len ? max(1, min(key_len[b], T)) : T;
+  const int nblk = (kl + KB - 1) / KB;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) asm volatile("trap;");  // the swizzled tiles need 1024-byte alignment
+    prefetch_tensormap(&map_qkv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(smem + SM_Q, &map_qkv, q_full, h * HD, q0, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+        tma_load_3d(smem + SM_K + s * TILE_BYTES, &map_qkv, &kv_full[s], H + h * HD, j * KB, b);
+        tma_load_3d(smem + SM_V + s * TILE_BYTES, &map_qkv, &kv_full[s], 2 * H + h * HD, j * KB, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t DESC_HI = make_desc_hi(128);
+      const uint64_t qdesc = make_smem_desc(smem_u32(smem + SM_Q), DESC_HI);
+      const uint64_t pdesc = make_smem_desc(smem_u32(smem + SM_P), DESC_HI);
+      constexpr uint32_t IDESC_O = make_idesc_bf16(QT, HD, /*b_mn_major=*/1);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        const int nk16 = (min(KB, kl - j * KB) + 15) & ~15;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        // S = Q K^T.  (S of block j-1 has been consumed: the P V MMAs of j-1 were issued after p_full(j-1).)
+        const uint64_t kdesc = make_smem_desc(smem_u32(smem + SM_K + s * TILE_BYTES), DESC_HI);
+        const uint32_t idesc_s = make_idesc_bf16(QT, nk16);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) umma_bf16(tmem_base, qdesc + 2 * ks, kdesc + 2 * ks, idesc_s, ks > 0);
+        umma_commit(s_full);
+        // O_blk = P V
+        mbar_wait(p_full, j & 1);
+        mbar_wait(o_empty, (j & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t vdesc = make_smem_desc(smem_u32(smem + SM_V + s * TILE_BYTES), DESC_HI);
+        for (int ks = 0; ks < nk16 / 16; ++ks) {
+          // A: 16 keys = 32 bytes inside the swizzle row of P chunk ks/4;  B: 16 key rows of V = 2048 bytes further
+          const uint64_t a = pdesc + (uint64_t)((ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2);
+          const uint64_t bd = vdesc + (uint64_t)(ks * (16 * 128 >> 4));
+          umma_bf16(tmem_base + TMEM_O, a, bd, IDESC_O, ks > 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+        umma_commit(p_empty);
+      }
+    }
+  } else {
+    // ===================== softmax + output: thread r = query row r = TMEM lane r =====================
+    const int r = threadIdx.x;
+    const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t t_o = t_s + TMEM_O;
+    uint8_t* prow = smem + SM_P + r * 128;
+    const uint32_t swz = (uint32_t)(r & 7);
+    const float c = 0.125f * 1.4426950408889634f;  // d^-1/2 * log2(e)
+    float o_acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int nk = min(KB, kl - j * KB);
+      const int nk16 = (nk + 15) & ~15;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+      for (int c0 = 0; c0 < nk16; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_s + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c0 + i < nk) ? __uint_as_float(v[i]) : -INFINITY);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = fast_exp2((m_run - m_new) * c);   // exp2(-inf) = 0 on the first block
+      const float mc = m_new * c;
+      mbar_wait(p_empty, (j & 1) ^ 1);                      // the P V MMAs of block j-1 have read P
+      float sum = 0.f;
+      for (int c0 = 0; c0 < nk16; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_s + (uint32_t)c0, v);
+        float p[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          p[i] = (c0 + i < nk) ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          sum += p[i];
+        }
+        uint8_t* chunk = prow + (c0 >> 6) * TILE_BYTES;
+        const uint32_t u = (uint32_t)((c0 & 63) >> 3);
+        float lo[8], hi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { lo[i] = p[i]; hi[i] = p[8 + i]; }
+        *reinterpret_cast<uint4*>(chunk + ((u ^ swz) << 4)) = pack8(lo);
+        *reinterpret_cast<uint4*>(chunk + (((u + 1) ^ swz) << 4)) = pack8(hi);
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      tc_fence_before();
+      fence_async_smem();   // generic-proxy stores of P -> visible to the tensor core's async-proxy reads
+      mbar_arrive(p_full);
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < HD; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_o + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty);
+    }
+    if (q0 + r < T) {
+      const float inv = 1.f / l_run;
+      uint4* dst = reinterpret_cast<uint4*>(out + ((int64_t)b * T + q0 + r) * H + h * HD);
+#pragma unroll
+      for (int u = 0; u < HD / 8; ++u) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = o_acc[8 * u + i] * inv;
+        dst[u] = pack8(f);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace
+
+// bf16 arm of sib_attention (see attention_f32.cu for the dispatcher and the fp32 SIMT arm).
+int sib_attention_bf16_tc(const void* qkv, const int32_t* key_len, void* out, int batch, int t, int heads,
+                          cudaStream_t stream) {
+  const int H = heads * HD;
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)3 * H, (cuuint64_t)t, (cuuint64_t)batch};
+  const cuuint64_t strides[3] = {2, (cuuint64_t)3 * H * 2, (cuuint64_t)t * 3 * H * 2};
+  const cuuint32_t box[3] = {HD, 128, 1};
+  if (int rc = encode_map(&map, qkv, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "sib_attention", "qkv")) return rc;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      sib::set_error("sib_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return SIB_ERR_CUDA;
+    }
+    attr_set[dev] = true;
+  }
+  dim3 grid(sib::ceil_div(t, QT), heads, batch);
+  attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map, (__nv_bfloat16*)out, key_len, t, heads);
+  SIB_CHECK_LAUNCH("sib_attention");
+  return SIB_OK;
+}

@@ -14,13 +14,17 @@
 //   warp 0      TMA producer: shared-memory ring of STAGES K-blocks, runs ahead across tile boundaries
 //   warp 1      TMEM owner + single-thread tcgen05.mma issuer; TWO accumulators (2 x bn TMEM columns) so the
 //               epilogue of tile i overlaps the mainloop of tile i+1
-//   warps 2-5   epilogue, warp q owns TMEM lanes / tile rows [32q, 32q+32): residual and the accumulate input are
-//               prefetched by TMA into a swizzled staging slab, tcgen05.ld -> bias / residual / accumulate /
-//               activation -> bf16 into the slab -> TMA store (coalesced, rows >= t_out clipped by the TMA unit).
+//   warp 2      B producer (halo mode)
+//   warps 4-11  epilogue, warps (q, q+4) own TMEM lanes / tile rows [32q, 32q+32).  The tile is drained in column
+//               blocks of `cw` channels through a ring of small swizzled staging boxes (32 rows x cw): residual and
+//               accumulate inputs are prefetched by TMA `ahead` blocks in advance (across tile boundaries),
+//               tcgen05.ld -> bias / residual / accumulate / activation -> bf16 into the box -> TMA store
+//               (coalesced, rows >= t_out clipped by the TMA unit).  The ring costs 16 KB per block and tensor, which
+//               leaves the bulk of shared memory to the operand rings (latency hiding of the weight stream).
 #include <cuda.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -38,8 +42,12 @@ struct TcArgs {
   int t_out, cout_g, groups, batch;
   int post_act, accumulate, res_after_act;
   float post_slope, out_scale, act2_slope;
-  int bn;            // tile width in output channels (multiple of 16, <= 128) == UMMA N
-  int cw, cw_shift;  // staging box width in channels (64 / 32 / 16) and its log2
+  int bn;            // tile width in output channels (multiple of 16, <= 256) == UMMA N
+  int cw, cw_shift;  // epilogue block / staging box width in channels (64 / 32 / 16) and its log2
+  int nblk;          // epilogue blocks per tile = bn / cw
+  int nb;            // staging ring depth in blocks (per warp pair and tensor)
+  int ahead;         // residual / accumulate prefetch distance in blocks (<= nb - 1)
+  int need_r;        // second staging ring present (residual input and / or y_act output)
   int tiles_m, tiles_n, total_tiles;
   int acc_stride;    // TMEM columns between the two accumulators
   int stages, stage_bytes;        // mode 0: combined A+B ring
@@ -48,7 +56,6 @@ struct TcArgs {
   int mode, rows_h, tap_step, off0;
   int a_stages, a_stage_bytes, b_stages, b_stage_bytes, b_tap_bytes, tg, b_resident, b_region_bytes;
   int ring_bytes;                 // bytes of all operand rings (slabs start here)
-  int slab_depth;                 // epilogue staging ring depth D: residual prefetched D-1 tiles ahead
   // mainloop
   int n_chunks, n_tapblocks, tb, cc, n_taps, cin_g;
   int a_sub_bytes, b_sub_bytes;  // bytes of one (tap) sub-tile of A / B inside a stage
@@ -58,114 +65,33 @@ struct TcArgs {
   int tap_ch[SIB_MAX_TAPS];      // channel coordinate delta per tap (stride-s view)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace sib_tc;
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-//   bits [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4 (8 rows of the
-//   swizzle width) | [46,48) version = 1 | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
-__host__ __device__ constexpr uint32_t make_desc_hi(int row_bytes) {
-  return (uint32_t)((8 * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u)) << 29);
-}
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t desc_hi) {
-  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)desc_hi << 32);
-}
-
-// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 at 17, M>>4 at 24.
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
-  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h2[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  uint4 o;
-  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return o;
-}
-
+__host__ __device__ constexpr uint32_t make_idesc(int n) { return make_idesc_bf16(BM, n); }
 
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // mode 0: 16 KB of A per pipeline stage regardless of the sub-tile split
-constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 16, MAX_SLAB_DEPTH = 4;
+constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 16, MAX_NB = 6;
+
+// exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below
+// the bf16 rounding of the output): 1 rcp + 1 ex2 + 7 fma instead of erff's ~35 instructions - the FFN-in epilogue
+// (128 x 128 GELUs per tile) would otherwise outlast its mainloop.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erfc_abs = poly * t * e;                 // erfc(|x| / sqrt 2)
+  const float cdf = x >= 0.f ? fmaf(-0.5f, erfc_abs, 1.0f) : 0.5f * erfc_abs;
+  return x * cdf;
+}
 
 template <int POST_ACT>
 __device__ __forceinline__ float act_t(float v, float slope) {
-  if (POST_ACT == SIB_ACT_GELU) return sib::gelu_erf(v);
+  if (POST_ACT == SIB_ACT_GELU) return gelu_erf_fast(v);
   if (POST_ACT == SIB_ACT_LRELU) return v > 0.f ? v : v * slope;
   if (POST_ACT == SIB_ACT_TANH) return tanhf(v);
   return v;
@@ -178,18 +104,18 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                       const __grid_constant__ CUtensorMap map_r, const __grid_constant__ TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int slab_bytes = 32 * p.bn * 2;                       // one epilogue warp-pair's 32 rows x bn bf16
+  const int box_bytes = 32 * p.cw * 2;                        // one staging box: 32 rows x cw bf16 (4 / 2 / 1 KB)
   uint8_t* b_region = smem + p.a_stages * p.a_stage_bytes;    // mode 1 only
-  uint8_t* stage_y = smem + p.ring_bytes;                     // D x 4 slabs: output (and accumulate input)
-  uint8_t* stage_r = stage_y + p.slab_depth * 4 * slab_bytes; // D x 4 slabs: residual input / second output
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(stage_r + p.slab_depth * 4 * slab_bytes);
+  uint8_t* stage_y = smem + p.ring_bytes;                     // nb x 4 boxes: output (and accumulate input)
+  uint8_t* stage_r = stage_y + p.nb * 4 * box_bytes;          // nb x 4 boxes: residual input / second output
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(stage_r + (p.need_r ? p.nb * 4 * box_bytes : 0));
   uint64_t* a_empty = a_full + MAX_A_STAGES;
   uint64_t* b_full = a_empty + MAX_A_STAGES;
   uint64_t* b_empty = b_full + MAX_B_STAGES;
   uint64_t* tmem_full_bar = b_empty + MAX_B_STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint64_t* res_bar = tmem_empty_bar + 2;            // [4 pairs][MAX_SLAB_DEPTH]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4 * MAX_SLAB_DEPTH);
+  uint64_t* res_bar = tmem_empty_bar + 2;            // [4 pairs][MAX_NB]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4 * MAX_NB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -209,7 +135,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
-    for (int s = 0; s < 4 * MAX_SLAB_DEPTH; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < 4 * MAX_NB; ++s) mbar_init(&res_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t tmem_cols = 2 * p.acc_stride;  // power of two >= 32 (host guarantees)
@@ -386,37 +312,39 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue: warps (q, q+4) share TMEM lanes / tile rows [32q, 32q+32) ============
-    // and split the 16-column chunks between them (even / odd); warp `half == 0` drives the TMA traffic.
+    // and split the 16-column chunks of every block between them; warp `half == 0` drives the TMA traffic.
     const int q = warp & 3;
     const int half = (warp - EPI_WARP0) >> 2;
-    const int D = p.slab_depth;
-    const int row_bytes = p.cw * 2;                  // 128 / 64 / 32: also the TMA swizzle width of the slab boxes
-    const int box_bytes = 32 * row_bytes;
+    const int NB = p.nb;
+    const int row_bytes = p.cw * 2;                  // 128 / 64 / 32: also the TMA swizzle width of the boxes
     const int chunks_per_row = row_bytes >> 4;       // 16-byte chunks per box row
     const int swz_shift = row_bytes == 128 ? 0 : (row_bytes == 64 ? 1 : 2);
     const uint32_t swz = ((uint32_t)lane >> swz_shift) & (uint32_t)(chunks_per_row - 1);
-    const int nboxes = p.bn >> p.cw_shift;
     const bool prefetch = p.has_res || p.accumulate;
-    const uint32_t pre_bytes = (uint32_t)((p.has_res ? 1 : 0) + (p.accumulate ? 1 : 0)) * (uint32_t)slab_bytes;
+    const uint32_t pre_bytes = (uint32_t)((p.has_res ? 1 : 0) + (p.accumulate ? 1 : 0)) * (uint32_t)box_bytes;
     const uint32_t pair_bar = 1 + q;                 // named barrier of the warp pair (64 threads)
     const bool leader = half == 0 && lane == 0;
-    uint64_t* my_res_bar = res_bar + q * MAX_SLAB_DEPTH;
-    // residual / accumulate-input prefetch of one tile into slab slot `slot` (leader lane only)
-    auto issue_prefetch = [&](int tile, int slot) {
+    uint64_t* my_res_bar = res_bar + q * MAX_NB;
+    // residual / accumulate-input prefetch of block `blk` of tile `tile` into ring slot `slot` (leader lane only)
+    auto issue_prefetch = [&](int tile, int blk, int slot) {
       int t0, n0, b, g;
       decode(tile, t0, n0, b, g);
-      uint8_t* sy = stage_y + (slot * 4 + q) * slab_bytes;
-      uint8_t* sr = stage_r + (slot * 4 + q) * slab_bytes;
+      const int ch = g * p.cout_g + n0 + blk * p.cw;
       mbar_expect_tx(&my_res_bar[slot], pre_bytes);
-      for (int bx = 0; bx < nboxes; ++bx) {
-        if (p.has_res) tma_load_3d(sr + bx * box_bytes, &map_r, &my_res_bar[slot], g * p.cout_g + n0 + bx * p.cw, t0 + q * 32, b);
-        if (p.accumulate) tma_load_3d(sy + bx * box_bytes, &map_y, &my_res_bar[slot], g * p.cout_g + n0 + bx * p.cw, t0 + q * 32, b);
-      }
+      if (p.has_res) tma_load_3d(stage_r + (slot * 4 + q) * box_bytes, &map_r, &my_res_bar[slot], ch, t0 + q * 32, b);
+      if (p.accumulate) tma_load_3d(stage_y + (slot * 4 + q) * box_bytes, &map_y, &my_res_bar[slot], ch, t0 + q * 32, b);
     };
-    if (prefetch && leader) {
-      const int ahead = D > 1 ? D - 1 : 1;
-      int tile = blockIdx.x;
-      for (int k = 0; k < ahead && tile < p.total_tiles; ++k, tile += gridDim.x) issue_prefetch(tile, k % D);
+    // prefetch cursor: runs `ahead` blocks in front of the block being drained
+    int pf_tile = blockIdx.x, pf_blk = 0, pf_slot = 0;
+    auto pf_advance = [&]() {
+      if (++pf_blk == p.nblk) { pf_blk = 0; pf_tile += gridDim.x; }
+      if (++pf_slot == NB) pf_slot = 0;
+    };
+    if (prefetch) {
+      for (int k = 0; k < p.ahead; ++k) {
+        if (leader && pf_tile < p.total_tiles) issue_prefetch(pf_tile, pf_blk, pf_slot);
+        pf_advance();
+      }
     }
     int acc = 0, slot = 0;
     uint32_t acc_phase = 0, res_phase_bits = 0;
@@ -425,89 +353,91 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       decode(tile, t0, n0, b, g);
       const int r0 = t0 + q * 32;
       const int ch0 = g * p.cout_g + n0;
-      uint8_t* slab_y = stage_y + (slot * 4 + q) * slab_bytes;
-      uint8_t* slab_r = stage_r + (slot * 4 + q) * slab_bytes;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (prefetch) {
-        mbar_wait(&my_res_bar[slot], (res_phase_bits >> slot) & 1u);
-        res_phase_bits ^= 1u << slot;
-      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
 #pragma unroll 1
-      for (int c0 = half * 16; c0 < p.bn; c0 += 32) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
+      for (int blk = 0; blk < p.nblk; ++blk) {
+        uint8_t* box_y = stage_y + (slot * 4 + q) * box_bytes;
+        uint8_t* box_r = stage_r + (slot * 4 + q) * box_bytes;
+        if (prefetch) {
+          mbar_wait(&my_res_bar[slot], (res_phase_bits >> slot) & 1u);
+          res_phase_bits ^= 1u << slot;
+        }
+        const int cb = blk * p.cw;                   // first tile column of this block
+#pragma unroll 1
+        for (int c0 = half * 16; c0 < p.cw; c0 += 32) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)(cb + c0), v);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int col = c0 + 8 * h;
-          const int bx = col >> p.cw_shift;
-          const uint32_t chunk = (uint32_t)((col - (bx << p.cw_shift)) >> 3);
-          const uint32_t off = (uint32_t)(bx * box_bytes + lane * row_bytes) + ((chunk ^ swz) << 4);
-          float f[8];
+          for (int h = 0; h < 2; ++h) {
+            const int col = c0 + 8 * h;              // column inside the box
+            const uint32_t off = (uint32_t)(lane * row_bytes) + ((((uint32_t)col >> 3) ^ swz) << 4);
+            float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]);
-          if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + col + 4));
-            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-          }
-          float r[8];
-          if (p.has_res) {
-            unpack8(*reinterpret_cast<const uint4*>(slab_r + off), r);
-            if (!p.res_after_act) {
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]);
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            float r[8];
+            if (p.has_res) {
+              unpack8(*reinterpret_cast<const uint4*>(box_r + off), r);
+              if (!p.res_after_act) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += r[i];
+              }
+            }
+            if (p.accumulate) {
+              float o[8];
+              unpack8(*reinterpret_cast<const uint4*>(box_y + off), o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += o[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = act_t<POST_ACT>(f[i] * p.out_scale, p.post_slope);
+            if (p.has_res && p.res_after_act) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += r[i];
             }
-          }
-          if (p.accumulate) {
-            float o[8];
-            unpack8(*reinterpret_cast<const uint4*>(slab_y + off), o);
+            *reinterpret_cast<uint4*>(box_y + off) = pack8(f);
+            if (p.has_y2) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += o[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = act_t<POST_ACT>(f[i] * p.out_scale, p.post_slope);
-          if (p.has_res && p.res_after_act) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += r[i];
-          }
-          *reinterpret_cast<uint4*>(slab_y + off) = pack8(f);
-          if (p.has_y2) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * p.act2_slope;
-            *reinterpret_cast<uint4*>(slab_r + off) = pack8(f);
+              for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * p.act2_slope;
+              *reinterpret_cast<uint4*>(box_r + off) = pack8(f);
+            }
           }
         }
+        if (blk == p.nblk - 1) {
+          // accumulator drained: hand it back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        // box -> global through the async proxy, once both warps of the pair have written their columns
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        if (leader) {
+          tma_store_3d(&map_y, box_y, ch0 + cb, r0, b);
+          if (p.has_y2) tma_store_3d(&map_y2, box_r, ch0 + cb, r0, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          // the slot that is written next (prefetch: `ahead` blocks from now; otherwise by the next block) was last
+          // used nb - ahead (resp. nb - 1) store groups ago: wait until those stores have left shared memory
+          const int pending = prefetch ? NB - p.ahead : NB - 1;
+          if (pending <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else if (pending == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else if (pending == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+          if (prefetch && pf_tile < p.total_tiles) issue_prefetch(pf_tile, pf_blk, pf_slot);
+        }
+        if (prefetch) pf_advance();
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        if (++slot == NB) slot = 0;
       }
-      // accumulator drained: hand it back to the MMA warp
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-      // slab -> global through the async proxy, once both warps of the pair have written their columns
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      if (leader) {
-        for (int bx = 0; bx < nboxes; ++bx) {
-          tma_store_3d(&map_y, slab_y + bx * box_bytes, ch0 + bx * p.cw, r0, b);
-          if (p.has_y2) tma_store_3d(&map_y2, slab_r + bx * box_bytes, ch0 + bx * p.cw, r0, b);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        // the slot written D-1 tiles from now is the one the PREVIOUS tile used (or this one when D == 1):
-        // wait until its stores have left shared memory, then refill it with the residual of tile i + D - 1
-        if (D > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (prefetch) {
-          const int ahead = D > 1 ? D - 1 : 1;
-          const long long nt = (long long)tile + (long long)ahead * gridDim.x;
-          if (nt < p.total_tiles) issue_prefetch((int)nt, D > 1 ? (slot + D - 1) % D : 0);
-        }
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      if (++slot == D) slot = 0;
     }
     if (half == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -520,40 +450,9 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      ptr = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(ptr);
-  }();
-  return fn;
-}
-
 int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) {
-    sib::set_error("sib_conv1d_bf16: cuTensorMapEncodeTiled unavailable");
-    return SIB_ERR_CUDA;
-  }
-  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
-                   strides_bytes + 1, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    sib::set_error("sib_conv1d_bf16: cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu stride1 %llu)",
-                   what, (int)r, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
-                   (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides_bytes[1] : 0));
-    return SIB_ERR_CUDA;
-  }
-  return SIB_OK;
+  return sib_tc::encode_map(m, base, rank, dims, strides_bytes, box, swz, "sib_conv1d_bf16", what);
 }
 
 }  // namespace
@@ -588,10 +487,53 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   SIB_REQUIRE(!y_act || al16(y_act), "sib_conv1d_bf16: y_act must be 16-byte aligned (it shares y's strides)");
   SIB_REQUIRE(!bias || al16(bias), "sib_conv1d_bf16: bias must be 16-byte aligned");
 
-  // tile width: the largest multiple of 16 that is <= 128 and divides c_out/groups (== UMMA N)
+  const int row_bytes = cc * 2;  // one K-row of a sub-tile == the swizzle width (128 / 64 / 32 bytes)
+  const int nsm = sm_count_of_current_device();
+
+  // ---- mode: "halo" whenever all taps are row shifts of one (128 + span)-row tile
+  int step = 1;
+  bool uniform = d->stride == 1;
+  if (uniform && d->n_taps > 1) {
+    step = d->tap_offset[1] - d->tap_offset[0];
+    uniform = step >= 1;
+    for (int j = 2; uniform && j < d->n_taps; ++j) uniform = (d->tap_offset[j] - d->tap_offset[j - 1]) == step;
+  }
+  const int rows_h = BM + (d->n_taps - 1) * step;
+  static const bool force_mode0 = getenv("SIB_TC_FORCE_PER_TAP") != nullptr;  // A/B switch for profiling
+  // (plain GEMMs, n_taps == 1, have nothing to share between taps: they keep the combined A+B ring of mode 0)
+  const bool halo = uniform && d->n_taps > 1 && rows_h <= 256 && !force_mode0;
+
+  // ---- tile width bn (== UMMA N): a multiple of 16 dividing c_out/groups, chosen by a small cost model.
+  // cycles/tile on the tensor pipe = MMAs x max(bn/2, (4 KB A + bn*32 B of B) / 128 B/clk shared-memory port);
+  // the tile count is rounded up to whole waves of persistent CTAs (M = batch x frames is rarely a multiple of
+  // 148 x 128); operands come from L2 at ~5.5 KB/clk chip-wide, so wider tiles (more FLOP per operand byte) win
+  // until the waves quantise badly.  Halo-mode weights stream per tile, hence bn <= 128 there keeps the B ring deep.
+  const int tiles_m = sib::ceil_div(d->t_out, BM);
+  const int64_t k16 = (int64_t)d->n_taps * cin_g / UMMA_K;            // MMAs per tile
+  auto tile_cost = [&](int cand) -> double {
+    const int64_t tiles = (int64_t)tiles_m * (cout_g / cand) * d->batch * d->groups;
+    const int ctas = nsm * (cand <= 32 ? 2 : 1);
+    const int64_t rounds = (tiles + ctas - 1) / ctas;
+    const double mma_cyc = cand / 2.0 > 32.0 + cand / 4.0 ? cand / 2.0 : 32.0 + cand / 4.0;
+    const double t_mma = (double)rounds * ((double)k16 * mma_cyc + 400.0);
+    const double a_bytes = halo ? (double)(cin_g / cc) * rows_h * row_bytes : (double)d->n_taps * cin_g * BM * 2;
+    const bool resident = halo && d->groups == 1 && cand == cout_g && (int64_t)d->n_taps * cin_g * cand * 2 <= 120 * 1024;
+    const double b_bytes = resident ? 0.0 : (double)d->n_taps * cin_g * cand * 2;
+    const double t_l2 = (double)tiles * (a_bytes + b_bytes) / 5500.0;
+    return t_mma > t_l2 ? t_mma : t_l2;
+  };
   int bn = 0;
-  for (int cand = 128; cand >= 16; cand -= 16)
-    if (cout_g % cand == 0) { bn = cand; break; }
+  {
+    static const int force_bn = getenv("SIB_TC_BN") ? atoi(getenv("SIB_TC_BN")) : 0;  // tuning / profiling override
+    const int bn_max = halo ? 128 : 256;
+    double best = 0.0;
+    for (int cand = bn_max; cand >= 16; cand -= 16) {
+      if (cout_g % cand) continue;
+      if (force_bn && cand == force_bn) { bn = cand; break; }
+      const double c = tile_cost(cand);
+      if (bn == 0 || c < best * 0.97) { bn = cand; best = c; }     // prefer the wider tile unless clearly slower
+    }
+  }
   const int cw = bn % 64 == 0 ? 64 : (bn % 32 == 0 ? 32 : 16);
 
   TcArgs a;
@@ -603,17 +545,17 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   a.post_act = d->post_act; a.accumulate = d->accumulate; a.res_after_act = d->res_after_act;
   a.post_slope = d->post_slope; a.out_scale = d->out_scale; a.act2_slope = d->act2_slope;
   a.bn = bn; a.cw = cw; a.cw_shift = cw == 64 ? 6 : (cw == 32 ? 5 : 4);
-  a.tiles_m = sib::ceil_div(d->t_out, BM);
+  a.nblk = bn / cw;
+  a.tiles_m = tiles_m;
   a.tiles_n = cout_g / bn;
   const int64_t total = (int64_t)a.tiles_m * a.tiles_n * d->batch * d->groups;
   SIB_REQUIRE(total < (1ll << 31), "sib_conv1d_bf16: too many tiles");
   a.total_tiles = (int)total;
-  a.acc_stride = bn <= 16 ? 16 : (bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
+  a.acc_stride = bn <= 16 ? 16 : (bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256)));
   a.cc = cc; a.tb = tb; a.cin_g = cin_g;
   a.n_chunks = cin_g / cc;
   a.n_tapblocks = (d->n_taps + tb - 1) / tb;
   a.n_taps = d->n_taps;
-  const int row_bytes = cc * 2;  // one K-row of a sub-tile == the swizzle width (128 / 64 / 32 bytes)
   a.desc_hi = make_desc_hi(row_bytes);
   a.idesc = make_idesc(bn);
   auto swz_of = [](int rb) {
@@ -622,32 +564,29 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   a.a_sub_bytes = BM * row_bytes;
   a.b_sub_bytes = bn * row_bytes;
   a.b_tap_bytes = bn * row_bytes;
-  // epilogue staging ring: deep enough to hide the residual TMA latency behind D-1 tiles of work; layers whose
-  // tiles carry a long K loop and no residual keep a single slab and give the memory to the operand rings
+  // epilogue staging ring (blocks of cw columns): with a residual / accumulate input the ring must cover the TMA
+  // latency (~2-3k cycles) with prefetched blocks; when one block's share of the mainloop already exceeds that,
+  // one block ahead is enough and the memory goes to the operand rings instead
   const bool pre = a.has_res || a.accumulate;
-  const int kblocks = a.n_chunks * d->n_taps * cc / BK;
-  a.slab_depth = pre ? (bn <= 64 ? 3 : 2) : (bn <= 64 ? 2 : (kblocks >= 8 ? 1 : 2));
-  const int slab_total = a.slab_depth * 2 * 4 * 32 * bn * 2;  // D x (y + r) staging, 4 epilogue warp pairs
+  a.need_r = a.has_res || a.has_y2;
+  {
+    const double mma_cyc = bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0;
+    const double cyc_per_block = (double)k16 * mma_cyc / a.nblk;
+    static const int force_nb = getenv("SIB_TC_NB") ? atoi(getenv("SIB_TC_NB")) : 0;
+    a.nb = pre ? (cyc_per_block >= 3000.0 ? 2 : 3) : 2;
+    if (force_nb >= 2 && force_nb <= MAX_NB) a.nb = force_nb;
+    a.ahead = pre ? a.nb - 1 : 0;
+  }
+  const int slab_total = a.nb * (1 + a.need_r) * 4 * 32 * cw * 2;  // nb x (y [+ r]) boxes for 4 epilogue warp pairs
   // narrow layers (bn <= 32: 8 KB output tiles) are bound by the per-tile latency chain of one CTA, not by any
   // throughput: run two persistent CTAs per SM on half the shared memory each
   const int ctas_per_sm = bn <= 32 ? 2 : 1;
   const int smem_budget = ctas_per_sm == 2 ? 112 * 1024 : 227 * 1024;
   const int avail = smem_budget - 2048 - slab_total - 1024;
 
-  // ---- mode selection: "halo" mode whenever all taps are row shifts of one (128 + span)-row tile
   a.mode = 0;
   a.tg = 1;
-  int step = 1;
-  bool uniform = d->stride == 1;
-  if (uniform && d->n_taps > 1) {
-    step = d->tap_offset[1] - d->tap_offset[0];
-    uniform = step >= 1;
-    for (int j = 2; uniform && j < d->n_taps; ++j) uniform = (d->tap_offset[j] - d->tap_offset[j - 1]) == step;
-  }
-  const int rows_h = BM + (d->n_taps - 1) * step;
-  static const bool force_mode0 = getenv("SIB_TC_FORCE_PER_TAP") != nullptr;  // A/B switch for profiling
-  // (plain GEMMs, n_taps == 1, have nothing to share between taps: they keep the combined A+B ring of mode 0)
-  if (uniform && d->n_taps > 1 && rows_h <= 256 && !force_mode0) {
+  if (halo) {
     a.rows_h = rows_h; a.tap_step = step; a.off0 = d->tap_offset[0];
     a.a_stage_bytes = (rows_h * row_bytes + 1023) / 1024 * 1024;
     int tg = 16384 / a.b_tap_bytes;
@@ -665,10 +604,10 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
       if (a.a_stages > MAX_A_STAGES) a.a_stages = MAX_A_STAGES;
     } else {
       a.b_stage_bytes = tg * a.b_tap_bytes;
-      // split the operand budget about evenly between the A ring and the B ring
-      int as = (avail / 2) / a.a_stage_bytes;
-      if (as > a.n_chunks * 3) as = a.n_chunks * 3;   // no point in buffering more than ~3 tiles of A
-      if (as > MAX_A_STAGES) as = MAX_A_STAGES;
+      // the weight stream carries n_taps x more bytes than the halo tiles: two or three A stages (one tile's worth of
+      // chunks in flight), everything else to the B ring
+      int as = a.n_chunks + 1;
+      if (as > 3) as = 3;
       if (as < 2) as = 2;
       for (; as >= 2 && a.mode == 0; --as) {
         int bs = (avail - as * a.a_stage_bytes) / a.b_stage_bytes;
@@ -690,6 +629,12 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     a.a_stages = 0;
   }
   const int smem_bytes = a.ring_bytes + slab_total + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static const bool verbose = getenv("SIB_TC_VERBOSE") != nullptr;
+  if (verbose)
+    fprintf(stderr, "[sib_conv1d_bf16] B%d T%d C%d->%d k%d g%d s%d: bn=%d mode=%d resident=%d a_stages=%d b_stages=%d "
+            "stages=%d nb=%d ahead=%d need_r=%d smem=%d tiles=%d\n", d->batch, d->t_out, d->c_in, d->c_out, d->n_taps,
+            d->groups, d->stride, bn, a.mode, a.b_resident, a.a_stages, a.b_stages, a.stages, a.nb, a.ahead, a.need_r,
+            smem_bytes, a.total_tiles);
 
   const int s = d->stride;
   SIB_REQUIRE(s >= 1, "sib_conv1d_bf16: stride must be positive");
@@ -754,7 +699,6 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     }
     sm_count[dev] = n > 0 ? n : 148;
   }
-  const int nsm = (dev >= 0 && dev < 64) ? sm_count[dev] : 148;
   const int grid = a.total_tiles < nsm * ctas_per_sm ? a.total_tiles : nsm * ctas_per_sm;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   switch (d->post_act) {

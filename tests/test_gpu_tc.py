@@ -123,3 +123,29 @@ def test_conv_transpose_bf16_tc(sib, ks, cin, cout):
     y = torch.empty(B, T * s, cout, dtype=torch.bfloat16, device="cuda")
     sib.ops.conv1d(xd, sib.ops.to_kmajor_bf16(wp), bp, y.view(B, T, s * cout), taps)
     _close(ref, y.float().cpu(), f"convT {ks}")
+
+
+@pytest.mark.parametrize("B,T,nh,padded", [(3, 99, 4, False), (2, 199, 12, True), (2, 128, 2, False), (3, 130, 4, True),
+                                            (2, 499, 3, True), (1, 257, 2, False), (2, 16, 2, True)])
+def test_attention_bf16_tc(sib, B, T, nh, padded):
+    """tcgen05 attention (HF:234-259) vs torch fp32 on the same bf16-rounded q|k|v: S and O accumulate in fp32 (TMEM),
+    P is rounded to bf16 before P.V, the output to bf16 - tolerance a few bf16 ulps of the output scale."""
+    d = 64
+    H = nh * d
+    qkv = _bf(_rand(B, T, 3 * H, seed=T + nh))
+    kl = None
+    if padded:
+        kl = torch.tensor([T, max(1, T - 17), 5][:B], dtype=torch.int32)
+    q, k, v = [t.view(B, T, nh, d).transpose(1, 2) for t in qkv.split(H, dim=-1)]
+    s = torch.matmul(q, k.transpose(2, 3)) * d ** -0.5
+    if padded:
+        km = torch.arange(T)[None, :] < kl[:, None]
+        s = s.masked_fill(~km[:, None, None, :], torch.finfo(torch.float32).min)
+    ref = torch.matmul(F.softmax(s, -1), v).transpose(1, 2).reshape(B, T, H)
+    out = torch.full((B, T, H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    sib.ops.attention(qkv.cuda().to(torch.bfloat16), None if kl is None else kl.cuda(), out, nh)
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    err = (ref - got).abs().max().item()
+    assert err < 2.5e-2 * max(1.0, ref.abs().max().item()), f"max err {err:.4g} (ref max {ref.abs().max():.3g})"
+    assert (ref - got).abs().mean().item() < 3e-3
