@@ -54,7 +54,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
   uint64_t* o_empty = bars + 9;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role dispatch
   const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
   const int H = heads * HD;
   const int kl = key_len ? max(1, min(key_len[b], T)) : T;
@@ -87,21 +87,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 4) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp in the loop, one elected lane issues) =====================
+    const uint32_t issuer = elect_one_sync();
+    if (issuer) {
       mbar_expect_tx(q_full, TILE_BYTES);
       tma_load_3d(smem + SM_Q, &map_qkv, q_full, h * HD, q0, b);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+    }
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+      if (issuer) {
         mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
         tma_load_3d(smem + SM_K + s * TILE_BYTES, &map_qkv, &kv_full[s], H + h * HD, j * KB, b);
         tma_load_3d(smem + SM_V + s * TILE_BYTES, &map_qkv, &kv_full[s], 2 * H + h * HD, j * KB, b);
       }
     }
   } else if (warp == 5) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform loop (descriptors in uniform registers), one lane issues ======
+    {
+      const uint32_t issuer = elect_one_sync();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t DESC_HI = make_desc_hi(128);
       const uint64_t qdesc = make_smem_desc(smem_u32(smem + SM_Q), DESC_HI);
       const uint64_t pdesc = make_smem_desc(smem_u32(smem + SM_P), DESC_HI);
@@ -115,23 +120,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
         // S = Q K^T.  (S of block j-1 has been consumed: the P V MMAs of j-1 were issued after p_full(j-1).)
         const uint64_t kdesc = make_smem_desc(smem_u32(smem + SM_K + s * TILE_BYTES), DESC_HI);
         const uint32_t idesc_s = make_idesc_bf16(QT, nk16);
+        if (issuer) {
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) umma_bf16(tmem_base, qdesc + 2 * ks, kdesc + 2 * ks, idesc_s, ks > 0);
-        umma_commit(s_full);
+          for (int ks = 0; ks < HD / 16; ++ks) umma_bf16(tmem_u, qdesc + 2 * ks, kdesc + 2 * ks, idesc_s, ks > 0);
+          umma_commit(s_full);
+        }
         // O_blk = P V
         mbar_wait(p_full, j & 1);
         mbar_wait(o_empty, (j & 1) ^ 1);
         tc_fence_after();
         const uint64_t vdesc = make_smem_desc(smem_u32(smem + SM_V + s * TILE_BYTES), DESC_HI);
-        for (int ks = 0; ks < nk16 / 16; ++ks) {
-          // A: 16 keys = 32 bytes inside the swizzle row of P chunk ks/4;  B: 16 key rows of V = 2048 bytes further
-          const uint64_t a = pdesc + (uint64_t)((ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2);
-          const uint64_t bd = vdesc + (uint64_t)(ks * (16 * 128 >> 4));
-          umma_bf16(tmem_base + TMEM_O, a, bd, IDESC_O, ks > 0);
+        if (issuer) {
+          for (int ks = 0; ks < nk16 / 16; ++ks) {
+            // A: 16 keys = 32 bytes inside the swizzle row of P chunk ks/4;  B: 16 key rows of V = 2048 bytes further
+            const uint64_t a = pdesc + (uint64_t)((ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2);
+            const uint64_t bd = vdesc + (uint64_t)(ks * (16 * 128 >> 4));
+            umma_bf16(tmem_u + TMEM_O, a, bd, IDESC_O, ks > 0);
+          }
+          umma_commit(o_full);
+          umma_commit(&kv_empty[s]);
+          umma_commit(p_empty);
         }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[s]);
-        umma_commit(p_empty);
       }
     }
   } else {

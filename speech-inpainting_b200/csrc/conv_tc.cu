@@ -117,7 +117,8 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint64_t* res_bar = tmem_empty_bar + 2;            // [4 pairs][MAX_NB]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4 * MAX_NB);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows that every role branch below is warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -166,27 +167,31 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
   if (warp == 0) {
     // ===================== A producer (mode 0: A and B of every K-block) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int t0, n0, b, g;
-        decode(tile, t0, n0, b, g);
-        if (p.mode == 1) {
-          for (int cc = 0; cc < p.n_chunks; ++cc) {
-            mbar_wait(&a_empty[stage], phase ^ 1);
+    // whole warp in the loop (uniform coordinates -> uniform registers for UTMALDG), one elected lane issues
+    const uint32_t issuer = elect_one_sync();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int t0, n0, b, g;
+      decode(tile, t0, n0, b, g);
+      if (p.mode == 1) {
+        for (int cc = 0; cc < p.n_chunks; ++cc) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          if (issuer) {
             mbar_expect_tx(&a_full[stage], (uint32_t)(p.rows_h * row_bytes_k));
             tma_load_3d(smem + stage * p.a_stage_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc, t0 + p.off0, b);
-            if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
           }
-        } else {
-          const int iters = p.n_chunks * p.n_tapblocks;
-          for (int it = 0; it < iters; ++it) {
-            const int cc = it / p.n_tapblocks, tb = it - cc * p.n_tapblocks;
-            mbar_wait(&a_empty[stage], phase ^ 1);
-            uint8_t* a_dst = smem + stage * p.stage_bytes;
-            uint8_t* b_dst = a_dst + A_STAGE_BYTES;
-            const int nsub = min(p.tb, p.n_taps - tb * p.tb);
+          if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        const int iters = p.n_chunks * p.n_tapblocks;
+        int cc = 0, tb = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * p.stage_bytes;
+          uint8_t* b_dst = a_dst + A_STAGE_BYTES;
+          const int nsub = min(p.tb, p.n_taps - tb * p.tb);
+          if (issuer) {
             mbar_expect_tx(&a_full[stage], (uint32_t)nsub * (uint32_t)(p.a_sub_bytes + p.b_sub_bytes));
             for (int sidx = 0; sidx < nsub; ++sidx) {
               const int j = tb * p.tb + sidx;
@@ -195,20 +200,24 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               tma_load_3d(b_dst + sidx * p.b_sub_bytes, &map_b, &a_full[stage], 0, n0,
                           (g * p.n_chunks + cc) * p.n_taps + j);
             }
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+          if (++tb == p.n_tapblocks) { tb = 0; ++cc; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 2) {
     // ===================== B producer (mode 1) =====================
-    if (lane == 0 && p.mode == 1) {
+    const uint32_t issuer = elect_one_sync();
+    if (p.mode == 1) {
       if (p.b_resident) {
         // every tile of this launch uses the same weights: load them once (groups == 1, tiles_n == 1)
         const int slabs = p.n_chunks * p.n_taps;
-        mbar_expect_tx(&b_full[0], (uint32_t)(((slabs + p.tg - 1) / p.tg) * p.b_stage_bytes));
-        for (int s0 = 0; s0 < slabs; s0 += p.tg)
-          tma_load_3d(b_region + (s0 / p.tg) * p.b_stage_bytes, &map_b, &b_full[0], 0, 0, s0);
+        if (issuer) {
+          mbar_expect_tx(&b_full[0], (uint32_t)(((slabs + p.tg - 1) / p.tg) * p.b_stage_bytes));
+          for (int s0 = 0; s0 < slabs; s0 += p.tg)
+            tma_load_3d(b_region + (s0 / p.tg) * p.b_stage_bytes, &map_b, &b_full[0], 0, 0, s0);
+        }
       } else {
         int stage = 0;
         uint32_t phase = 0;
@@ -218,9 +227,11 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           for (int cc = 0; cc < p.n_chunks; ++cc) {
             for (int j0 = 0; j0 < p.n_taps; j0 += p.tg) {
               mbar_wait(&b_empty[stage], phase ^ 1);
-              mbar_expect_tx(&b_full[stage], (uint32_t)p.b_stage_bytes);
-              tma_load_3d(b_region + stage * p.b_stage_bytes, &map_b, &b_full[stage], 0, n0,
-                          (g * p.n_chunks + cc) * p.n_taps + j0);
+              if (issuer) {
+                mbar_expect_tx(&b_full[stage], (uint32_t)p.b_stage_bytes);
+                tma_load_3d(b_region + stage * p.b_stage_bytes, &map_b, &b_full[stage], 0, n0,
+                            (g * p.n_chunks + cc) * p.n_taps + j0);
+              }
               if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -228,87 +239,92 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      int stage = 0, bstage = 0;
-      uint32_t phase = 0, bphase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      if (p.mode == 1 && p.b_resident) {
-        mbar_wait(&b_full[0], 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
-        if (p.mode == 1) {
-          // descriptor arithmetic is strength-reduced: this single thread paces every MMA of the SM
-          const uint32_t b_base = smem_u32(b_region);
-          const uint64_t a_tap_inc = (uint64_t)((p.tap_step * row_bytes_k) >> 4);   // next tap = shifted rows
-          const uint64_t b_tap_inc = (uint64_t)(p.b_tap_bytes >> 4);
-          uint64_t bdesc_res = make_smem_desc(b_base, p.desc_hi);                    // resident weights: walk the slabs
-          uint32_t accum = 0;
-          for (int cc = 0; cc < p.n_chunks; ++cc) {
-            mbar_wait(&a_full[stage], phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint64_t adesc = make_smem_desc(smem_u32(smem + stage * p.a_stage_bytes), p.desc_hi);
-            if (p.b_resident) {
-              for (int j = 0; j < p.n_taps; ++j) {
-                for (int k = 0; k < ksteps; ++k) {
-                  umma_bf16(tmem_d, adesc + 2 * k, bdesc_res + 2 * k, p.idesc, accum);
-                  accum = 1;
-                }
-                adesc += a_tap_inc;
-                bdesc_res += b_tap_inc;
+    // ===================== MMA issuer =====================
+    // The WHOLE warp walks the loop, so stages, phases and descriptors are warp-uniform values held in uniform
+    // registers that feed UTCHMMA directly; one elected lane issues.  (Walking the loop under `if (lane == 0)` turns
+    // every operand into a per-thread value: the compiler then wraps each MMA in a ~40-instruction uniformisation
+    // sequence and this warp, not the tensor pipe, paces the SM - measured 230 clk per MMA instead of 64.)
+    const uint32_t issuer = elect_one_sync();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int stage = 0, bstage = 0;
+    uint32_t phase = 0, bphase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (p.mode == 1 && p.b_resident) {
+      mbar_wait(&b_full[0], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t b_base = smem_u32(b_region);
+    const uint64_t a_tap_inc = (uint64_t)((p.tap_step * row_bytes_k) >> 4);   // next tap = shifted rows
+    const uint64_t b_tap_inc = (uint64_t)(p.b_tap_bytes >> 4);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_u + (uint32_t)(acc * p.acc_stride);
+      if (p.mode == 1) {
+        uint64_t bdesc_res = make_smem_desc(b_base, p.desc_hi);                    // resident weights: walk the slabs
+        uint32_t accum = 0;
+        for (int cc = 0; cc < p.n_chunks; ++cc) {
+          mbar_wait(&a_full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint64_t adesc = make_smem_desc(smem_base + (uint32_t)(stage * p.a_stage_bytes), p.desc_hi);
+          if (p.b_resident) {
+            for (int j = 0; j < p.n_taps; ++j) {
+              if (issuer) {
+                for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc_res + 2 * k, p.idesc, accum | (uint32_t)k);
               }
-            } else {
-              int j = 0;
-              while (j < p.n_taps) {
-                mbar_wait(&b_full[bstage], bphase);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint64_t bdesc = make_smem_desc(b_base + (uint32_t)(bstage * p.b_stage_bytes), p.desc_hi);
-                const int jend = min(j + p.tg, p.n_taps);
-                for (; j < jend; ++j) {
-                  for (int k = 0; k < ksteps; ++k) {
-                    umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum);
-                    accum = 1;
-                  }
-                  adesc += a_tap_inc;
-                  bdesc += b_tap_inc;
-                }
-                umma_commit(&b_empty[bstage]);
-                if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
-              }
+              accum = 1;
+              adesc += a_tap_inc;
+              bdesc_res += b_tap_inc;
             }
-            umma_commit(&a_empty[stage]);
-            if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+          } else {
+            int j = 0;
+            while (j < p.n_taps) {
+              mbar_wait(&b_full[bstage], bphase);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              uint64_t bdesc = make_smem_desc(b_base + (uint32_t)(bstage * p.b_stage_bytes), p.desc_hi);
+              const int jend = min(j + p.tg, p.n_taps);
+              for (; j < jend; ++j) {
+                if (issuer) {
+                  for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum | (uint32_t)k);
+                }
+                accum = 1;
+                adesc += a_tap_inc;
+                bdesc += b_tap_inc;
+              }
+              if (issuer) umma_commit(&b_empty[bstage]);
+              if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+            }
           }
-        } else {
-          const int iters = p.n_chunks * p.n_tapblocks;
-          for (int it = 0; it < iters; ++it) {
-            mbar_wait(&a_full[stage], phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-            const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-            const int tb = it % p.n_tapblocks;
-            const int nsub = min(p.tb, p.n_taps - tb * p.tb);
+          if (issuer) umma_commit(&a_empty[stage]);
+          if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        const int iters = p.n_chunks * p.n_tapblocks;
+        int tb = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&a_full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_base + (uint32_t)(stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const int nsub = min(p.tb, p.n_taps - tb * p.tb);
+          if (issuer) {
             for (int sidx = 0; sidx < nsub; ++sidx) {
               const uint64_t adesc = make_smem_desc(a_addr + sidx * p.a_sub_bytes, p.desc_hi);
               const uint64_t bdesc = make_smem_desc(b_addr + sidx * p.b_sub_bytes, p.desc_hi);
-              for (int k = 0; k < ksteps; ++k) {
-                // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-                umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, (it | sidx | k) ? 1u : 0u);
-              }
+              // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+              for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, (uint32_t)(it | sidx | k));
             }
             umma_commit(&a_empty[stage]);  // frees the smem slot when these MMAs retire
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+          if (++tb == p.n_tapblocks) tb = 0;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
+      if (issuer) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue: warps (q, q+4) share TMEM lanes / tile rows [32q, 32q+32) ============

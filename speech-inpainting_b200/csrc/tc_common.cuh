@@ -50,6 +50,17 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// one lane of the (fully active) warp gets 1, all others 0
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+
 // ----------------------------------------------------------------------------------------------- cluster
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
