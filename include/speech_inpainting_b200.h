@@ -92,6 +92,12 @@ int sib_conv0_f32(int mode, const float* wave, int batch, int n_samples, int64_t
                   float* partial, const float* mean, const float* rstd, const float* gamma,
                   const float* beta, float* y, sib_stream_t stream);
 int sib_conv0_num_tiles(int t0);
+/* GroupNorm(C, C) statistics of conv0's output in closed form from the waveform's lag sums (conv0 is linear in the
+ * samples): mean[b,c], rstd[b,c] = 1/sqrt(var + eps), same outputs as mode 0 + sib_gn_finalize_f32 without
+ * evaluating conv0 (HF:154-175, torch GroupNorm biased variance).  k = 10, stride = 5 only. */
+int sib_conv0_gn_stats_f32(const float* wave, int batch, int n_samples, int64_t wave_batch_stride, const float* w,
+                           const float* bias, int c, int k, int stride, int t0, float eps, float* mean, float* rstd,
+                           sib_stream_t stream);
 int sib_gn_finalize_f32(const float* partial, int batch, int n_tiles, int c, int t0, float eps, float* mean,
                         float* rstd, sib_stream_t stream);
 

@@ -17,6 +17,7 @@ SHAPES = {
     "bigconv": (32, 4096, 512, 512, 11, 1, 1, False, False),
     "qkv": (1, 6368, 768, 2304, 1, 1, 1, False, False),
     "ffn1": (1, 6368, 768, 3072, 1, 1, 1, False, False),
+    "ffn1g": (1, 6368, 768, 3072, 1, 1, 1, False, False, "gelu"),
     "ffn2": (1, 6368, 3072, 768, 1, 1, 1, False, False),
     "hubconv1": (32, 12799, 512, 512, 3, 1, 2, False, False),
     "s1k11": (32, 2752, 256, 256, 11, 1, 1, True, True),
@@ -36,7 +37,9 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     a = ap.parse_args()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for name, (B, T, Cin, Cout, k, dil, stride, res, yact) in SHAPES.items():
+    for name, spec in SHAPES.items():
+        B, T, Cin, Cout, k, dil, stride, res, yact = spec[:9]
+        act = ops.ACT_GELU if len(spec) > 9 and spec[9] == "gelu" else ops.ACT_NONE
         if a.only and name not in a.only.split(","):
             continue
         t_out = (T - k) // stride + 1 if stride > 1 else T
@@ -53,7 +56,7 @@ def main():
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.conv1d(x, w, bias, y, taps, stride=stride, residual=r, y_act=y2, act2_slope=0.1)
+            ops.conv1d(x, w, bias, y, taps, stride=stride, residual=r, y_act=y2, act2_slope=0.1, post_act=act)
             e1.record()
             torch.cuda.synchronize()
             if it >= 2:

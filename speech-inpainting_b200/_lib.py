@@ -43,6 +43,7 @@ _SIGS = {
     "sib_conv0_f32": ([_I, _P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_conv0_num_tiles": ([_I], _I),
     "sib_gn_finalize_f32": ([_P, _I, _I, _I, _I, _F, _P, _P, _P], _I),
+    "sib_conv0_gn_stats_f32": ([_P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P], _I),
     "sib_layernorm_f32": ([_P, _P, _P, _P, _P, _L, _I, _F, _I, _P], _I),
     "sib_attention_f32": ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
     "sib_zero_padded_frames_f32": ([_P, _P, _I, _I, _I, _P], _I),

@@ -77,7 +77,8 @@ constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 16, MAX_NB = 6;
 // (128 x 128 GELUs per tile) would otherwise outlast its mainloop.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // argument in [1, inf)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
@@ -381,10 +382,9 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           res_phase_bits ^= 1u << slot;
         }
         const int cb = blk * p.cw;                   // first tile column of this block
-#pragma unroll 1
-        for (int c0 = half * 16; c0 < p.cw; c0 += 32) {
-          uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)(cb + c0), v);
+        // the two warps of a pair take the two column halves of the block; with cw == 64 that is 32 columns per
+        // warp: both 16-column TMEM loads are issued before the single wait
+        auto process16 = [&](const uint32_t (&v)[16], const int c0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int col = c0 + 8 * h;              // column inside the box
@@ -425,6 +425,18 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               *reinterpret_cast<uint4*>(box_r + off) = pack8(f);
             }
           }
+        };
+        if (p.cw == 64) {
+          uint32_t va[16], vb[16];
+          tmem_ld16_nowait(taddr + (uint32_t)(cb + half * 32), va);
+          tmem_ld16_nowait(taddr + (uint32_t)(cb + half * 32 + 16), vb);
+          tmem_ld_wait();
+          process16(va, half * 32);
+          process16(vb, half * 32 + 16);
+        } else if (half * 16 < p.cw) {
+          uint32_t va[16];
+          tmem_ld16(taddr + (uint32_t)(cb + half * 16), va);
+          process16(va, half * 16);
         }
         if (blk == p.nblk - 1) {
           // accumulator drained: hand it back to the MMA warp

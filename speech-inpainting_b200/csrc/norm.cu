@@ -124,6 +124,140 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int n_tile
   rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// ------------------------------------------------------------------------------------------ conv0: closed-form GN stats
+// GroupNorm(C, C) statistics of conv0's output WITHOUT evaluating conv0: y[c,t] = sum_j w[c,j] x[S t + j] is linear
+// in the waveform, so with  s1[j] = sum_t x[S t + j]  and  R[j][j'] = sum_t x[S t + j] x[S t + j']  (K + K(K+1)/2
+// numbers per utterance, one pass over the samples):
+//     sum_t y[c,t]   = w_c . s1 + T0 b_c         sum_t (y[c,t] - b_c)^2 = w_c^T R w_c
+// One CTA per utterance; per-thread fp32 partial sums over ~T0/256 frames, then a fixed-order (deterministic)
+// reduction and the per-channel quadratic forms in double.  Replaces a full [B, T0, C] evaluation pass.
+template <int K, int S>
+__global__ void __launch_bounds__(256) conv0_gn_stats_kernel(const float* __restrict__ wave, int64_t wave_bs,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             int C, int T0, float eps, float* __restrict__ mean,
+                                                             float* __restrict__ rstd) {
+  constexpr int NR = K * (K + 1) / 2;
+  constexpr int NV = K + NR;
+  __shared__ float part[16][NV];
+  __shared__ double tot[NV];
+  const float* xb = wave + (int64_t)blockIdx.x * wave_bs;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  for (int t = threadIdx.x; t < T0; t += blockDim.x) {
+    float x[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) x[j] = xb[(int64_t)t * S + j];
+    int idx = K;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      acc[j] += x[j];
+#pragma unroll
+      for (int j2 = j; j2 < K; ++j2) acc[idx++] = fmaf(x[j], x[j2], acc[idx]);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float v = sib::warp_sum(acc[i]);
+    if (lane == 0) part[wid][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double v = 0.0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += (double)part[wv][threadIdx.x];
+    tot[threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double wr[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) wr[j] = (double)w[c * K + j];
+    double lin = 0.0, quad = 0.0;
+    int idx = K;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      lin += wr[j] * tot[j];
+#pragma unroll
+      for (int j2 = j; j2 < K; ++j2) quad += (j2 == j ? 1.0 : 2.0) * wr[j] * wr[j2] * tot[idx++];
+    }
+    const double m0 = lin / T0;                  // mean of the bias-free response
+    double var = quad / T0 - m0 * m0;
+    if (var < 0.0) var = 0.0;
+    mean[(int64_t)blockIdx.x * C + c] = (float)(m0 + (bias ? (double)bias[c] : 0.0));
+    rstd[(int64_t)blockIdx.x * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+// conv0 + GroupNorm + GELU apply pass for K = 10, S = 5 (HuBERT): the normalisation is folded into the taps
+// (w' = w rstd gamma, b' = beta + (bias - mean) rstd gamma), a thread owns two adjacent channels and walks the tile four
+// frames at a time so that 25 broadcast shared-memory loads feed 80 FMAs; outputs leave as packed pairs (coalesced
+// 4 / 8 bytes x 256 threads per frame).  bf16 output uses the 2-MUFU erf (|err| < 1.5e-7), fp32 output erff.
+__device__ __forceinline__ float gelu_erf_as(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // argument in [1, inf)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erfc_abs = poly * t * e;
+  return x * (x >= 0.f ? fmaf(-0.5f, erfc_abs, 1.0f) : 0.5f * erfc_abs);
+}
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+__device__ __forceinline__ float gelu_for(float v, float*) { return sib::gelu_erf(v); }
+__device__ __forceinline__ float gelu_for(float v, __nv_bfloat16*) { return gelu_erf_as(v); }
+
+template <typename TY>
+__global__ void __launch_bounds__(256) conv0_gn_apply_k10s5_kernel(const float* __restrict__ wave, int64_t wave_bs,
+                                                                    const float* __restrict__ w,
+                                                                    const float* __restrict__ bias, int C, int T0,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, TY* __restrict__ y) {
+  constexpr int K = 10, S = 5, TILE = 64;
+  __shared__ float xs[(TILE - 1) * S + K + 3];
+  const int b = blockIdx.y, t_begin = blockIdx.x * TILE;
+  const int nt = min(TILE, T0 - t_begin);
+  const int span = (nt - 1) * S + K;
+  const float* wb = wave + (int64_t)b * wave_bs + (int64_t)t_begin * S;
+  for (int i = threadIdx.x; i < (TILE - 1) * S + K + 3; i += blockDim.x) xs[i] = i < span ? wb[i] : 0.f;
+  __syncthreads();
+  for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {
+    float w0[K], w1[K];
+    const float g0 = rstd[b * C + c] * gamma[c], g1 = rstd[b * C + c + 1] * gamma[c + 1];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      w0[j] = w[c * K + j] * g0;
+      w1[j] = w[(c + 1) * K + j] * g1;
+    }
+    const float b0 = fmaf((bias ? bias[c] : 0.f) - mean[b * C + c], g0, beta[c]);
+    const float b1 = fmaf((bias ? bias[c + 1] : 0.f) - mean[b * C + c + 1], g1, beta[c + 1]);
+    TY* yb = y + ((int64_t)b * T0 + t_begin) * C + c;
+    for (int t = 0; t < nt; t += 4) {
+      float x[3 * S + K];
+#pragma unroll
+      for (int i = 0; i < 3 * S + K; ++i) x[i] = xs[t * S + i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float a0 = b0, a1 = b1;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          a0 = fmaf(w0[j], x[u * S + j], a0);
+          a1 = fmaf(w1[j], x[u * S + j], a1);
+        }
+        if (t + u < nt) st2(yb + (int64_t)(t + u) * C, gelu_for(a0, (TY*)nullptr), gelu_for(a1, (TY*)nullptr));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ z-norm
 // One CTA per utterance: mean, then centred sum of squares (two passes; the second hits L2), then apply.
 __global__ void __launch_bounds__(1024) znorm_kernel(const float* __restrict__ x, float* __restrict__ y, int n,
@@ -255,7 +389,14 @@ extern "C" int sib_conv0(int mode, const float* wave, int batch, int n_samples, 
                                                    nullptr, nullptr, nullptr, nullptr, nullptr);
   } else if (mode == 1) {
     SIB_REQUIRE(mean && rstd && gamma && beta && y, "sib_conv0_f32: mode 1 needs mean/rstd/gamma/beta/y");
-    if (y_dtype == SIB_BF16)
+    if (k == 10 && stride == 5 && c % 2 == 0) {
+      if (y_dtype == SIB_BF16)
+        conv0_gn_apply_k10s5_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(wave, wave_batch_stride, w, bias, c, t0, mean, rstd,
+                                                                        gamma, beta, (__nv_bfloat16*)y);
+      else
+        conv0_gn_apply_k10s5_kernel<float><<<grid, 256, 0, s>>>(wave, wave_batch_stride, w, bias, c, t0, mean, rstd, gamma,
+                                                                beta, (float*)y);
+    } else if (y_dtype == SIB_BF16)
       conv0_kernel<1, __nv_bfloat16><<<grid, 256, smem, s>>>(wave, n_samples, wave_batch_stride, w, bias, c, k, stride, t0,
                                                              nullptr, mean, rstd, gamma, beta, (__nv_bfloat16*)y);
     else
@@ -273,6 +414,20 @@ extern "C" int sib_conv0(int mode, const float* wave, int batch, int n_samples, 
     SIB_REQUIRE(false, "sib_conv0_f32: unknown mode %d", mode);
   }
   SIB_CHECK_LAUNCH("sib_conv0");
+  return SIB_OK;
+}
+
+extern "C" int sib_conv0_gn_stats_f32(const float* wave, int batch, int n_samples, int64_t wave_batch_stride,
+                                      const float* w, const float* bias, int c, int k, int stride, int t0, float eps,
+                                      float* mean, float* rstd, sib_stream_t stream) {
+  SIB_REQUIRE(wave && w && mean && rstd && batch > 0 && c > 0 && t0 > 0, "sib_conv0_gn_stats_f32: bad argument");
+  SIB_REQUIRE(k == 10 && stride == 5, "sib_conv0_gn_stats_f32: k=%d stride=%d unsupported (HuBERT conv0 is k=10, stride=5); "
+                                      "use sib_conv0 mode 0 + sib_gn_finalize_f32", k, stride);
+  SIB_REQUIRE((int64_t)(t0 - 1) * stride + k <= n_samples, "sib_conv0_gn_stats_f32: t0=%d does not fit n_samples=%d", t0,
+              n_samples);
+  conv0_gn_stats_kernel<10, 5><<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(wave, wave_batch_stride, w, bias, c, t0,
+                                                                                    eps, mean, rstd);
+  SIB_CHECK_LAUNCH("sib_conv0_gn_stats_f32");
   return SIB_OK;
 }
 

@@ -240,11 +240,15 @@ class HubertModel(_StateHolder):
             a = act_buf(B, t0, C)
             k0, s0 = cfg.conv_kernel[0], cfg.conv_stride[0]
             if cfg.feat_extract_norm == "group":
-                nt = ops.conv0_num_tiles(t0)
-                part = torch.empty(B, nt, C, 2, **real_f32)
                 mean, rstd = torch.empty(B, C, **real_f32), torch.empty(B, C, **real_f32)
-                ops.conv0(0, io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, partial=part)
-                ops.gn_finalize(part, B, nt, C, t0, 1e-5, mean, rstd)
+                if (k0, s0) == (10, 5):
+                    # closed-form statistics from the waveform's lag sums: no [B, T0, C] evaluation pass
+                    ops.conv0_gn_stats(io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, 1e-5, mean, rstd)
+                else:
+                    nt = ops.conv0_num_tiles(t0)
+                    part = torch.empty(B, nt, C, 2, **real_f32)
+                    ops.conv0(0, io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, partial=part)
+                    ops.gn_finalize(part, B, nt, C, t0, 1e-5, mean, rstd)
                 ops.conv0(1, io.wave, P["conv0.w"], P["conv0.b"], C, k0, s0, t0, mean=mean, rstd=rstd,
                           gamma=P["conv0.g"], beta=P["conv0.beta"], y=a)
             else:

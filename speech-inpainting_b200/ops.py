@@ -239,6 +239,14 @@ def gn_finalize(partial, batch, n_tiles, c, t0, eps, mean, rstd):
     _emit("sib_gn_finalize_f32", (_p(partial), batch, n_tiles, c, t0, eps, _p(mean), _p(rstd)), keep=(partial, mean, rstd))
 
 
+def conv0_gn_stats(wave, w, bias, c, k, stride, t0, eps, mean, rstd):
+    """GroupNorm statistics of conv0's output in closed form from the waveform (no conv0 evaluation pass)."""
+    B, n = wave.shape
+    _chk(wave, torch.float32, "wave"); _chk(mean, torch.float32, "mean"); _chk(rstd, torch.float32, "rstd")
+    _emit("sib_conv0_gn_stats_f32", (_p(wave), B, n, wave.stride(0), _p(w), _p(bias), c, k, stride, t0, eps, _p(mean), _p(rstd)),
+          keep=(wave, w, bias, mean, rstd))
+
+
 def layernorm(x, gamma, beta, y, eps=1e-5, residual=None, post_act=ACT_NONE):
     c = x.shape[-1]
     rows = x.numel() // c

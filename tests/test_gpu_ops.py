@@ -145,7 +145,16 @@ def test_conv0(sib, mode):
         mean, rstd = torch.empty(B, Cc, device="cuda"), torch.empty(B, Cc, device="cuda")
         sib.ops.conv0(0, x.cuda(), wd, None, Cc, 10, 5, t0, partial=part)
         sib.ops.gn_finalize(part, B, nt, Cc, t0, 1e-5, mean, rstd)
-        sib.ops.conv0(1, x.cuda(), wd, None, Cc, 10, 5, t0, mean=mean, rstd=rstd, gamma=g.cuda(), beta=be.cuda(), y=y)
+        # closed-form statistics from the waveform's lag sums must agree with the evaluated ones
+        mean2, rstd2 = torch.empty_like(mean), torch.empty_like(rstd)
+        sib.ops.conv0_gn_stats(x.cuda(), wd, None, Cc, 10, 5, t0, 1e-5, mean2, rstd2)
+        assert max_abs(h.mean(-1), mean2.cpu()) < 1e-5
+        assert max_abs(1.0 / torch.sqrt(h.var(-1, unbiased=False) + 1e-5), rstd2.cpu()) < 1e-4
+        assert max_abs(mean.cpu(), mean2.cpu()) < 1e-5 and max_abs(rstd.cpu(), rstd2.cpu()) < 1e-4
+        sib.ops.conv0(1, x.cuda(), wd, None, Cc, 10, 5, t0, mean=mean2, rstd=rstd2, gamma=g.cuda(), beta=be.cuda(), y=y)
+        yb = torch.empty(B, t0, Cc, device="cuda", dtype=torch.bfloat16)
+        sib.ops.conv0(1, x.cuda(), wd, None, Cc, 10, 5, t0, mean=mean2, rstd=rstd2, gamma=g.cuda(), beta=be.cuda(), y=yb)
+        assert max_abs(to_frame_major(ref), yb.float().cpu()) < 2e-2
     else:
         ref = F.gelu(F.layer_norm(h.transpose(1, 2), (Cc,), g, be, 1e-5)).transpose(1, 2)
         sib.ops.conv0(2, x.cuda(), wd, bias.cuda(), Cc, 10, 5, t0, y=y)
