@@ -163,6 +163,23 @@ int sib_mel_spectrogram_f32(const float* wave, int batch, int n, int hop, int pa
 int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void* w, const float* bias,
                     const void* residual, void* y, void* y_act /* nullable 2nd output = lrelu(y, act2_slope) */,
                     sib_stream_t stream);
+/* Fused ResBlock1 unit (I_ea/hifi_gan/models.py:36-43; I_da/src/models.py ResBlock1.forward) for the narrow stages:
+ *   y = (conv2_{k,1}(lrelu(conv1_{k,dilation}(lrelu(x, slope_in)) + b1, slope_mid)) + b2 + x [+ y_old]) * out_scale
+ *   y_act = lrelu(y, act2_slope)            (optional second output for an unfused consumer)
+ * x, y [B, T, C] frame-major bf16, C in {16, 32, 64}; w1 / w2 in the sib_conv1d_bf16 layout ([k][c_out][c_in]);
+ * both convolutions zero-pad ("same"), exactly like the two Conv1d modules.  The intermediate never leaves the SM.
+ * y must not alias x.  sib_resunit_bf16_supported() says whether (c, k, dilation) fits (weights stay resident). */
+typedef struct sib_resunit_desc {
+  int32_t batch, t, c, k, dilation;
+  int32_t accumulate;                 /* y += result before scaling (MRF sum, models.py:113-118) */
+  float slope_in, slope_mid, out_scale, act2_slope;
+  int64_t x_batch_stride, y_batch_stride; /* elements */
+  int32_t x_row_stride, y_row_stride;
+} sib_resunit_desc;
+int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const void* w1, const float* b1, const void* w2,
+                     const float* b2, void* y, void* y_act /* nullable */, sib_stream_t stream);
+int sib_resunit_bf16_supported(int c, int k, int dilation, int accumulate, int has_y_act);
+
 /* K-block geometry the kernel uses for c_in/groups: cc channels x tb taps per pipeline stage (cc*tb = 64). */
 int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb);
 

@@ -29,6 +29,17 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ResUnitDesc(C.Structure):
+    """mirror of `sib_resunit_desc`"""
+    _fields_ = [
+        ("batch", C.c_int32), ("t", C.c_int32), ("c", C.c_int32), ("k", C.c_int32), ("dilation", C.c_int32),
+        ("accumulate", C.c_int32),
+        ("slope_in", C.c_float), ("slope_mid", C.c_float), ("out_scale", C.c_float), ("act2_slope", C.c_float),
+        ("x_batch_stride", C.c_int64), ("y_batch_stride", C.c_int64),
+        ("x_row_stride", C.c_int32), ("y_row_stride", C.c_int32),
+    ]
+
+
 class SibError(RuntimeError):
     pass
 
@@ -59,6 +70,8 @@ _SIGS = {
     "sib_pack_int16_f32": ([_P, _P, _L, _P], _I),
     "sib_mel_spectrogram_f32": ([_P, _I, _I, _I, _I, _P, _I, _P, _I, _P], _I),
     "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
+    "sib_resunit_bf16": ([C.POINTER(ResUnitDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "sib_resunit_bf16_supported": ([_I, _I, _I, _I, _I], _I),
     "sib_conv1d_bf16_kblock": ([_I, C.POINTER(C.c_int), C.POINTER(C.c_int)], _I),
     "sib_layernorm": ([_P, _I, _P, _I, _P, _P, _P, _I, _L, _I, _F, _I, _P], _I),
     "sib_attention": ([_P, _I, _P, _P, _I, _I, _I, _I, _P], _I),

@@ -1,0 +1,468 @@
+// Fused HiFi-GAN ResBlock1 unit on the tensor cores (I_ea/hifi_gan/models.py:36-43, I_da/src/models.py ResBlock1):
+//     xt = leaky_relu(x, 0.1); xt = conv1_{k, dilation d}(xt); xt = leaky_relu(xt, 0.1); xt = conv2_{k, 1}(xt); x = xt + x
+// for the narrow, HBM-bound stages (C = 64 / 32 / 16 channels, frame-major bf16 [B, T, C]).  Unfused, one unit moves six
+// activation tensors through HBM (conv1: read lrelu(x), write t1; conv2: read t1, read x, write y, write lrelu(y));
+// here it reads x once (plus the dilated halo) and writes y once:
+//   * TMA brings a (128 + 2 p1)-row tile of raw x into shared memory (zero fill outside [0, T) == the convs' padding);
+//     two warps apply the leaky-relu IN PLACE (generic proxy -> fence.proxy.async) - the TMA-fed MMA cannot
+//     transform its A operand, but it can be handed a transformed tile;
+//   * conv1 = k taps x (C/16) tcgen05.mma, every tap a row-shifted descriptor on that tile, weights resident;
+//   * epilogue 1: TMEM -> + b1 -> leaky-relu -> rows outside [0, T) zeroed (conv2 pads t1 with zeros, not with
+//     conv1 of padding) -> bf16 -> shared memory in the swizzled K-major layout of an A operand (never touches HBM);
+//   * conv2 = k taps on that intermediate tile; epilogue 2: + b2 + x (+ the running MRF sum) x scale -> TMA store.
+//     R = 128 - (k - 1) output rows per tile (the intermediate needs conv2's halo); the last quarter stores through a
+//     shorter box so that rows >= R are never written.
+// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer (conv1 runs one tile ahead of conv2 so the tensor pipe works
+// while epilogue 1 converts), 2-3 activation, 4-7 epilogue 1, 8-11 epilogue 2 (one warp per TMEM lane quarter each).
+// Both accumulators are double-buffered in TMEM (4 C columns).  C = 32 / 16 fit two CTAs per SM.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace sib_tc;
+
+constexpr int NUM_THREADS = 384;
+
+struct RuArgs {
+  const float* b1;
+  const float* b2;
+  int T, C, k, dil, batch;
+  int R, p1, p2, xr, tail_rows;
+  int tiles_m, total_tiles;
+  int row_bytes, ksteps, tap_bytes;
+  int x_stage_bytes, t1_bytes, w_bytes, w_tx_bytes, w_tg, w_loads;   // per-conv weight region: w_loads boxes of w_tg taps
+  int stage_box_bytes;                                   // one staging tile: 128 rows x C bf16
+  int need_b;                                            // second staging box per slot (accumulate input / y_act output)
+  float slope_in, slope_mid, out_scale, act2_slope;
+  int accumulate, has_y2;
+  uint32_t desc_hi, idesc;
+  uint32_t tmem_cols;
+};
+
+template <int UNUSED = 0>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
+                  const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yt,
+                  const __grid_constant__ CUtensorMap map_y2, const __grid_constant__ CUtensorMap map_y2t,
+                  const __grid_constant__ RuArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_x = smem;                                   // [2] raw -> activated x tiles
+  uint8_t* sm_t1 = sm_x + 2 * p.x_stage_bytes;            // conv1 output tile (A operand of conv2)
+  uint8_t* sm_w1 = sm_t1 + p.t1_bytes;
+  uint8_t* sm_w2 = sm_w1 + p.w_bytes;
+  uint8_t* sm_sa = sm_w2 + p.w_bytes;                     // [2] staging A: residual in -> y out
+  uint8_t* sm_sb = sm_sa + 2 * p.stage_box_bytes;         // [2] staging B: accumulate in -> y_act out
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_sb + (p.need_b ? 2 * p.stage_box_bytes : 0));
+  uint64_t* x_full = bars;            // [2]
+  uint64_t* x_empty = bars + 2;       // [2]
+  uint64_t* act_done = bars + 4;      // [2]
+  uint64_t* acc1_full = bars + 6;     // [2]
+  uint64_t* acc1_empty = bars + 8;    // [2]
+  uint64_t* acc2_full = bars + 10;    // [2]
+  uint64_t* acc2_empty = bars + 12;   // [2]
+  uint64_t* t1_full = bars + 14;
+  uint64_t* t1_empty = bars + 15;
+  uint64_t* w_full = bars + 16;
+  uint64_t* res_bar = bars + 17;      // [4 quarters][2 slots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 25);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_w1);
+    prefetch_tensormap(&map_w2);
+    prefetch_tensormap(&map_res);
+    prefetch_tensormap(&map_y);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+      mbar_init(&act_done[s], 2);
+      mbar_init(&acc1_full[s], 1);
+      mbar_init(&acc1_empty[s], 4);
+      mbar_init(&acc2_full[s], 1);
+      mbar_init(&acc2_empty[s], 4);
+    }
+    mbar_init(t1_full, 4);
+    mbar_init(t1_empty, 1);
+    mbar_init(w_full, 1);
+    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_my = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto tile_of = [&](int i, int& t0, int& b) {
+    const int tile = blockIdx.x + i * gridDim.x;
+    b = tile / p.tiles_m;
+    t0 = (tile - b * p.tiles_m) * p.R;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer: weights once, then one raw x tile per output tile =====================
+    const uint32_t issuer = elect_one_sync();
+    if (issuer) {
+      mbar_expect_tx(w_full, (uint32_t)(2 * p.w_tx_bytes));
+      for (int l = 0; l < p.w_loads; ++l) {
+        tma_load_3d(sm_w1 + l * p.w_tg * p.tap_bytes, &map_w1, w_full, 0, 0, l * p.w_tg);
+        tma_load_3d(sm_w2 + l * p.w_tg * p.tap_bytes, &map_w2, w_full, 0, 0, l * p.w_tg);
+      }
+    }
+    for (int i = 0; i < n_my; ++i) {
+      int t0, b;
+      tile_of(i, t0, b);
+      const int s = i & 1;
+      mbar_wait(&x_empty[s], ((i >> 1) & 1) ^ 1);
+      if (issuer) {
+        mbar_expect_tx(&x_full[s], (uint32_t)(p.xr * p.row_bytes));
+        tma_load_3d(sm_x + s * p.x_stage_bytes, &map_x, &x_full[s], 0, t0 - p.p2 - p.p1, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
+    const uint32_t issuer = elect_one_sync();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t x_base = smem_u32(sm_x), t1_base = smem_u32(sm_t1);
+    const uint64_t w1desc = make_smem_desc(smem_u32(sm_w1), p.desc_hi);
+    const uint64_t w2desc = make_smem_desc(smem_u32(sm_w2), p.desc_hi);
+    const uint64_t a1_inc = (uint64_t)((p.dil * p.row_bytes) >> 4);
+    const uint64_t a2_inc = (uint64_t)(p.row_bytes >> 4);
+    const uint64_t w_inc = (uint64_t)(p.tap_bytes >> 4);
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    auto conv1 = [&](int i) {
+      const int s = i & 1;
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      mbar_wait(&act_done[s], ph);
+      mbar_wait(&acc1_empty[s], ph ^ 1);
+      tc_fence_after();
+      uint64_t adesc = make_smem_desc(x_base + (uint32_t)(s * p.x_stage_bytes), p.desc_hi);
+      uint64_t bdesc = w1desc;
+      const uint32_t d = tmem_u + (uint32_t)(s * p.C);
+      for (int j = 0; j < p.k; ++j) {
+        if (issuer)
+          for (int ks = 0; ks < p.ksteps; ++ks) umma_bf16(d, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (uint32_t)(j | ks));
+        adesc += a1_inc;
+        bdesc += w_inc;
+      }
+      if (issuer) {
+        umma_commit(&acc1_full[s]);
+        umma_commit(&x_empty[s]);
+      }
+    };
+    auto conv2 = [&](int i) {
+      const int a = i & 1;
+      mbar_wait(t1_full, (uint32_t)(i & 1));
+      mbar_wait(&acc2_empty[a], (uint32_t)(((i >> 1) & 1) ^ 1));
+      tc_fence_after();
+      uint64_t adesc = make_smem_desc(t1_base, p.desc_hi);
+      uint64_t bdesc = w2desc;
+      const uint32_t d = tmem_u + (uint32_t)((2 + a) * p.C);
+      for (int j = 0; j < p.k; ++j) {
+        if (issuer)
+          for (int ks = 0; ks < p.ksteps; ++ks) umma_bf16(d, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (uint32_t)(j | ks));
+        adesc += a2_inc;
+        bdesc += w_inc;
+      }
+      if (issuer) {
+        umma_commit(&acc2_full[a]);
+        umma_commit(t1_empty);
+      }
+    };
+    if (n_my > 0) conv1(0);
+    for (int i = 0; i < n_my; ++i) {
+      if (i + 1 < n_my) conv1(i + 1);
+      conv2(i);
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ===================== activation: leaky-relu in place on the freshly landed x tile =====================
+    const int tid = threadIdx.x - 64;
+    const int n16 = (p.xr * p.row_bytes) >> 4;
+    const float slope = p.slope_in;
+    for (int i = 0; i < n_my; ++i) {
+      const int s = i & 1;
+      mbar_wait(&x_full[s], (uint32_t)((i >> 1) & 1));
+      uint4* tile = reinterpret_cast<uint4*>(sm_x + s * p.x_stage_bytes);
+      for (int e = tid; e < n16; e += 64) {
+        float f[8];
+        unpack8(tile[e], f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] = f[u] > 0.f ? f[u] : f[u] * slope;
+        tile[e] = pack8(f);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&act_done[s]);
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue 1: conv1 accumulator -> lrelu -> bf16 A tile of conv2 =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                               // tile row == TMEM lane == t1-local row
+    const int chunks_per_row = p.row_bytes >> 4;
+    const int swz_shift = p.row_bytes == 128 ? 0 : (p.row_bytes == 64 ? 1 : 2);
+    const uint32_t swz = ((uint32_t)r >> swz_shift) & (uint32_t)(chunks_per_row - 1);
+    uint8_t* row_ptr = sm_t1 + r * p.row_bytes;
+    for (int i = 0; i < n_my; ++i) {
+      int t0, b;
+      tile_of(i, t0, b);
+      const int a = i & 1;
+      mbar_wait(&acc1_full[a], (uint32_t)((i >> 1) & 1));
+      mbar_wait(t1_empty, (uint32_t)((i & 1) ^ 1));            // conv2 of the previous tile has read T1
+      tc_fence_after();
+      const int tg = t0 - p.p2 + r;                            // global frame of this t1 row
+      const bool inside = tg >= 0 && tg < p.T;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.C);
+      for (int c0 = 0; c0 < p.C; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = c0 + 8 * h;
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b1 + col));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + col + 4));
+          float f[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            f[u] += __uint_as_float(v[8 * h + u]);
+            f[u] = f[u] > 0.f ? f[u] : f[u] * p.slope_mid;
+            f[u] = inside ? f[u] : 0.f;
+          }
+          *reinterpret_cast<uint4*>(row_ptr + ((((uint32_t)col >> 3) ^ swz) << 4)) = pack8(f);
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(t1_full);
+        mbar_arrive(&acc1_empty[a]);
+      }
+    }
+  } else {
+    // ===================== epilogue 2: conv2 accumulator + bias + x (+ running sum) -> y (and lrelu(y)) ==========
+    const int q = warp & 3;
+    const int chunks_per_row = p.row_bytes >> 4;
+    const int swz_shift = p.row_bytes == 128 ? 0 : (p.row_bytes == 64 ? 1 : 2);
+    const uint32_t swz = ((uint32_t)lane >> swz_shift) & (uint32_t)(chunks_per_row - 1);
+    const int box_bytes = 32 * p.row_bytes;
+    const uint32_t pre_bytes = (uint32_t)(1 + (p.accumulate ? 1 : 0)) * (uint32_t)box_bytes;
+    const int rows_q = q < 3 ? 32 : p.tail_rows;               // rows of this quarter that belong to the tile (R = 96 + tail)
+    uint64_t* my_res = res_bar + q * 2;
+    auto prefetch = [&](int i) {                               // lane 0 only
+      int t0, b;
+      tile_of(i, t0, b);
+      const int slot = i & 1;
+      mbar_expect_tx(&my_res[slot], pre_bytes);
+      tma_load_3d(sm_sa + slot * p.stage_box_bytes + q * box_bytes, &map_res, &my_res[slot], 0, t0 + q * 32, b);
+      if (p.accumulate)
+        tma_load_3d(sm_sb + slot * p.stage_box_bytes + q * box_bytes, &map_y, &my_res[slot], 0, t0 + q * 32, b);
+    };
+    if (lane == 0 && n_my > 0) prefetch(0);
+    for (int i = 0; i < n_my; ++i) {
+      int t0, b;
+      tile_of(i, t0, b);
+      const int a = i & 1, slot = i & 1;
+      if (lane == 0) {
+        // the other slot was stored from one tile ago: once those stores have left shared memory, refill it
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (i + 1 < n_my) prefetch(i + 1);
+      }
+      __syncwarp();
+      uint8_t* box_a = sm_sa + slot * p.stage_box_bytes + q * box_bytes + lane * p.row_bytes;
+      uint8_t* box_b = sm_sb + slot * p.stage_box_bytes + q * box_bytes + lane * p.row_bytes;
+      mbar_wait(&acc2_full[a], (uint32_t)((i >> 1) & 1));
+      mbar_wait(&my_res[slot], (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + a) * p.C);
+      for (int c0 = 0; c0 < p.C; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = c0 + 8 * h;
+          const uint32_t off = (((uint32_t)col >> 3) ^ swz) << 4;
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + col));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col + 4));
+          float f[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          float xr[8];
+          unpack8(*reinterpret_cast<const uint4*>(box_a + off), xr);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[u] += __uint_as_float(v[8 * h + u]) + xr[u];
+          if (p.accumulate) {
+            float o[8];
+            unpack8(*reinterpret_cast<const uint4*>(box_b + off), o);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] += o[u];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[u] *= p.out_scale;
+          *reinterpret_cast<uint4*>(box_a + off) = pack8(f);
+          if (p.has_y2) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] = f[u] > 0.f ? f[u] : f[u] * p.act2_slope;
+            *reinterpret_cast<uint4*>(box_b + off) = pack8(f);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&acc2_empty[a]);
+        if (rows_q > 0) {
+          const uint8_t* src_a = sm_sa + slot * p.stage_box_bytes + q * box_bytes;
+          const uint8_t* src_b = sm_sb + slot * p.stage_box_bytes + q * box_bytes;
+          tma_store_3d(q < 3 ? &map_y : &map_yt, src_a, 0, t0 + q * 32, b);
+          if (p.has_y2) tma_store_3d(q < 3 ? &map_y2 : &map_y2t, src_b, 0, t0 + q * 32, b);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+struct RuPlan {
+  RuArgs a;
+  int smem_bytes, ctas_per_sm;
+};
+
+int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out) {
+  if (!(c == 64 || c == 32 || c == 16)) {
+    sib::set_error("sib_resunit_bf16: c=%d unsupported (16 / 32 / 64; wider stages use sib_conv1d_bf16)", c);
+    return SIB_ERR_UNSUPPORTED;
+  }
+  if (k < 1 || (k & 1) == 0 || k > 15 || dil < 1) {
+    sib::set_error("sib_resunit_bf16: k=%d dilation=%d unsupported (odd k <= 15)", k, dil);
+    return SIB_ERR_UNSUPPORTED;
+  }
+  RuArgs& a = out->a;
+  memset(&a, 0, sizeof(a));
+  a.C = c; a.k = k; a.dil = dil;
+  a.p2 = (k - 1) / 2;
+  a.p1 = (k - 1) * dil / 2;
+  a.R = 128 - 2 * a.p2;
+  a.xr = 128 + 2 * a.p1;
+  a.tail_rows = a.R - 96;
+  if (a.xr > 256 || a.tail_rows < 1) {
+    sib::set_error("sib_resunit_bf16: k=%d dilation=%d needs a %d-row halo tile (max 256)", k, dil, a.xr);
+    return SIB_ERR_UNSUPPORTED;
+  }
+  a.row_bytes = c * 2;
+  a.ksteps = c / 16;
+  a.tap_bytes = c * a.row_bytes;
+  a.x_stage_bytes = (a.xr * a.row_bytes + 1023) / 1024 * 1024;
+  a.t1_bytes = ((128 + k - 1) * a.row_bytes + 1023) / 1024 * 1024;
+  a.w_tg = 16384 / a.tap_bytes;
+  if (a.w_tg > k) a.w_tg = k;
+  if (a.w_tg < 1) a.w_tg = 1;
+  a.w_loads = (k + a.w_tg - 1) / a.w_tg;
+  a.w_tx_bytes = a.w_loads * a.w_tg * a.tap_bytes;   // full boxes: taps past k are TMA zero fill but still counted
+  a.w_bytes = (a.w_tx_bytes + 1023) / 1024 * 1024;
+  a.stage_box_bytes = 128 * a.row_bytes;
+  a.need_b = (accumulate || has_y2) ? 1 : 0;
+  a.accumulate = accumulate; a.has_y2 = has_y2;
+  a.desc_hi = make_desc_hi(a.row_bytes);
+  a.idesc = make_idesc_bf16(128, c);
+  a.tmem_cols = 4 * c < 32 ? 32 : 4 * c;
+  out->smem_bytes = 2 * a.x_stage_bytes + a.t1_bytes + 2 * a.w_bytes + 2 * a.stage_box_bytes * (1 + a.need_b) + 512 + 1024;
+  if (out->smem_bytes > 227 * 1024) {
+    sib::set_error("sib_resunit_bf16: c=%d k=%d dilation=%d needs %d bytes of shared memory (weights must stay resident)",
+                   c, k, dil, out->smem_bytes);
+    return SIB_ERR_UNSUPPORTED;
+  }
+  out->ctas_per_sm = out->smem_bytes <= 112 * 1024 ? 2 : 1;
+  return SIB_OK;
+}
+
+}  // namespace
+
+extern "C" int sib_resunit_bf16_supported(int c, int k, int dilation, int accumulate, int has_y_act) {
+  RuPlan pl;
+  return plan_resunit(c, k, dilation, accumulate, has_y_act, &pl) == SIB_OK ? 1 : 0;
+}
+
+extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const void* w1, const float* b1, const void* w2,
+                                const float* b2, void* y, void* y_act, sib_stream_t stream) {
+  SIB_REQUIRE(d && x && w1 && b1 && w2 && b2 && y, "sib_resunit_bf16: null argument");
+  SIB_REQUIRE(d->batch > 0 && d->t > 0, "sib_resunit_bf16: empty shape");
+  SIB_REQUIRE(x != y && x != y_act, "sib_resunit_bf16: in-place operation is not supported (tiles read x halos)");
+  RuPlan pl;
+  if (int rc = plan_resunit(d->c, d->k, d->dilation, d->accumulate, y_act != nullptr, &pl)) return rc;
+  RuArgs& a = pl.a;
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+  SIB_REQUIRE(al16(x) && al16(y) && al16(w1) && al16(w2) && al16(b1) && al16(b2) && (!y_act || al16(y_act)),
+              "sib_resunit_bf16: pointers must be 16-byte aligned");
+  SIB_REQUIRE(d->x_row_stride % 8 == 0 && d->x_batch_stride % 8 == 0 && d->y_row_stride % 8 == 0 && d->y_batch_stride % 8 == 0,
+              "sib_resunit_bf16: strides must be multiples of 8 elements");
+  a.b1 = b1; a.b2 = b2;
+  a.T = d->t; a.batch = d->batch;
+  a.slope_in = d->slope_in; a.slope_mid = d->slope_mid; a.out_scale = d->out_scale; a.act2_slope = d->act2_slope;
+  a.tiles_m = sib::ceil_div(d->t, a.R);
+  const int64_t total = (int64_t)a.tiles_m * d->batch;
+  SIB_REQUIRE(total < (1ll << 31), "sib_resunit_bf16: too many tiles");
+  a.total_tiles = (int)total;
+  const CUtensorMapSwizzle swz = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                    : (a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const char* who = "sib_resunit_bf16";
+  CUtensorMap map_x, map_w1, map_w2, map_res, map_y, map_yt, map_y2, map_y2t;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)d->c, (cuuint64_t)d->t, (cuuint64_t)d->batch};
+    const cuuint64_t xs[3] = {2, (cuuint64_t)d->x_row_stride * 2, (cuuint64_t)d->x_batch_stride * 2};
+    const cuuint64_t ys[3] = {2, (cuuint64_t)d->y_row_stride * 2, (cuuint64_t)d->y_batch_stride * 2};
+    const cuuint32_t box_x[3] = {(cuuint32_t)d->c, (cuuint32_t)a.xr, 1};
+    const cuuint32_t box_q[3] = {(cuuint32_t)d->c, 32, 1};
+    const cuuint32_t box_t[3] = {(cuuint32_t)d->c, (cuuint32_t)a.tail_rows, 1};
+    if (int rc = encode_map(&map_x, x, 3, dims, xs, box_x, swz, who, "x")) return rc;
+    if (int rc = encode_map(&map_res, x, 3, dims, xs, box_q, swz, who, "x (residual)")) return rc;
+    if (int rc = encode_map(&map_y, y, 3, dims, ys, box_q, swz, who, "y")) return rc;
+    if (int rc = encode_map(&map_yt, y, 3, dims, ys, box_t, swz, who, "y (tail)")) return rc;
+    if (int rc = encode_map(&map_y2, y_act ? y_act : y, 3, dims, ys, box_q, swz, who, "y_act")) return rc;
+    if (int rc = encode_map(&map_y2t, y_act ? y_act : y, 3, dims, ys, box_t, swz, who, "y_act (tail)")) return rc;
+  }
+  {
+    // weights in the sib_conv1d_bf16 layout [1][1 chunk][k][c_out][c_in]: one K-major slab per tap
+    const cuuint64_t dims[3] = {(cuuint64_t)d->c, (cuuint64_t)d->c, (cuuint64_t)d->k};
+    const cuuint64_t ws[3] = {2, (cuuint64_t)d->c * 2, (cuuint64_t)d->c * d->c * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)d->c, (cuuint32_t)d->c, (cuuint32_t)a.w_tg};
+    if (int rc = encode_map(&map_w1, w1, 3, dims, ws, box, swz, who, "w1")) return rc;
+    if (int rc = encode_map(&map_w2, w2, 3, dims, ws, box, swz, who, "w2")) return rc;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)resunit_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      sib::set_error("sib_resunit_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return SIB_ERR_CUDA;
+    }
+    attr_set[dev] = true;
+  }
+  const int slots = sm_count_of_current_device() * pl.ctas_per_sm;
+  const int grid = a.total_tiles < slots ? a.total_tiles : slots;
+  const RuArgs args = a;
+  resunit_tc_kernel<0><<<grid, NUM_THREADS, pl.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+      map_x, map_w1, map_w2, map_res, map_y, map_yt, map_y2, map_y2t, args);
+  SIB_CHECK_LAUNCH("sib_resunit_bf16");
+  return SIB_OK;
+}

@@ -60,6 +60,7 @@ class Generator(_StateHolder):
         self._weight_norm_removed = False
         self._plans = {}
         self.use_cuda_graph = False
+        self.use_fused_resunits = True   # bf16 arm: fused ResBlock1 units on the narrow stages (A/B switch)
 
     # ---- state
     def _conv_names(self):
@@ -167,12 +168,26 @@ class Generator(_StateHolder):
                 last_stage = i == self.num_upsamples - 1
                 up, up_act = view(UP, L_, C_), view(UPA, L_, C_)
                 xs, xs_act = (view(XS0, L_, C_), view(XS0A, L_, C_)) if i % 2 == 0 else (view(XS1, L_, C_), view(XS1A, L_, C_))
+                # Narrow stages (C <= 64) run fused ResBlock1 units (sib_resunit_bf16: lrelu -> conv1 -> lrelu -> conv2 ->
+                # + x in one kernel, raw x in, y out) wherever the unit's weights fit in shared memory; a fused unit
+                # needs no activated copy of its input, so y_act / up_act are only written for unfused consumers.
+                fused = []
+                for j, (rk, dils) in enumerate(zip(self.rb_kernels, self.rb_dilations)):
+                    row = [False] * len(dils)
+                    for m in reversed(range(len(dils))):
+                        last_m = m == len(dils) - 1
+                        # a unit writes lrelu(y) only for an unfused consumer (next unit / next stage / conv_post)
+                        need_act = (j == self.num_kernels - 1) if last_m else (not row[m + 1])
+                        row[m] = (self.resblock == "1" and self.use_fused_resunits and
+                                  ops.resunit_supported(C_, rk, dils[m], last_m and j > 0, need_act))
+                    fused.append(row)
+                need_up_act = not all(f[0] for f in fused)
                 ops.conv1d(cur_act, P[f"ups.{i}.w"], P[f"ups.{i}.b"], up.view(B, t_in, u * C_), P[f"ups.{i}.taps"],
-                           y_act=up_act.view(B, t_in, u * C_), act2_slope=LRELU_SLOPE)
+                           y_act=up_act.view(B, t_in, u * C_) if need_up_act else None, act2_slope=LRELU_SLOPE)
                 for j, (rk, dils) in enumerate(zip(self.rb_kernels, self.rb_dilations)):
                     n = i * self.num_kernels + j
                     last_j = j == self.num_kernels - 1
-                    xcur, xcur_act = up, up_act
+                    xcur, xcur_act = up, (up_act if need_up_act else None)
                     for m, dl in enumerate(dils):
                         last_m = m == len(dils) - 1
                         if last_m:
@@ -182,17 +197,26 @@ class Generator(_StateHolder):
                         else:
                             dst, dst_act = (view(PA, L_, C_), view(PAA, L_, C_)) if m % 2 == 0 else (view(PB, L_, C_), view(PBA, L_, C_))
                             slope2 = LRELU_SLOPE
-                        kw = dict(accumulate=last_m and j > 0, out_scale=(1.0 / self.num_kernels) if (last_m and last_j) else 1.0,
-                                  residual=xcur, y_act=dst_act, act2_slope=slope2)
-                        if self.resblock == "1":
-                            t1 = view(T1, L_, C_)
-                            ops.conv1d(xcur_act, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
-                                       t1, ops.conv_taps(rk, dl, get_padding(rk, dl)), post_act=ops.ACT_LRELU, post_slope=LRELU_SLOPE)
-                            ops.conv1d(t1, P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
-                                       dst, ops.conv_taps(rk, 1, get_padding(rk, 1)), **kw)
+                            if fused[j][m + 1]:
+                                dst_act = None      # the consumer activates its own input tile
+                        acc = last_m and j > 0
+                        scale = (1.0 / self.num_kernels) if (last_m and last_j) else 1.0
+                        if fused[j][m]:
+                            ops.resunit(xcur, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
+                                        P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
+                                        dst, rk, dl, y_act=dst_act, accumulate=acc, out_scale=scale,
+                                        slope_in=LRELU_SLOPE, slope_mid=LRELU_SLOPE, act2_slope=slope2)
                         else:
-                            ops.conv1d(xcur_act, P[f"resblocks.{n}.convs.{m}.w"], self._sd[f"resblocks.{n}.convs.{m}.bias"],
-                                       dst, ops.conv_taps(rk, dl, get_padding(rk, dl)), **kw)
+                            kw = dict(accumulate=acc, out_scale=scale, residual=xcur, y_act=dst_act, act2_slope=slope2)
+                            if self.resblock == "1":
+                                t1 = view(T1, L_, C_)
+                                ops.conv1d(xcur_act, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
+                                           t1, ops.conv_taps(rk, dl, get_padding(rk, dl)), post_act=ops.ACT_LRELU, post_slope=LRELU_SLOPE)
+                                ops.conv1d(t1, P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
+                                           dst, ops.conv_taps(rk, 1, get_padding(rk, 1)), **kw)
+                            else:
+                                ops.conv1d(xcur_act, P[f"resblocks.{n}.convs.{m}.w"], self._sd[f"resblocks.{n}.convs.{m}.bias"],
+                                           dst, ops.conv_taps(rk, dl, get_padding(rk, dl)), **kw)
                         xcur, xcur_act = dst, dst_act
                 cur_act = xs_act
                 t_in = L_

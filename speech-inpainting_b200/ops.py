@@ -13,7 +13,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_TANH, ConvDesc, SibError  # noqa: F401
+from ._lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_TANH, ConvDesc, ResUnitDesc, SibError  # noqa: F401
 
 _active_plan = None
 
@@ -207,6 +207,27 @@ def conv1d(x, w, bias, y, taps, *, stride=1, groups=1, residual=None, y_act=None
               keep=(d, x, w, bias, residual, y, y_act))
     else:
         raise SibError(f"unsupported dtype {x.dtype}")
+
+
+def resunit_supported(c: int, k: int, dilation: int, accumulate: bool = False, has_y_act: bool = False) -> bool:
+    return bool(_lib.lib().sib_resunit_bf16_supported(c, k, dilation, int(accumulate), int(has_y_act)))
+
+
+def resunit(x, w1, b1, w2, b2, y, k, dilation, *, y_act=None, accumulate=False, out_scale=1.0, slope_in=0.1,
+            slope_mid=0.1, act2_slope=0.1):
+    """Fused ResBlock1 unit: y = (conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 + x [+ y]) * out_scale on bf16 [B,T,C]."""
+    B, T, Cc = x.shape
+    for t, nme in ((x, "x"), (w1, "w1"), (w2, "w2"), (y, "y"), (y_act, "y_act")):
+        _chk(t, torch.bfloat16, nme)
+    _chk(b1, torch.float32, "b1"); _chk(b2, torch.float32, "b2")
+    d = ResUnitDesc()
+    d.batch, d.t, d.c, d.k, d.dilation = B, T, Cc, k, dilation
+    d.accumulate = int(accumulate)
+    d.slope_in, d.slope_mid, d.out_scale, d.act2_slope = slope_in, slope_mid, out_scale, act2_slope
+    d.x_batch_stride, d.y_batch_stride = x.stride(0), y.stride(0)
+    d.x_row_stride, d.y_row_stride = x.stride(1), y.stride(1)
+    _emit("sib_resunit_bf16", (C.byref(d), _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y), _p(y_act)),
+          keep=(d, x, w1, b1, w2, b2, y, y_act))
 
 
 def linear(x2d, w, bias, y2d, *, residual=None, **kw):

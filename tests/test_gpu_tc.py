@@ -149,3 +149,53 @@ def test_attention_bf16_tc(sib, B, T, nh, padded):
     err = (ref - got).abs().max().item()
     assert err < 2.5e-2 * max(1.0, ref.abs().max().item()), f"max err {err:.4g} (ref max {ref.abs().max():.3g})"
     assert (ref - got).abs().mean().item() < 3e-3
+
+
+RU_CASES = [
+    # B, T, C, k, dil, accumulate, y_act, scale
+    (2, 1000, 32, 3, 1, False, False, 1.0),
+    (2, 777, 32, 7, 3, False, False, 1.0),
+    (3, 500, 32, 11, 5, True, True, 1.0 / 3),
+    (1, 118, 32, 11, 1, False, True, 1.0),       # exactly one tile
+    (2, 119, 32, 11, 5, True, False, 1.0),       # one row into the second tile
+    (2, 640, 64, 3, 5, False, False, 1.0),
+    (2, 300, 64, 3, 1, True, True, 1.0 / 3),
+    (2, 333, 64, 7, 3, False, True, 1.0),
+    (2, 50, 64, 7, 1, False, False, 1.0),        # shorter than one tile
+    (2, 400, 16, 3, 1, False, False, 1.0),       # I_da last stage
+    (2, 401, 16, 11, 5, True, True, 1.0 / 3),
+]
+
+
+@pytest.mark.parametrize("case", RU_CASES)
+def test_resunit_bf16(sib, case):
+    """Fused ResBlock1 unit (models.py:36-43) vs the two torch convs in fp32 on the same bf16-rounded operands; the
+    intermediate is rounded to bf16 in the kernel (it is the A operand of conv2), so the reference rounds it too."""
+    B, T, C, k, dil, accumulate, want_act, scale = case
+    ops = sib.ops
+    if not ops.resunit_supported(C, k, dil, accumulate, want_act):
+        pytest.skip("configuration does not fit in shared memory")
+    x = _bf(_rand(B, C, T, seed=1))
+    w1 = _bf(_rand(C, C, k, seed=2, scale=1.0 / math.sqrt(C * k)))
+    w2 = _bf(_rand(C, C, k, seed=3, scale=1.0 / math.sqrt(C * k)))
+    b1, b2 = _rand(C, seed=4, scale=0.1), _rand(C, seed=5, scale=0.1)
+    y_old = _bf(_rand(B, C, T, seed=6))
+    t1 = _bf(F.leaky_relu(F.conv1d(F.leaky_relu(x, 0.1), w1, b1, padding=(k - 1) * dil // 2, dilation=dil), 0.1))
+    ref = F.conv1d(t1, w2, b2, padding=(k - 1) // 2) + x
+    if accumulate:
+        ref = ref + y_old
+    ref = ref * scale
+    xd = to_frame_major(x).cuda().to(torch.bfloat16).contiguous()
+    yd = to_frame_major(y_old).cuda().to(torch.bfloat16).contiguous() if accumulate else \
+        torch.full((B, T, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ya = torch.full((B, T, C), float("nan"), device="cuda", dtype=torch.bfloat16) if want_act else None
+    w1d = ops.to_kmajor_bf16(ops.pack_conv_weight(w1.cuda()))
+    w2d = ops.to_kmajor_bf16(ops.pack_conv_weight(w2.cuda()))
+    ops.resunit(xd, w1d, b1.cuda(), w2d, b2.cuda(), yd, k, dil, y_act=ya, accumulate=accumulate, out_scale=scale,
+                act2_slope=0.01)
+    torch.cuda.synchronize()
+    got = yd.float().cpu()
+    assert torch.isfinite(got).all()
+    _close(to_frame_major(ref), got, f"resunit {case}")
+    if want_act:
+        _close(to_frame_major(F.leaky_relu(ref, 0.01)), ya.float().cpu(), f"resunit y_act {case}")
