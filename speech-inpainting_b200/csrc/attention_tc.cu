@@ -148,7 +148,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
     const int r = threadIdx.x;
     const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t t_o = t_s + TMEM_O;
-    uint8_t* prow = smem + SM_P + r * 128;
+    const uint32_t prow = smem_u32(smem + SM_P + r * 128);
     const uint32_t swz = (uint32_t)(r & 7);
     const float c = 0.125f * 1.4426950408889634f;  // d^-1/2 * log2(e)
     float o_acc[HD];
@@ -181,13 +181,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
           p[i] = (c0 + i < nk) ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
           sum += p[i];
         }
-        uint8_t* chunk = prow + (c0 >> 6) * TILE_BYTES;
+        const uint32_t chunk = prow + (uint32_t)((c0 >> 6) * TILE_BYTES);
         const uint32_t u = (uint32_t)((c0 & 63) >> 3);
         float lo[8], hi[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { lo[i] = p[i]; hi[i] = p[8 + i]; }
-        *reinterpret_cast<uint4*>(chunk + ((u ^ swz) << 4)) = pack8(lo);
-        *reinterpret_cast<uint4*>(chunk + (((u + 1) ^ swz) << 4)) = pack8(hi);
+        sts128(chunk + ((u ^ swz) << 4), pack8(lo));
+        sts128(chunk + (((u + 1) ^ swz) << 4), pack8(hi));
       }
       l_run = l_run * alpha + sum;
       m_run = m_new;

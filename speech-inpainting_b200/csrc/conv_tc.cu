@@ -257,43 +257,35 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t b_base = smem_u32(b_region);
-    const uint64_t a_tap_inc = (uint64_t)((p.tap_step * row_bytes_k) >> 4);   // next tap = shifted rows
-    const uint64_t b_tap_inc = (uint64_t)(p.b_tap_bytes >> 4);
+    // descriptor low words only (32-bit arithmetic): next tap = row-shifted A view / next weight slab
+    const uint32_t a_tap_inc = (uint32_t)((p.tap_step * row_bytes_k) >> 4);
+    const uint32_t b_tap_inc = (uint32_t)(p.b_tap_bytes >> 4);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_u + (uint32_t)(acc * p.acc_stride);
       if (p.mode == 1) {
-        uint64_t bdesc_res = make_smem_desc(b_base, p.desc_hi);                    // resident weights: walk the slabs
+        uint32_t b_res_lo = make_desc_lo(b_base);                                   // resident weights: walk the slabs
         uint32_t accum = 0;
         for (int cc = 0; cc < p.n_chunks; ++cc) {
           mbar_wait(&a_full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint64_t adesc = make_smem_desc(smem_base + (uint32_t)(stage * p.a_stage_bytes), p.desc_hi);
+          uint32_t a_lo = make_desc_lo(smem_base + (uint32_t)(stage * p.a_stage_bytes));
           if (p.b_resident) {
-            for (int j = 0; j < p.n_taps; ++j) {
-              if (issuer) {
-                for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc_res + 2 * k, p.idesc, accum | (uint32_t)k);
-              }
-              accum = 1;
-              adesc += a_tap_inc;
-              bdesc_res += b_tap_inc;
-            }
+            umma_taps_ks(ksteps, issuer, tmem_d, a_lo, b_res_lo, a_tap_inc, b_tap_inc, p.n_taps, p.desc_hi, p.idesc, accum);
+            accum = 1;
+            b_res_lo += (uint32_t)p.n_taps * b_tap_inc;
           } else {
             int j = 0;
             while (j < p.n_taps) {
               mbar_wait(&b_full[bstage], bphase);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              uint64_t bdesc = make_smem_desc(b_base + (uint32_t)(bstage * p.b_stage_bytes), p.desc_hi);
-              const int jend = min(j + p.tg, p.n_taps);
-              for (; j < jend; ++j) {
-                if (issuer) {
-                  for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, accum | (uint32_t)k);
-                }
-                accum = 1;
-                adesc += a_tap_inc;
-                bdesc += b_tap_inc;
-              }
+              const int nt = min(p.tg, p.n_taps - j);
+              umma_taps_ks(ksteps, issuer, tmem_d, a_lo, make_desc_lo(b_base + (uint32_t)(bstage * p.b_stage_bytes)), a_tap_inc,
+                           b_tap_inc, nt, p.desc_hi, p.idesc, accum);
+              accum = 1;
+              a_lo += (uint32_t)nt * a_tap_inc;
+              j += nt;
               if (issuer) umma_commit(&b_empty[bstage]);
               if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
             }
@@ -303,22 +295,17 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
       } else {
         const int iters = p.n_chunks * p.n_tapblocks;
+        const uint32_t a_sub_inc = (uint32_t)(p.a_sub_bytes >> 4), b_sub_inc = (uint32_t)(p.b_sub_bytes >> 4);
         int tb = 0;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&a_full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = smem_base + (uint32_t)(stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
           const int nsub = min(p.tb, p.n_taps - tb * p.tb);
-          if (issuer) {
-            for (int sidx = 0; sidx < nsub; ++sidx) {
-              const uint64_t adesc = make_smem_desc(a_addr + sidx * p.a_sub_bytes, p.desc_hi);
-              const uint64_t bdesc = make_smem_desc(b_addr + sidx * p.b_sub_bytes, p.desc_hi);
-              // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-              for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, (uint32_t)(it | sidx | k));
-            }
-            umma_commit(&a_empty[stage]);  // frees the smem slot when these MMAs retire
-          }
+          // sub-tiles of a stage are consecutive (tap) slabs of A and B; K advances 32 bytes per step inside a row
+          umma_taps_ks(ksteps, issuer, tmem_d, make_desc_lo(a_addr), make_desc_lo(a_addr + A_STAGE_BYTES), a_sub_inc, b_sub_inc,
+                       nsub, p.desc_hi, p.idesc, (uint32_t)(it > 0));
+          if (issuer) umma_commit(&a_empty[stage]);  // frees the smem slot when these MMAs retire
           if (++tb == p.n_tapblocks) tb = 0;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -377,6 +364,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       for (int blk = 0; blk < p.nblk; ++blk) {
         uint8_t* box_y = stage_y + (slot * 4 + q) * box_bytes;
         uint8_t* box_r = stage_r + (slot * 4 + q) * box_bytes;
+        const uint32_t sy = smem_u32(box_y), sr = smem_u32(box_r);
         if (prefetch) {
           mbar_wait(&my_res_bar[slot], (res_phase_bits >> slot) & 1u);
           res_phase_bits ^= 1u << slot;
@@ -400,7 +388,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
             float r[8];
             if (p.has_res) {
-              unpack8(*reinterpret_cast<const uint4*>(box_r + off), r);
+              unpack8(lds128(sr + off), r);
               if (!p.res_after_act) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += r[i];
@@ -408,7 +396,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
             if (p.accumulate) {
               float o[8];
-              unpack8(*reinterpret_cast<const uint4*>(box_y + off), o);
+              unpack8(lds128(sy + off), o);
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += o[i];
             }
@@ -418,11 +406,11 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += r[i];
             }
-            *reinterpret_cast<uint4*>(box_y + off) = pack8(f);
+            sts128(sy + off, pack8(f));
             if (p.has_y2) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * p.act2_slope;
-              *reinterpret_cast<uint4*>(box_r + off) = pack8(f);
+              sts128(sr + off, pack8(f));
             }
           }
         };

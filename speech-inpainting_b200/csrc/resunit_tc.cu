@@ -35,6 +35,9 @@ struct RuArgs {
   int x_stage_bytes, t1_bytes, w_bytes, w_tx_bytes, w_tg, w_loads;   // per-conv weight region: w_loads boxes of w_tg taps
   int stage_box_bytes;                                   // one staging tile: 128 rows x C bf16
   int need_b;                                            // second staging box per slot (accumulate input / y_act output)
+  int nxs;                                               // x-tile ring depth (2..4): short tiles need the loads further ahead
+  int slots;                                             // staging slots (2, or 1 when shared memory is tight)
+  int t1_bufs;                                           // intermediate tiles (2: epilogue 1 of tile i+1 overlaps conv2 of tile i)
   float slope_in, slope_mid, out_scale, act2_slope;
   int accumulate, has_y2;
   uint32_t desc_hi, idesc;
@@ -50,25 +53,25 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                   const __grid_constant__ RuArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sm_x = smem;                                   // [2] raw -> activated x tiles
-  uint8_t* sm_t1 = sm_x + 2 * p.x_stage_bytes;            // conv1 output tile (A operand of conv2)
-  uint8_t* sm_w1 = sm_t1 + p.t1_bytes;
+  uint8_t* sm_x = smem;                                   // [nxs] raw -> activated x tiles
+  uint8_t* sm_t1 = sm_x + p.nxs * p.x_stage_bytes;        // conv1 output tile (A operand of conv2)
+  uint8_t* sm_w1 = sm_t1 + p.t1_bufs * p.t1_bytes;
   uint8_t* sm_w2 = sm_w1 + p.w_bytes;
   uint8_t* sm_sa = sm_w2 + p.w_bytes;                     // [2] staging A: residual in -> y out
-  uint8_t* sm_sb = sm_sa + 2 * p.stage_box_bytes;         // [2] staging B: accumulate in -> y_act out
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_sb + (p.need_b ? 2 * p.stage_box_bytes : 0));
-  uint64_t* x_full = bars;            // [2]
-  uint64_t* x_empty = bars + 2;       // [2]
-  uint64_t* act_done = bars + 4;      // [2]
-  uint64_t* acc1_full = bars + 6;     // [2]
-  uint64_t* acc1_empty = bars + 8;    // [2]
-  uint64_t* acc2_full = bars + 10;    // [2]
-  uint64_t* acc2_empty = bars + 12;   // [2]
-  uint64_t* t1_full = bars + 14;
-  uint64_t* t1_empty = bars + 15;
-  uint64_t* w_full = bars + 16;
-  uint64_t* res_bar = bars + 17;      // [4 quarters][2 slots]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 25);
+  uint8_t* sm_sb = sm_sa + p.slots * p.stage_box_bytes;   // [slots] staging B: accumulate in -> y_act out
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_sb + (p.need_b ? p.slots * p.stage_box_bytes : 0));
+  uint64_t* x_full = bars;            // [4]
+  uint64_t* x_empty = bars + 4;       // [4]
+  uint64_t* act_done = bars + 8;      // [4]
+  uint64_t* acc1_full = bars + 12;    // [2]
+  uint64_t* acc1_empty = bars + 14;   // [2]
+  uint64_t* acc2_full = bars + 16;    // [2]
+  uint64_t* acc2_empty = bars + 18;   // [2]
+  uint64_t* t1_full = bars + 20;      // [2]
+  uint64_t* t1_empty = bars + 22;     // [2]
+  uint64_t* w_full = bars + 24;
+  uint64_t* res_bar = bars + 25;      // [4 quarters][2 slots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 33);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -78,17 +81,21 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     prefetch_tensormap(&map_w2);
     prefetch_tensormap(&map_res);
     prefetch_tensormap(&map_y);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
       mbar_init(&act_done[s], 2);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&acc1_full[s], 1);
       mbar_init(&acc1_empty[s], 4);
       mbar_init(&acc2_full[s], 1);
       mbar_init(&acc2_empty[s], 4);
     }
-    mbar_init(t1_full, 4);
-    mbar_init(t1_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&t1_full[s], 4);
+      mbar_init(&t1_empty[s], 1);
+    }
     mbar_init(w_full, 1);
     for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
@@ -121,65 +128,55 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         tma_load_3d(sm_w2 + l * p.w_tg * p.tap_bytes, &map_w2, w_full, 0, 0, l * p.w_tg);
       }
     }
+    int s = 0;
+    uint32_t ph = 0;
     for (int i = 0; i < n_my; ++i) {
       int t0, b;
       tile_of(i, t0, b);
-      const int s = i & 1;
-      mbar_wait(&x_empty[s], ((i >> 1) & 1) ^ 1);
+      mbar_wait(&x_empty[s], ph ^ 1);
       if (issuer) {
         mbar_expect_tx(&x_full[s], (uint32_t)(p.xr * p.row_bytes));
         tma_load_3d(sm_x + s * p.x_stage_bytes, &map_x, &x_full[s], 0, t0 - p.p2 - p.p1, b);
       }
+      if (++s == p.nxs) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
     const uint32_t issuer = elect_one_sync();
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t x_base = smem_u32(sm_x), t1_base = smem_u32(sm_t1);
-    const uint64_t w1desc = make_smem_desc(smem_u32(sm_w1), p.desc_hi);
-    const uint64_t w2desc = make_smem_desc(smem_u32(sm_w2), p.desc_hi);
-    const uint64_t a1_inc = (uint64_t)((p.dil * p.row_bytes) >> 4);
-    const uint64_t a2_inc = (uint64_t)(p.row_bytes >> 4);
-    const uint64_t w_inc = (uint64_t)(p.tap_bytes >> 4);
+    const uint32_t w1_lo = make_desc_lo(smem_u32(sm_w1)), w2_lo = make_desc_lo(smem_u32(sm_w2));
+    const uint32_t a1_inc = (uint32_t)((p.dil * p.row_bytes) >> 4);
+    const uint32_t a2_inc = (uint32_t)(p.row_bytes >> 4);
+    const uint32_t w_inc = (uint32_t)(p.tap_bytes >> 4);
     mbar_wait(w_full, 0);
     tc_fence_after();
+    int xs = 0;
+    uint32_t xph = 0;
     auto conv1 = [&](int i) {
-      const int s = i & 1;
-      const uint32_t ph = (uint32_t)((i >> 1) & 1);
-      mbar_wait(&act_done[s], ph);
-      mbar_wait(&acc1_empty[s], ph ^ 1);
+      const int a = i & 1;
+      mbar_wait(&act_done[xs], xph);
+      mbar_wait(&acc1_empty[a], (uint32_t)(((i >> 1) & 1) ^ 1));
       tc_fence_after();
-      uint64_t adesc = make_smem_desc(x_base + (uint32_t)(s * p.x_stage_bytes), p.desc_hi);
-      uint64_t bdesc = w1desc;
-      const uint32_t d = tmem_u + (uint32_t)(s * p.C);
-      for (int j = 0; j < p.k; ++j) {
-        if (issuer)
-          for (int ks = 0; ks < p.ksteps; ++ks) umma_bf16(d, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (uint32_t)(j | ks));
-        adesc += a1_inc;
-        bdesc += w_inc;
-      }
+      umma_taps_ks(p.ksteps, issuer, tmem_u + (uint32_t)(a * p.C), make_desc_lo(x_base + (uint32_t)(xs * p.x_stage_bytes)), w1_lo,
+                   a1_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
       if (issuer) {
-        umma_commit(&acc1_full[s]);
-        umma_commit(&x_empty[s]);
+        umma_commit(&acc1_full[a]);
+        umma_commit(&x_empty[xs]);
       }
+      if (++xs == p.nxs) { xs = 0; xph ^= 1; }
     };
     auto conv2 = [&](int i) {
       const int a = i & 1;
-      mbar_wait(t1_full, (uint32_t)(i & 1));
+      const int tb = p.t1_bufs == 2 ? (i & 1) : 0;
+      mbar_wait(&t1_full[tb], (uint32_t)(p.t1_bufs == 2 ? (i >> 1) & 1 : i & 1));
       mbar_wait(&acc2_empty[a], (uint32_t)(((i >> 1) & 1) ^ 1));
       tc_fence_after();
-      uint64_t adesc = make_smem_desc(t1_base, p.desc_hi);
-      uint64_t bdesc = w2desc;
-      const uint32_t d = tmem_u + (uint32_t)((2 + a) * p.C);
-      for (int j = 0; j < p.k; ++j) {
-        if (issuer)
-          for (int ks = 0; ks < p.ksteps; ++ks) umma_bf16(d, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (uint32_t)(j | ks));
-        adesc += a2_inc;
-        bdesc += w_inc;
-      }
+      umma_taps_ks(p.ksteps, issuer, tmem_u + (uint32_t)((2 + a) * p.C), make_desc_lo(t1_base + (uint32_t)(tb * p.t1_bytes)), w2_lo,
+                   a2_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
       if (issuer) {
         umma_commit(&acc2_full[a]);
-        umma_commit(t1_empty);
+        umma_commit(&t1_empty[tb]);
       }
     };
     if (n_my > 0) conv1(0);
@@ -192,20 +189,23 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int tid = threadIdx.x - 64;
     const int n16 = (p.xr * p.row_bytes) >> 4;
     const float slope = p.slope_in;
+    int s = 0;
+    uint32_t ph = 0;
     for (int i = 0; i < n_my; ++i) {
-      const int s = i & 1;
-      mbar_wait(&x_full[s], (uint32_t)((i >> 1) & 1));
-      uint4* tile = reinterpret_cast<uint4*>(sm_x + s * p.x_stage_bytes);
+      mbar_wait(&x_full[s], ph);
+      const uint32_t tile = smem_u32(sm_x + s * p.x_stage_bytes);
+#pragma unroll 4
       for (int e = tid; e < n16; e += 64) {
         float f[8];
-        unpack8(tile[e], f);
+        unpack8(lds128(tile + (uint32_t)e * 16u), f);
 #pragma unroll
         for (int u = 0; u < 8; ++u) f[u] = f[u] > 0.f ? f[u] : f[u] * slope;
-        tile[e] = pack8(f);
+        sts128(tile + (uint32_t)e * 16u, pack8(f));
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&act_done[s]);
+      if (++s == p.nxs) { s = 0; ph ^= 1; }
     }
   } else if (warp < 8) {
     // ===================== epilogue 1: conv1 accumulator -> lrelu -> bf16 A tile of conv2 =====================
@@ -214,20 +214,20 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int chunks_per_row = p.row_bytes >> 4;
     const int swz_shift = p.row_bytes == 128 ? 0 : (p.row_bytes == 64 ? 1 : 2);
     const uint32_t swz = ((uint32_t)r >> swz_shift) & (uint32_t)(chunks_per_row - 1);
-    uint8_t* row_ptr = sm_t1 + r * p.row_bytes;
     for (int i = 0; i < n_my; ++i) {
       int t0, b;
       tile_of(i, t0, b);
       const int a = i & 1;
+      const int tb = p.t1_bufs == 2 ? (i & 1) : 0;
+      const uint32_t row_ptr = smem_u32(sm_t1 + tb * p.t1_bytes + r * p.row_bytes);
       mbar_wait(&acc1_full[a], (uint32_t)((i >> 1) & 1));
-      mbar_wait(t1_empty, (uint32_t)((i & 1) ^ 1));            // conv2 of the previous tile has read T1
+      // conv2 of the tile that last used this intermediate buffer has read it
+      mbar_wait(&t1_empty[tb], (uint32_t)((p.t1_bufs == 2 ? (i >> 1) & 1 : i & 1) ^ 1));
       tc_fence_after();
       const int tg = t0 - p.p2 + r;                            // global frame of this t1 row
       const bool inside = tg >= 0 && tg < p.T;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.C);
-      for (int c0 = 0; c0 < p.C; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
+      auto emit16 = [&](const uint32_t (&v)[16], int c0) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col = c0 + 8 * h;
@@ -240,14 +240,22 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             f[u] = f[u] > 0.f ? f[u] : f[u] * p.slope_mid;
             f[u] = inside ? f[u] : 0.f;
           }
-          *reinterpret_cast<uint4*>(row_ptr + ((((uint32_t)col >> 3) ^ swz) << 4)) = pack8(f);
+          sts128(row_ptr + ((((uint32_t)col >> 3) ^ swz) << 4), pack8(f));
         }
+      };
+      for (int c0 = 0; c0 < p.C; c0 += 32) {                   // two TMEM loads in flight per wait
+        uint32_t va[16], vb[16];
+        tmem_ld16_nowait(taddr + (uint32_t)c0, va);
+        if (c0 + 16 < p.C) tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), vb);
+        tmem_ld_wait();
+        emit16(va, c0);
+        if (c0 + 16 < p.C) emit16(vb, c0 + 16);
       }
       tc_fence_before();
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(t1_full);
+        mbar_arrive(&t1_full[tb]);
         mbar_arrive(&acc1_empty[a]);
       }
     }
@@ -261,10 +269,11 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t pre_bytes = (uint32_t)(1 + (p.accumulate ? 1 : 0)) * (uint32_t)box_bytes;
     const int rows_q = q < 3 ? 32 : p.tail_rows;               // rows of this quarter that belong to the tile (R = 96 + tail)
     uint64_t* my_res = res_bar + q * 2;
+    const int slot_mask = p.slots - 1;                         // slots is 1 or 2
     auto prefetch = [&](int i) {                               // lane 0 only
       int t0, b;
       tile_of(i, t0, b);
-      const int slot = i & 1;
+      const int slot = i & slot_mask;
       mbar_expect_tx(&my_res[slot], pre_bytes);
       tma_load_3d(sm_sa + slot * p.stage_box_bytes + q * box_bytes, &map_res, &my_res[slot], 0, t0 + q * 32, b);
       if (p.accumulate)
@@ -274,22 +283,20 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int i = 0; i < n_my; ++i) {
       int t0, b;
       tile_of(i, t0, b);
-      const int a = i & 1, slot = i & 1;
-      if (lane == 0) {
+      const int a = i & 1, slot = i & slot_mask;
+      if (lane == 0 && p.slots == 2) {
         // the other slot was stored from one tile ago: once those stores have left shared memory, refill it
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         if (i + 1 < n_my) prefetch(i + 1);
       }
       __syncwarp();
-      uint8_t* box_a = sm_sa + slot * p.stage_box_bytes + q * box_bytes + lane * p.row_bytes;
-      uint8_t* box_b = sm_sb + slot * p.stage_box_bytes + q * box_bytes + lane * p.row_bytes;
+      const uint32_t box_a = smem_u32(sm_sa + slot * p.stage_box_bytes + q * box_bytes + lane * p.row_bytes);
+      const uint32_t box_b = smem_u32(sm_sb + slot * p.stage_box_bytes + q * box_bytes + lane * p.row_bytes);
       mbar_wait(&acc2_full[a], (uint32_t)((i >> 1) & 1));
-      mbar_wait(&my_res[slot], (uint32_t)((i >> 1) & 1));
+      mbar_wait(&my_res[slot], (uint32_t)(p.slots == 2 ? (i >> 1) & 1 : i & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + a) * p.C);
-      for (int c0 = 0; c0 < p.C; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
+      auto emit16 = [&](const uint32_t (&v)[16], int c0) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col = c0 + 8 * h;
@@ -298,24 +305,32 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col + 4));
           float f[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           float xr[8];
-          unpack8(*reinterpret_cast<const uint4*>(box_a + off), xr);
+          unpack8(lds128(box_a + off), xr);
 #pragma unroll
           for (int u = 0; u < 8; ++u) f[u] += __uint_as_float(v[8 * h + u]) + xr[u];
           if (p.accumulate) {
             float o[8];
-            unpack8(*reinterpret_cast<const uint4*>(box_b + off), o);
+            unpack8(lds128(box_b + off), o);
 #pragma unroll
             for (int u = 0; u < 8; ++u) f[u] += o[u];
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) f[u] *= p.out_scale;
-          *reinterpret_cast<uint4*>(box_a + off) = pack8(f);
+          sts128(box_a + off, pack8(f));
           if (p.has_y2) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) f[u] = f[u] > 0.f ? f[u] : f[u] * p.act2_slope;
-            *reinterpret_cast<uint4*>(box_b + off) = pack8(f);
+            sts128(box_b + off, pack8(f));
           }
         }
+      };
+      for (int c0 = 0; c0 < p.C; c0 += 32) {                   // two TMEM loads in flight per wait
+        uint32_t va[16], vb[16];
+        tmem_ld16_nowait(taddr + (uint32_t)c0, va);
+        if (c0 + 16 < p.C) tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), vb);
+        tmem_ld_wait();
+        emit16(va, c0);
+        if (c0 + 16 < p.C) emit16(vb, c0 + 16);
       }
       tc_fence_before();
       fence_async_smem();
@@ -329,6 +344,11 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           if (p.has_y2) tma_store_3d(q < 3 ? &map_y2 : &map_y2t, src_b, 0, t0 + q * 32, b);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (p.slots == 1) {
+          // single staging slot: refill it as soon as this tile's stores have been read out
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (i + 1 < n_my) prefetch(i + 1);
+        }
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -372,10 +392,9 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
   a.tap_bytes = c * a.row_bytes;
   a.x_stage_bytes = (a.xr * a.row_bytes + 1023) / 1024 * 1024;
   a.t1_bytes = ((128 + k - 1) * a.row_bytes + 1023) / 1024 * 1024;
-  a.w_tg = 16384 / a.tap_bytes;
-  if (a.w_tg > k) a.w_tg = k;
-  if (a.w_tg < 1) a.w_tg = 1;
-  a.w_loads = (k + a.w_tg - 1) / a.w_tg;
+  // weights: as few TMA boxes as possible (<= 32 KB each), no padding taps when one box takes them all
+  a.w_loads = (k * a.tap_bytes + 32767) / 32768;
+  a.w_tg = (k + a.w_loads - 1) / a.w_loads;
   a.w_tx_bytes = a.w_loads * a.w_tg * a.tap_bytes;   // full boxes: taps past k are TMA zero fill but still counted
   a.w_bytes = (a.w_tx_bytes + 1023) / 1024 * 1024;
   a.stage_box_bytes = 128 * a.row_bytes;
@@ -384,13 +403,28 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
   a.desc_hi = make_desc_hi(a.row_bytes);
   a.idesc = make_idesc_bf16(128, c);
   a.tmem_cols = 4 * c < 32 ? 32 : 4 * c;
-  out->smem_bytes = 2 * a.x_stage_bytes + a.t1_bytes + 2 * a.w_bytes + 2 * a.stage_box_bytes * (1 + a.need_b) + 512 + 1024;
-  if (out->smem_bytes > 227 * 1024) {
+  // ring depths: prefer (4 x-tiles, 2 staging slots) inside the two-CTAs-per-SM budget, then the same inside one SM,
+  // then shrink (3, 2 x-tiles; finally a single staging slot) until the resident weights fit
+  const int fixed = 2 * a.w_bytes + 512 + 1024;
+  auto need = [&](int nxs, int slots, int t1b) {
+    return fixed + t1b * a.t1_bytes + nxs * a.x_stage_bytes + slots * a.stage_box_bytes * (1 + a.need_b);
+  };
+  const int two_cta = 115 * 1024 - 1024, one_cta = 227 * 1024;
+  a.nxs = 0;
+  const int tries[7][3] = {{4, 2, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {3, 1, 1}, {2, 1, 2}, {2, 1, 1}};
+  for (int pass = 0; pass < 2 && a.nxs == 0; ++pass)
+    for (const auto& tr : tries)
+      if (need(tr[0], tr[1], tr[2]) <= (pass == 0 ? two_cta : one_cta) && (pass == 1 || tr[1] == 2)) {
+        a.nxs = tr[0]; a.slots = tr[1]; a.t1_bufs = tr[2];
+        break;
+      }
+  if (a.nxs == 0) {
     sib::set_error("sib_resunit_bf16: c=%d k=%d dilation=%d needs %d bytes of shared memory (weights must stay resident)",
-                   c, k, dil, out->smem_bytes);
+                   c, k, dil, need(2, 1, 1));
     return SIB_ERR_UNSUPPORTED;
   }
-  out->ctas_per_sm = out->smem_bytes <= 112 * 1024 ? 2 : 1;
+  out->smem_bytes = need(a.nxs, a.slots, a.t1_bufs);
+  out->ctas_per_sm = out->smem_bytes <= 115 * 1024 - 1024 ? 2 : 1;
   return SIB_OK;
 }
 
@@ -461,6 +495,11 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
   const int slots = sm_count_of_current_device() * pl.ctas_per_sm;
   const int grid = a.total_tiles < slots ? a.total_tiles : slots;
   const RuArgs args = a;
+  static const bool verbose = getenv("SIB_TC_VERBOSE") != nullptr;
+  if (verbose)
+    fprintf(stderr, "[sib_resunit_bf16] B%d T%d C%d k%d d%d acc=%d y2=%d: R=%d xr=%d nxs=%d slots=%d t1=%d smem=%d ctas/sm=%d tiles=%d\n",
+            d->batch, d->t, d->c, d->k, d->dilation, a.accumulate, a.has_y2, a.R, a.xr, a.nxs, a.slots, a.t1_bufs, pl.smem_bytes,
+            pl.ctas_per_sm, a.total_tiles);
   resunit_tc_kernel<0><<<grid, NUM_THREADS, pl.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
       map_x, map_w1, map_w2, map_res, map_y, map_yt, map_y2, map_y2t, args);
   SIB_CHECK_LAUNCH("sib_resunit_bf16");

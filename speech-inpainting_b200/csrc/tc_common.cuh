@@ -124,6 +124,48 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// Same MMA with the descriptors passed as (low word, shared high word): the high word (SBO / version / swizzle) is a
+// per-kernel constant and the start address only moves inside the 14-bit field of the low word, so all descriptor
+// arithmetic in the issue loops is 32-bit (this one thread paces the tensor pipe: instructions per MMA matter).
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(desc_hi)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t make_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+// n_taps x KS MMAs: tap j reads A at a_lo + j a_inc and B at b_lo + j b_inc (units of 16 bytes); the KS k-steps of a tap
+// are 32 bytes apart inside the swizzle row.  `accum` = 0 makes the very first MMA overwrite the accumulator.
+template <int KS>
+__device__ __forceinline__ void umma_taps(uint32_t issuer, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_inc,
+                                          uint32_t b_inc, int n_taps, uint32_t desc_hi, uint32_t idesc, uint32_t accum) {
+  if (issuer) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) umma_bf16_lo(tmem_d, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, accum | (uint32_t)ks);
+  }
+#pragma unroll 1
+  for (int j = 1; j < n_taps; ++j) {
+    a_lo += a_inc;
+    b_lo += b_inc;
+    if (issuer) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) umma_bf16_lo(tmem_d, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, 1u);
+    }
+  }
+}
+__device__ __forceinline__ void umma_taps_ks(int ksteps, uint32_t issuer, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                             uint32_t a_inc, uint32_t b_inc, int n_taps, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accum) {
+  if (ksteps == 4) umma_taps<4>(issuer, tmem_d, a_lo, b_lo, a_inc, b_inc, n_taps, desc_hi, idesc, accum);
+  else if (ksteps == 2) umma_taps<2>(issuer, tmem_d, a_lo, b_lo, a_inc, b_inc, n_taps, desc_hi, idesc, accum);
+  else umma_taps<1>(issuer, tmem_d, a_lo, b_lo, a_inc, b_inc, n_taps, desc_hi, idesc, accum);
+}
+
 // CTA-pair MMA (issued by the leader CTA only): M = 256 spans both CTAs' TMEM, B is split between their shared memories
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -165,6 +207,18 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16-byte shared-memory accesses through 32-bit shared addresses: pointers carved out of the dynamic shared-memory
+// block lose their address space and alignment in the compiler's eyes (generic LD.E, 16-byte loads split into four
+// 4-byte loads = 4-way bank conflicts on 64 / 128-byte rows); the explicit form is one conflict-free wavefront.
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
   const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
