@@ -211,9 +211,39 @@ def profile_plans(sib, plans, detail=None):
                     detail.append({"kernel": name, "B": d.batch, "t_out": d.t_out, "c_in": d.c_in, "c_out": d.c_out,
                                    "groups": d.groups, "taps": d.n_taps, "stride": d.stride, "ms": round(ms_, 4),
                                    "tflops": round(fl / ms_ / 1e9, 1) if ms_ > 0 else None})
+            elif name == "sib_resunit_bf16":
+                d = args[0]._obj
+                ms_ = e0.elapsed_time(e1)
+                fl = 2.0 * 2.0 * d.batch * d.t * d.c * d.c * d.k          # two k-tap convs per unit
+                n_t = 2 + int(bool(d.accumulate)) + int(args[7] is not None)  # x in, y out (+ running sum in, + lrelu(y) out)
+                by = 2.0 * d.batch * d.t * d.c * n_t
+                a["flops"] += fl
+                a["bytes"] = a.get("bytes", 0.0) + by
+                if detail is not None:
+                    detail.append({"kernel": name, "B": d.batch, "t": d.t, "c": d.c, "k": d.k, "dilation": d.dilation,
+                                   "tensors": n_t, "ms": round(ms_, 4), "tflops": round(fl / ms_ / 1e9, 1),
+                                   "gbs": round(by / ms_ / 1e6, 1)})
             elif detail is not None:
                 detail.append({"kernel": name, "ms": round(e0.elapsed_time(e1), 4)})
     return agg
+
+
+def ncu_traffic(kernel_key):
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel family from the newest
+    committed ncu capture of this same command (profiles/r*_ncu_step_*_summary.json); None if there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_step_*_summary.json")))
+    if not files:
+        return None, None
+    try:
+        doc = json.load(open(files[-1]))
+        for k in doc["kernels"]:
+            if kernel_key in k["kernel"]:
+                per_launch = (k["dram_read_bytes_per_step"] + k["dram_write_bytes_per_step"]) / k["launches_per_step"]
+                return per_launch, os.path.basename(files[-1])
+    except Exception:
+        pass
+    return None, None
 
 
 def main():
@@ -345,12 +375,29 @@ def main():
         ach = top["flops"] / (top["ms"] / 1e3) / 1e12 if top["ms"] else 0.0
         # fp32 SIMT arm: no tensor pipe; the bound quoted is still the tensor roofline the bf16 arm is judged by
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        ncu_key = {"sib_conv1d_bf16": "conv1d_bf16_tc_kernel", "sib_resunit_bf16": "resunit_tc_kernel"}.get(name, name)
+        traffic, traffic_src = ncu_traffic(ncu_key)
         roofline = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"
+                    "frac": ach / peak, "traffic": traffic,
+                    "traffic_note": (f"DRAM bytes per launch, averaged over the family's launches of one step ({traffic_src})"
+                                     if traffic else "no ncu capture committed"),
+                    "algorithmic_flops_per_launch": top["flops"] / max(top["launches"], 1),
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
                     if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
                     "kernel_share_of_step": top["ms"] / total_ms if total_ms else None,
                     "launches_per_step": top["launches"], "algorithmic_flops_per_step": top["flops"],
                     "per_kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}}
+        ru = agg.get("sib_resunit_bf16")
+        if ru and ru.get("bytes") and ru["ms"] > 0:
+            # second family: the fused ResBlock units of the narrow stages are HBM-bound (x in, y out)
+            hbm_peak = peaks.get("hbm_gbs", 6650.0)
+            gbs = ru["bytes"] / (ru["ms"] / 1e3) / 1e9
+            t2, _ = ncu_traffic("resunit_tc_kernel")
+            roofline["secondary"] = [{"bound": "hbm", "kernel": "sib_resunit_bf16", "achieved": gbs, "peak": hbm_peak,
+                                      "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": t2,
+                                      "algorithmic_bytes_per_launch": ru["bytes"] / ru["launches"],
+                                      "tflops": ru["flops"] / (ru["ms"] / 1e3) / 1e12,
+                                      "kernel_share_of_step": ru["ms"] / total_ms}]
         if not args.no_cpu_baseline:
             v, sec = time_cpu_reference(state, 3, 1, args.cpu_sample_utts)
             cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
