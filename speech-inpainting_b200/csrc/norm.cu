@@ -55,6 +55,86 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TX* __restrict__ x
   }
 }
 
+// bf16 rows with C % 8 == 0: one warp per row, 16-byte loads / stores (lane owns chunks lane, lane+32, ... of 8 channels),
+// row in registers, two-pass variance in fp32.  3 vector loads per tensor per lane at C = 768 instead of 24 scalar ones.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                 const __nv_bfloat16* __restrict__ res,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta,
+                                                                 __nv_bfloat16* __restrict__ y, int64_t rows, int C,
+                                                                 float eps, int post_act) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nchunks = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  const uint4* rr = res ? reinterpret_cast<const uint4*>(res + row * C) : nullptr;
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int ch = lane + i * 32;
+    if (ch < nchunks) {
+      const uint4 a = __ldg(xr + ch);
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 t = __bfloat1622float2(a2[u]);
+        v[i][2 * u] = t.x; v[i][2 * u + 1] = t.y;
+      }
+      if (rr) {
+        const uint4 b = __ldg(rr + ch);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 t = __bfloat1622float2(b2[u]);
+          v[i][2 * u] += t.x; v[i][2 * u + 1] += t.y;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[i][u];
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[i][u] = 0.f;
+    }
+  }
+  const float mean = sib::warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + i * 32 < nchunks) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float dlt = v[i][u] - mean;
+        q += dlt * dlt;
+      }
+    }
+  }
+  const float rstd = rsqrtf(sib::warp_sum(q) / C + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int ch = lane + i * 32;
+    if (ch < nchunks) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * ch), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * ch + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint4 o;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float e0 = (v[i][2 * u] - mean) * rstd * g[2 * u] + bb[2 * u];
+        float e1 = (v[i][2 * u + 1] - mean) * rstd * g[2 * u + 1] + bb[2 * u + 1];
+        if (post_act == SIB_ACT_GELU) { e0 = sib::gelu_erf(e0); e1 = sib::gelu_erf(e1); }
+        o2[u] = __floats2bfloat162_rn(e0, e1);
+      }
+      yr[ch] = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ conv0
 // HuBERT conv0: Conv1d(1 -> C, k, stride) over the raw waveform (HF:154-175).  10 MACs per output, so
 // it is recomputed in both GroupNorm passes instead of materialising [B,C,N/5] twice.
@@ -354,6 +434,20 @@ extern "C" int sib_layernorm(const void* x, int x_dtype, const void* residual, i
   SIB_REQUIRE(post_act == SIB_ACT_NONE || post_act == SIB_ACT_GELU, "sib_layernorm: unsupported post_act");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int key = (x_dtype << 2) | ((residual ? r_dtype : x_dtype) << 1) | y_dtype;
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+  if (key == 7 && c % 8 == 0 && c <= 2048 && al16(x) && al16(y) && al16(gamma) && al16(beta) && (!residual || al16(residual))) {
+    const int warps = 8;
+    const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+    const __nv_bfloat16* rb = (const __nv_bfloat16*)residual;
+    __nv_bfloat16* yb = (__nv_bfloat16*)y;
+    const int nv = (c / 8 + 31) / 32;
+    if (nv <= 2) layernorm_bf16_vec_kernel<2><<<grid, warps * 32, 0, s>>>(xb, rb, gamma, beta, yb, rows, c, eps, post_act);
+    else if (nv <= 4) layernorm_bf16_vec_kernel<4><<<grid, warps * 32, 0, s>>>(xb, rb, gamma, beta, yb, rows, c, eps, post_act);
+    else layernorm_bf16_vec_kernel<8><<<grid, warps * 32, 0, s>>>(xb, rb, gamma, beta, yb, rows, c, eps, post_act);
+    SIB_CHECK_LAUNCH("sib_layernorm");
+    return SIB_OK;
+  }
   switch (key) {
     case 0: launch_ln<float, float, float>(x, residual, gamma, beta, y, rows, c, eps, post_act, s); break;
     case 1: launch_ln<float, float, __nv_bfloat16>(x, residual, gamma, beta, y, rows, c, eps, post_act, s); break;

@@ -199,3 +199,30 @@ def test_resunit_bf16(sib, case):
     _close(to_frame_major(ref), got, f"resunit {case}")
     if want_act:
         _close(to_frame_major(F.leaky_relu(ref, 0.01)), ya.float().cpu(), f"resunit y_act {case}")
+
+
+@pytest.mark.parametrize("c,res,act", [(768, True, False), (512, False, False), (1024, True, True), (80, True, False), (2048, False, False)])
+def test_layernorm_bf16(sib, c, res, act):
+    """bf16 LayerNorm (vectorised path for C % 8 == 0, scalar otherwise) vs torch fp32 on the same bf16 inputs."""
+    x, r = _bf(_rand(41, 7, c, seed=1, scale=2.0)), _bf(_rand(41, 7, c, seed=2))
+    g, b = 1 + 0.1 * _rand(c, seed=3), _rand(c, seed=4)
+    y = torch.empty(41, 7, c, device="cuda", dtype=torch.bfloat16)
+    sib.ops.layernorm(x.cuda().to(torch.bfloat16), g.cuda(), b.cuda(), y, 1e-5,
+                      residual=r.cuda().to(torch.bfloat16) if res else None,
+                      post_act=sib.ops.ACT_GELU if act else sib.ops.ACT_NONE)
+    ref = F.layer_norm(x + r if res else x, (c,), g, b, 1e-5)
+    if act:
+        ref = F.gelu(ref)
+    _close(ref, y.float().cpu(), f"layernorm bf16 c={c}")
+
+
+@pytest.mark.parametrize("B,T,C,k", [(2, 1000, 32, 7), (3, 257, 16, 7), (1, 255, 64, 3), (2, 5, 32, 7)])
+def test_conv_cout1_bf16(sib, B, T, C, k):
+    """conv_post (models.py:119-121: lrelu(0.01) -> Conv1d(C, 1, 7) -> tanh) on bf16 frame-major activations."""
+    x = _bf(_rand(B, C, T, seed=1))
+    w, b = _rand(1, C, k, seed=2, scale=0.2), _rand(1, seed=3, scale=0.1)
+    ref = torch.tanh(F.conv1d(F.leaky_relu(x, 0.01), w, b, padding=k // 2))
+    y = torch.empty(B, T, device="cuda")
+    sib.ops.conv1d_cout1(to_frame_major(x).cuda().to(torch.bfloat16).contiguous(), w[0].t().contiguous().cuda(), b.cuda(), y,
+                         k, k // 2, 0.01, sib.ops.ACT_TANH)
+    assert max_abs(ref[:, 0], y.cpu()) < 2e-5
