@@ -12,8 +12,8 @@
 //   * conv2 = k taps on that intermediate tile; epilogue 2: + b2 + x (+ the running MRF sum) x scale -> TMA store.
 //     R = 128 - (k - 1) output rows per tile (the intermediate needs conv2's halo); the last quarter stores through a
 //     shorter box so that rows >= R are never written.
-// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer (conv1 runs one tile ahead of conv2 so the tensor pipe works
-// while epilogue 1 converts), 2-3 activation, 4-7 epilogue 1, 8-11 epilogue 2 (one warp per TMEM lane quarter each).
+// Warp roles (512 threads): 0 TMA producer, 1 MMA issuer (conv1 runs one tile ahead of conv2 so the tensor pipe works
+// while epilogue 1 converts), 2-3 + 12-15 activation, 4-7 epilogue 1, 8-11 epilogue 2 (one warp per TMEM lane quarter).
 // Both accumulators are double-buffered in TMEM (4 C columns).  C = 32 / 16 fit two CTAs per SM.
 #include <stdlib.h>
 
@@ -23,7 +23,8 @@ namespace {
 
 using namespace sib_tc;
 
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 512;
+constexpr int ACT_WARPS = 6;                        // warps 2-3 and 12-15
 
 struct RuArgs {
   const float* b1;
@@ -70,8 +71,8 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint64_t* t1_full = bars + 20;      // [2]
   uint64_t* t1_empty = bars + 22;     // [2]
   uint64_t* w_full = bars + 24;
-  uint64_t* res_bar = bars + 25;      // [4 quarters][2 slots]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 33);
+  uint64_t* res_bar = bars + 25;      // [4 quarters][3 slots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 37);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -84,7 +85,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int s = 0; s < 4; ++s) {
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
-      mbar_init(&act_done[s], 2);
+      mbar_init(&act_done[s], ACT_WARPS);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc1_full[s], 1);
@@ -97,7 +98,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_init(&t1_empty[s], 1);
     }
     mbar_init(w_full, 1);
-    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < 12; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -184,9 +185,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (i + 1 < n_my) conv1(i + 1);
       conv2(i);
     }
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp == 2 || warp == 3 || warp >= 12) {
     // ===================== activation: leaky-relu in place on the freshly landed x tile =====================
-    const int tid = threadIdx.x - 64;
+    // (six warps: with two, this stage paced the whole kernel on the short k = 3 tiles - the MMA warp sat on act_done)
+    const int tid = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
     const int n16 = (p.xr * p.row_bytes) >> 4;
     const float slope = p.slope_in;
     int s = 0;
@@ -195,7 +197,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_wait(&x_full[s], ph);
       const uint32_t tile = smem_u32(sm_x + s * p.x_stage_bytes);
 #pragma unroll 4
-      for (int e = tid; e < n16; e += 64) {
+      for (int e = tid; e < n16; e += ACT_WARPS * 32) {
         float f[8];
         unpack8(lds128(tile + (uint32_t)e * 16u), f);
 #pragma unroll
@@ -268,32 +270,36 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int box_bytes = 32 * p.row_bytes;
     const uint32_t pre_bytes = (uint32_t)(1 + (p.accumulate ? 1 : 0)) * (uint32_t)box_bytes;
     const int rows_q = q < 3 ? 32 : p.tail_rows;               // rows of this quarter that belong to the tile (R = 96 + tail)
-    uint64_t* my_res = res_bar + q * 2;
-    const int slot_mask = p.slots - 1;                         // slots is 1 or 2
-    auto prefetch = [&](int i) {                               // lane 0 only
+    uint64_t* my_res = res_bar + q * 3;
+    auto prefetch = [&](int i, int slot) {                     // lane 0 only
       int t0, b;
       tile_of(i, t0, b);
-      const int slot = i & slot_mask;
       mbar_expect_tx(&my_res[slot], pre_bytes);
       tma_load_3d(sm_sa + slot * p.stage_box_bytes + q * box_bytes, &map_res, &my_res[slot], 0, t0 + q * 32, b);
       if (p.accumulate)
         tma_load_3d(sm_sb + slot * p.stage_box_bytes + q * box_bytes, &map_y, &my_res[slot], 0, t0 + q * 32, b);
     };
-    if (lane == 0 && n_my > 0) prefetch(0);
+    if (lane == 0 && n_my > 0) prefetch(0, 0);
+    int slot = 0;
+    uint32_t res_phase_bits = 0;
     for (int i = 0; i < n_my; ++i) {
       int t0, b;
       tile_of(i, t0, b);
-      const int a = i & 1, slot = i & slot_mask;
-      if (lane == 0 && p.slots == 2) {
-        // the other slot was stored from one tile ago: once those stores have left shared memory, refill it
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (i + 1 < n_my) prefetch(i + 1);
+      const int a = i & 1;
+      const int next_slot = slot + 1 == p.slots ? 0 : slot + 1;
+      if (lane == 0 && p.slots >= 2) {
+        // the slot of tile i+1 was last stored from slots-1 tiles ago: with three slots the store of the previous tile
+        // may still be draining while the next residual is already being fetched
+        if (p.slots == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (i + 1 < n_my) prefetch(i + 1, next_slot);
       }
       __syncwarp();
       const uint32_t box_a = smem_u32(sm_sa + slot * p.stage_box_bytes + q * box_bytes + lane * p.row_bytes);
       const uint32_t box_b = smem_u32(sm_sb + slot * p.stage_box_bytes + q * box_bytes + lane * p.row_bytes);
       mbar_wait(&acc2_full[a], (uint32_t)((i >> 1) & 1));
-      mbar_wait(&my_res[slot], (uint32_t)(p.slots == 2 ? (i >> 1) & 1 : i & 1));
+      mbar_wait(&my_res[slot], (res_phase_bits >> slot) & 1u);
+      res_phase_bits ^= 1u << slot;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + a) * p.C);
       auto emit16 = [&](const uint32_t (&v)[16], int c0) {
@@ -347,9 +353,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (p.slots == 1) {
           // single staging slot: refill it as soon as this tile's stores have been read out
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          if (i + 1 < n_my) prefetch(i + 1);
+          if (i + 1 < n_my) prefetch(i + 1, 0);
         }
       }
+      slot = next_slot;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
@@ -411,10 +418,11 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
   };
   const int two_cta = 115 * 1024 - 1024, one_cta = 227 * 1024;
   a.nxs = 0;
+  // (three staging slots are supported by the kernel but measured 5-8 % slower than two: not offered)
   const int tries[7][3] = {{4, 2, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {3, 1, 1}, {2, 1, 2}, {2, 1, 1}};
   for (int pass = 0; pass < 2 && a.nxs == 0; ++pass)
     for (const auto& tr : tries)
-      if (need(tr[0], tr[1], tr[2]) <= (pass == 0 ? two_cta : one_cta) && (pass == 1 || tr[1] == 2)) {
+      if (need(tr[0], tr[1], tr[2]) <= (pass == 0 ? two_cta : one_cta) && (pass == 1 || tr[1] >= 2)) {
         a.nxs = tr[0]; a.slots = tr[1]; a.t1_bufs = tr[2];
         break;
       }
