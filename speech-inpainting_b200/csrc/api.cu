@@ -1,5 +1,7 @@
 // Library-wide state of the C-ABI: thread-local error text and launch counter.  No other global state
 // (re-entrant across devices, SURVEY 8b "Threading").
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -15,6 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+bool pdl_enabled() {
+  static const bool on = getenv("SIB_NO_PDL") == nullptr;
+  return on;
+}
 }  // namespace sib
 
 extern "C" int sib_abi_version(void) { return SIB_ABI_VERSION; }

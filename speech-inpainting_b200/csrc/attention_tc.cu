@@ -57,8 +57,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role dispatch
   const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
   const int H = heads * HD;
-  const int kl = key_len ? max(1, min(key_len[b], T)) : T;
-  const int nblk = (kl + KB - 1) / KB;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) asm volatile("trap;");  // the swizzled tiles need 1024-byte alignment
@@ -85,6 +83,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  sib::pdl_wait();                 // PDL: the prologue above overlapped the previous kernel's tail
+  sib::pdl_launch_dependents();
+  const int kl = key_len ? max(1, min(key_len[b], T)) : T;
+  const int nblk = (kl + KB - 1) / KB;
 
   if (warp == 4) {
     // ===================== TMA producer (whole warp in the loop, one elected lane issues) =====================
@@ -249,7 +251,12 @@ int sib_attention_bf16_tc(const void* qkv, const int32_t* key_len, void* out, in
     attr_set[dev] = true;
   }
   dim3 grid(sib::ceil_div(t, QT), heads, batch);
-  attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map, (__nv_bfloat16*)out, key_len, t, heads);
+  const cudaError_t le = sib::launch_pdl(attention_tc_kernel, grid, dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, map,
+                                         (__nv_bfloat16*)out, key_len, t, heads);
+  if (le != cudaSuccess) {
+    sib::set_error("sib_attention: launch failed: %s", cudaGetErrorString(le));
+    return SIB_ERR_CUDA;
+  }
   SIB_CHECK_LAUNCH("sib_attention");
   return SIB_OK;
 }

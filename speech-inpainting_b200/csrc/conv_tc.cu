@@ -151,6 +151,9 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: everything above overlapped the previous kernel's tail; from here on global memory is touched
+  sib::pdl_wait();
+  sib::pdl_launch_dependents();
 
   // tile -> (n fastest, m, batch*group): CTAs that run concurrently share the same A rows in L2
   auto decode = [&](int tile, int& t0, int& n0, int& b, int& g) {
@@ -717,21 +720,26 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   }
   const int grid = a.total_tiles < nsm * ctas_per_sm ? a.total_tiles : nsm * ctas_per_sm;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  cudaError_t le = cudaSuccess;
   switch (d->post_act) {
     case SIB_ACT_NONE:
-      conv1d_bf16_tc_kernel<SIB_ACT_NONE><<<grid, NUM_THREADS, smem_bytes, cs>>>(map_a, map_b, map_y, map_y2, map_r, a);
+      le = sib::launch_pdl(conv1d_bf16_tc_kernel<SIB_ACT_NONE>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, map_a, map_b, map_y, map_y2, map_r, a);
       break;
     case SIB_ACT_GELU:
-      conv1d_bf16_tc_kernel<SIB_ACT_GELU><<<grid, NUM_THREADS, smem_bytes, cs>>>(map_a, map_b, map_y, map_y2, map_r, a);
+      le = sib::launch_pdl(conv1d_bf16_tc_kernel<SIB_ACT_GELU>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, map_a, map_b, map_y, map_y2, map_r, a);
       break;
     case SIB_ACT_LRELU:
-      conv1d_bf16_tc_kernel<SIB_ACT_LRELU><<<grid, NUM_THREADS, smem_bytes, cs>>>(map_a, map_b, map_y, map_y2, map_r, a);
+      le = sib::launch_pdl(conv1d_bf16_tc_kernel<SIB_ACT_LRELU>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, map_a, map_b, map_y, map_y2, map_r, a);
       break;
     case SIB_ACT_TANH:
-      conv1d_bf16_tc_kernel<SIB_ACT_TANH><<<grid, NUM_THREADS, smem_bytes, cs>>>(map_a, map_b, map_y, map_y2, map_r, a);
+      le = sib::launch_pdl(conv1d_bf16_tc_kernel<SIB_ACT_TANH>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, map_a, map_b, map_y, map_y2, map_r, a);
       break;
     default:
       SIB_REQUIRE(false, "sib_conv1d_bf16: unknown post_act %d", d->post_act);
+  }
+  if (le != cudaSuccess) {
+    sib::set_error("sib_conv1d_bf16: launch failed: %s", cudaGetErrorString(le));
+    return SIB_ERR_CUDA;
   }
   SIB_CHECK_LAUNCH("sib_conv1d_bf16");
   return SIB_OK;

@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bflo
                                                                  const float* __restrict__ beta,
                                                                  __nv_bfloat16* __restrict__ y, int64_t rows, int C,
                                                                  float eps, int post_act) {
+  sib::pdl_wait();                 // PDL-launched: may start while the producing GEMM is still draining
+  sib::pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -442,9 +444,14 @@ extern "C" int sib_layernorm(const void* x, int x_dtype, const void* residual, i
     const __nv_bfloat16* rb = (const __nv_bfloat16*)residual;
     __nv_bfloat16* yb = (__nv_bfloat16*)y;
     const int nv = (c / 8 + 31) / 32;
-    if (nv <= 2) layernorm_bf16_vec_kernel<2><<<grid, warps * 32, 0, s>>>(xb, rb, gamma, beta, yb, rows, c, eps, post_act);
-    else if (nv <= 4) layernorm_bf16_vec_kernel<4><<<grid, warps * 32, 0, s>>>(xb, rb, gamma, beta, yb, rows, c, eps, post_act);
-    else layernorm_bf16_vec_kernel<8><<<grid, warps * 32, 0, s>>>(xb, rb, gamma, beta, yb, rows, c, eps, post_act);
+    cudaError_t le;
+    if (nv <= 2) le = sib::launch_pdl(layernorm_bf16_vec_kernel<2>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, post_act);
+    else if (nv <= 4) le = sib::launch_pdl(layernorm_bf16_vec_kernel<4>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, post_act);
+    else le = sib::launch_pdl(layernorm_bf16_vec_kernel<8>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, post_act);
+    if (le != cudaSuccess) {
+      sib::set_error("sib_layernorm: launch failed: %s", cudaGetErrorString(le));
+      return SIB_ERR_CUDA;
+    }
     SIB_CHECK_LAUNCH("sib_layernorm");
     return SIB_OK;
   }

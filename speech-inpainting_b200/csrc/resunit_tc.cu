@@ -111,6 +111,8 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  sib::pdl_wait();                 // PDL: the prologue above overlapped the previous kernel's tail
+  sib::pdl_launch_dependents();
 
   const int n_my = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   auto tile_of = [&](int i, int& t0, int& b) {
@@ -508,8 +510,13 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
     fprintf(stderr, "[sib_resunit_bf16] B%d T%d C%d k%d d%d acc=%d y2=%d: R=%d xr=%d nxs=%d slots=%d t1=%d smem=%d ctas/sm=%d tiles=%d\n",
             d->batch, d->t, d->c, d->k, d->dilation, a.accumulate, a.has_y2, a.R, a.xr, a.nxs, a.slots, a.t1_bufs, pl.smem_bytes,
             pl.ctas_per_sm, a.total_tiles);
-  resunit_tc_kernel<0><<<grid, NUM_THREADS, pl.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
-      map_x, map_w1, map_w2, map_res, map_y, map_yt, map_y2, map_y2t, args);
+  const cudaError_t le = sib::launch_pdl(resunit_tc_kernel<0>, dim3(grid), dim3(NUM_THREADS), (size_t)pl.smem_bytes,
+                                         static_cast<cudaStream_t>(stream), map_x, map_w1, map_w2, map_res, map_y, map_yt,
+                                         map_y2, map_y2t, args);
+  if (le != cudaSuccess) {
+    sib::set_error("sib_resunit_bf16: launch failed: %s", cudaGetErrorString(le));
+    return SIB_ERR_CUDA;
+  }
   SIB_CHECK_LAUNCH("sib_resunit_bf16");
   return SIB_OK;
 }
