@@ -43,6 +43,7 @@ struct TcArgs {
   int post_act, accumulate, res_after_act;
   float post_slope, out_scale, act2_slope;
   int bn;            // tile width in output channels (multiple of 16, <= 256) == UMMA N
+  int bn_cta;        // weight rows this CTA loads per slab: bn, or bn / 2 in pair mode
   int cw, cw_shift;  // epilogue block / staging box width in channels (64 / 32 / 16) and its log2
   int nblk;          // epilogue blocks per tile = bn / cw
   int nb;            // staging ring depth in blocks (per warp pair and tensor)
@@ -98,8 +99,23 @@ __device__ __forceinline__ float act_t(float v, float slope) {
   return v;
 }
 
-template <int POST_ACT>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+template <bool PAIR>
+__device__ __forceinline__ void tma_ld(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  if (PAIR) tma_load_3d_pair(dst, map, bar, c0, c1, c2);
+  else tma_load_3d(dst, map, bar, c0, c1, c2);
+}
+template <bool PAIR>
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  if (PAIR) umma_commit_pair(bar, (uint16_t)3);
+  else umma_commit(bar);
+}
+
+// PAIR = true: the kernel runs as CTA pairs (clusters of 2, cta_group::2): a pair owns a 256-row x bn tile, each CTA
+// loads its own 128 A rows and its own half (bn/2 rows) of every weight slab, the even CTA issues M = 256 MMAs that
+// read both shared memories and write both TMEMs.  Per CTA the B bytes (TMA writes, L2 traffic, MMA operand reads)
+// halve, and with half the columns per CTA twice as many weight sets stay resident.
+template <int POST_ACT, bool PAIR>
+__global__ void __launch_bounds__(NUM_THREADS, PAIR ? 1 : 2)
 conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y2,
                       const __grid_constant__ CUtensorMap map_r, const __grid_constant__ TcArgs p) {
@@ -135,22 +151,34 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], NUM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[s], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     for (int s = 0; s < 4 * MAX_NB; ++s) mbar_init(&res_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t tmem_cols = 2 * p.acc_stride;  // power of two >= 32 (host guarantees)
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "r"(tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      // both CTAs of the pair allocate the same columns (same warp index, same smem slot for the result)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                   "r"(tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                   "r"(tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised and its TMEM is allocated before anyone signals it
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent loop over (pair) tiles
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // PDL: everything above overlapped the previous kernel's tail; from here on global memory is touched
   sib::pdl_wait();
   sib::pdl_launch_dependents();
@@ -161,7 +189,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int rest = tile / p.tiles_n;
     const int mt = rest % p.tiles_m;
     const int z = rest / p.tiles_m;
-    t0 = mt * BM;
+    t0 = PAIR ? mt * (2 * BM) + (int)cta_rank * BM : mt * BM;   // this CTA's 128 rows of the (pair) tile
     n0 = nt * p.bn;
     b = z / p.groups;
     g = z - b * p.groups;
@@ -175,15 +203,16 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t issuer = elect_one_sync();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
       int t0, n0, b, g;
       decode(tile, t0, n0, b, g);
       if (p.mode == 1) {
         for (int cc = 0; cc < p.n_chunks; ++cc) {
           mbar_wait(&a_empty[stage], phase ^ 1);
           if (issuer) {
-            mbar_expect_tx(&a_full[stage], (uint32_t)(p.rows_h * row_bytes_k));
-            tma_load_3d(smem + stage * p.a_stage_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc, t0 + p.off0, b);
+            // pair: both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
+            if (!PAIR || cta_rank == 0) mbar_expect_tx(&a_full[stage], (uint32_t)((PAIR ? 2 : 1) * p.rows_h * row_bytes_k));
+            tma_ld<PAIR>(smem + stage * p.a_stage_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc, t0 + p.off0, b);
           }
           if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
@@ -196,13 +225,14 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           uint8_t* b_dst = a_dst + A_STAGE_BYTES;
           const int nsub = min(p.tb, p.n_taps - tb * p.tb);
           if (issuer) {
-            mbar_expect_tx(&a_full[stage], (uint32_t)nsub * (uint32_t)(p.a_sub_bytes + p.b_sub_bytes));
+            if (!PAIR || cta_rank == 0)
+              mbar_expect_tx(&a_full[stage], (uint32_t)((PAIR ? 2 : 1) * nsub) * (uint32_t)(p.a_sub_bytes + p.b_sub_bytes));
             for (int sidx = 0; sidx < nsub; ++sidx) {
               const int j = tb * p.tb + sidx;
-              tma_load_3d(a_dst + sidx * p.a_sub_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc + p.tap_ch[j],
-                          t0 + p.tap_row[j], b);
-              tma_load_3d(b_dst + sidx * p.b_sub_bytes, &map_b, &a_full[stage], 0, n0,
-                          (g * p.n_chunks + cc) * p.n_taps + j);
+              tma_ld<PAIR>(a_dst + sidx * p.a_sub_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc + p.tap_ch[j],
+                           t0 + p.tap_row[j], b);
+              tma_ld<PAIR>(b_dst + sidx * p.b_sub_bytes, &map_b, &a_full[stage], 0, n0 + (int)cta_rank * p.bn_cta,
+                           (g * p.n_chunks + cc) * p.n_taps + j);
             }
           }
           if (++tb == p.n_tapblocks) { tb = 0; ++cc; }
@@ -218,23 +248,24 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // every tile of this launch uses the same weights: load them once (groups == 1, tiles_n == 1)
         const int slabs = p.n_chunks * p.n_taps;
         if (issuer) {
-          mbar_expect_tx(&b_full[0], (uint32_t)(((slabs + p.tg - 1) / p.tg) * p.b_stage_bytes));
+          if (!PAIR || cta_rank == 0)
+            mbar_expect_tx(&b_full[0], (uint32_t)((PAIR ? 2 : 1) * ((slabs + p.tg - 1) / p.tg) * p.b_stage_bytes));
           for (int s0 = 0; s0 < slabs; s0 += p.tg)
-            tma_load_3d(b_region + (s0 / p.tg) * p.b_stage_bytes, &map_b, &b_full[0], 0, 0, s0);
+            tma_ld<PAIR>(b_region + (s0 / p.tg) * p.b_stage_bytes, &map_b, &b_full[0], 0, (int)cta_rank * p.bn_cta, s0);
         }
       } else {
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
           int t0, n0, b, g;
           decode(tile, t0, n0, b, g);
           for (int cc = 0; cc < p.n_chunks; ++cc) {
             for (int j0 = 0; j0 < p.n_taps; j0 += p.tg) {
               mbar_wait(&b_empty[stage], phase ^ 1);
               if (issuer) {
-                mbar_expect_tx(&b_full[stage], (uint32_t)p.b_stage_bytes);
-                tma_load_3d(b_region + stage * p.b_stage_bytes, &map_b, &b_full[stage], 0, n0,
-                            (g * p.n_chunks + cc) * p.n_taps + j0);
+                if (!PAIR || cta_rank == 0) mbar_expect_tx(&b_full[stage], (uint32_t)((PAIR ? 2 : 1) * p.b_stage_bytes));
+                tma_ld<PAIR>(b_region + stage * p.b_stage_bytes, &map_b, &b_full[stage], 0, n0 + (int)cta_rank * p.bn_cta,
+                             (g * p.n_chunks + cc) * p.n_taps + j0);
               }
               if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
             }
@@ -242,8 +273,8 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && (!PAIR || cta_rank == 0)) {
+    // ===================== MMA issuer (pair: the even CTA issues for both) =====================
     // The WHOLE warp walks the loop, so stages, phases and descriptors are warp-uniform values held in uniform
     // registers that feed UTCHMMA directly; one elected lane issues.  (Walking the loop under `if (lane == 0)` turns
     // every operand into a per-thread value: the compiler then wraps each MMA in a ~40-instruction uniformisation
@@ -263,7 +294,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // descriptor low words only (32-bit arithmetic): next tap = row-shifted A view / next weight slab
     const uint32_t a_tap_inc = (uint32_t)((p.tap_step * row_bytes_k) >> 4);
     const uint32_t b_tap_inc = (uint32_t)(p.b_tap_bytes >> 4);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_u + (uint32_t)(acc * p.acc_stride);
@@ -275,7 +306,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           uint32_t a_lo = make_desc_lo(smem_base + (uint32_t)(stage * p.a_stage_bytes));
           if (p.b_resident) {
-            umma_taps_ks(ksteps, issuer, tmem_d, a_lo, b_res_lo, a_tap_inc, b_tap_inc, p.n_taps, p.desc_hi, p.idesc, accum);
+            umma_taps_ks<PAIR>(ksteps, issuer, tmem_d, a_lo, b_res_lo, a_tap_inc, b_tap_inc, p.n_taps, p.desc_hi, p.idesc, accum);
             accum = 1;
             b_res_lo += (uint32_t)p.n_taps * b_tap_inc;
           } else {
@@ -284,16 +315,16 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               mbar_wait(&b_full[bstage], bphase);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const int nt = min(p.tg, p.n_taps - j);
-              umma_taps_ks(ksteps, issuer, tmem_d, a_lo, make_desc_lo(b_base + (uint32_t)(bstage * p.b_stage_bytes)), a_tap_inc,
+              umma_taps_ks<PAIR>(ksteps, issuer, tmem_d, a_lo, make_desc_lo(b_base + (uint32_t)(bstage * p.b_stage_bytes)), a_tap_inc,
                            b_tap_inc, nt, p.desc_hi, p.idesc, accum);
               accum = 1;
               a_lo += (uint32_t)nt * a_tap_inc;
               j += nt;
-              if (issuer) umma_commit(&b_empty[bstage]);
+              if (issuer) commit<PAIR>(&b_empty[bstage]);
               if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
             }
           }
-          if (issuer) umma_commit(&a_empty[stage]);
+          if (issuer) commit<PAIR>(&a_empty[stage]);
           if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
       } else {
@@ -306,14 +337,14 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const uint32_t a_addr = smem_base + (uint32_t)(stage * p.stage_bytes);
           const int nsub = min(p.tb, p.n_taps - tb * p.tb);
           // sub-tiles of a stage are consecutive (tap) slabs of A and B; K advances 32 bytes per step inside a row
-          umma_taps_ks(ksteps, issuer, tmem_d, make_desc_lo(a_addr), make_desc_lo(a_addr + A_STAGE_BYTES), a_sub_inc, b_sub_inc,
+          umma_taps_ks<PAIR>(ksteps, issuer, tmem_d, make_desc_lo(a_addr), make_desc_lo(a_addr + A_STAGE_BYTES), a_sub_inc, b_sub_inc,
                        nsub, p.desc_hi, p.idesc, (uint32_t)(it > 0));
-          if (issuer) umma_commit(&a_empty[stage]);  // frees the smem slot when these MMAs retire
+          if (issuer) commit<PAIR>(&a_empty[stage]);  // frees the smem slot (in both CTAs) when these MMAs retire
           if (++tb == p.n_tapblocks) tb = 0;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (issuer) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+      if (issuer) commit<PAIR>(&tmem_full_bar[acc]);  // accumulator complete (signals both CTAs' epilogues)
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -342,9 +373,9 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       if (p.accumulate) tma_load_3d(stage_y + (slot * 4 + q) * box_bytes, &map_y, &my_res_bar[slot], ch, t0 + q * 32, b);
     };
     // prefetch cursor: runs `ahead` blocks in front of the block being drained
-    int pf_tile = blockIdx.x, pf_blk = 0, pf_slot = 0;
+    int pf_tile = tile0, pf_blk = 0, pf_slot = 0;
     auto pf_advance = [&]() {
-      if (++pf_blk == p.nblk) { pf_blk = 0; pf_tile += gridDim.x; }
+      if (++pf_blk == p.nblk) { pf_blk = 0; pf_tile += tile_step; }
       if (++pf_slot == NB) pf_slot = 0;
     };
     if (prefetch) {
@@ -355,7 +386,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     int acc = 0, slot = 0;
     uint32_t acc_phase = 0, res_phase_bits = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
       int t0, n0, b, g;
       decode(tile, t0, n0, b, g);
       const int r0 = t0 + q * 32;
@@ -433,7 +464,10 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           // accumulator drained: hand it back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA warp waits for both CTAs
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
         }
         // box -> global through the async proxy, once both warps of the pair have written their columns
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -461,10 +495,12 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (half == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the pair's MMAs / multicast arrives touch it
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -541,9 +577,27 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     const double t_l2 = (double)tiles * (a_bytes + b_bytes) / 5500.0;
     return t_mma > t_l2 ? t_mma : t_l2;
   };
+  // CTA-pair variant (cta_group::2): a pair owns 256 rows x bn, every CTA loads only bn/2 rows of each weight slab.
+  // The pair MMA takes bn/2 clocks per k-step for twice the rows; per CTA the shared-memory port sees 4 KB of A +
+  // bn*16 B of B per MMA, L2 delivers half the weight bytes per FLOP, and half-width slabs stay resident twice as often.
+  const int pairs_m = sib::ceil_div(d->t_out, 2 * BM);
+  auto pair_cost = [&](int cand) -> double {
+    const int64_t tiles = (int64_t)pairs_m * (cout_g / cand) * d->batch;
+    const int clusters = nsm / 2;
+    const int64_t rounds = (tiles + clusters - 1) / clusters;
+    const double mma_cyc = cand / 2.0 > 32.0 + cand / 8.0 ? cand / 2.0 : 32.0 + cand / 8.0;
+    const double t_mma = (double)rounds * ((double)k16 * mma_cyc + 500.0);
+    const double a_bytes = 2.0 * (halo ? (double)(cin_g / cc) * rows_h * row_bytes : (double)d->n_taps * cin_g * BM * 2);
+    const bool resident = halo && cand == cout_g && (int64_t)d->n_taps * cin_g * (cand / 2) * 2 <= 150 * 1024;
+    const double b_bytes = resident ? 0.0 : (double)d->n_taps * cin_g * cand * 2;
+    const double t_l2 = (double)tiles * (a_bytes + b_bytes) / 5500.0;
+    return t_mma > t_l2 ? t_mma : t_l2;
+  };
   int bn = 0;
+  bool pair = false;
   {
     static const int force_bn = getenv("SIB_TC_BN") ? atoi(getenv("SIB_TC_BN")) : 0;  // tuning / profiling override
+    static const int pair_mode = getenv("SIB_TC_PAIR") ? atoi(getenv("SIB_TC_PAIR")) : -1;  // 0 never, 1 whenever legal
     const int bn_max = halo ? 128 : 256;
     double best = 0.0;
     for (int cand = bn_max; cand >= 16; cand -= 16) {
@@ -551,6 +605,18 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
       if (force_bn && cand == force_bn) { bn = cand; break; }
       const double c = tile_cost(cand);
       if (bn == 0 || c < best * 0.97) { bn = cand; best = c; }     // prefer the wider tile unless clearly slower
+    }
+    // pair tiles: one group, 64-channel K rows, bn in {256, 128}
+    if (pair_mode != 0 && d->groups == 1 && cc == 64 && tb == 1 && d->t_out > BM) {
+      int pbn = 0;
+      double pbest = 0.0;
+      for (int cand = 256; cand >= 128; cand >>= 1) {   // (bn = 64 pairs measured 40 % slower than single CTAs)
+        if (cout_g % cand) continue;
+        if (force_bn && cand != force_bn) continue;
+        const double c = pair_cost(cand);
+        if (pbn == 0 || c < pbest * 0.97) { pbn = cand; pbest = c; }
+      }
+      if (pbn && (pair_mode == 1 || pbest < best * 0.95)) { pair = true; bn = pbn; }
     }
   }
   const int cw = bn % 64 == 0 ? 64 : (bn % 32 == 0 ? 32 : 16);
@@ -565,8 +631,9 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   a.post_slope = d->post_slope; a.out_scale = d->out_scale; a.act2_slope = d->act2_slope;
   a.bn = bn; a.cw = cw; a.cw_shift = cw == 64 ? 6 : (cw == 32 ? 5 : 4);
   a.nblk = bn / cw;
-  a.tiles_m = tiles_m;
+  a.tiles_m = pair ? pairs_m : tiles_m;
   a.tiles_n = cout_g / bn;
+  a.bn_cta = pair ? bn / 2 : bn;
   const int64_t total = (int64_t)a.tiles_m * a.tiles_n * d->batch * d->groups;
   SIB_REQUIRE(total < (1ll << 31), "sib_conv1d_bf16: too many tiles");
   a.total_tiles = (int)total;
@@ -576,13 +643,13 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   a.n_tapblocks = (d->n_taps + tb - 1) / tb;
   a.n_taps = d->n_taps;
   a.desc_hi = make_desc_hi(row_bytes);
-  a.idesc = make_idesc(bn);
+  a.idesc = pair ? make_idesc_bf16(2 * BM, bn) : make_idesc(bn);
   auto swz_of = [](int rb) {
     return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   };
   a.a_sub_bytes = BM * row_bytes;
-  a.b_sub_bytes = bn * row_bytes;
-  a.b_tap_bytes = bn * row_bytes;
+  a.b_sub_bytes = a.bn_cta * row_bytes;   // per CTA: its half of the slab in pair mode
+  a.b_tap_bytes = a.bn_cta * row_bytes;
   // epilogue staging ring (blocks of cw columns): with a residual / accumulate input the ring must cover the TMA
   // latency (~2-3k cycles) with prefetched blocks; when one block's share of the mainloop already exceeds that,
   // one block ahead is enough and the memory goes to the operand rings instead
@@ -599,7 +666,7 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   const int slab_total = a.nb * (1 + a.need_r) * 4 * 32 * cw * 2;  // nb x (y [+ r]) boxes for 4 epilogue warp pairs
   // narrow layers (bn <= 32: 8 KB output tiles) are bound by the per-tile latency chain of one CTA, not by any
   // throughput: run two persistent CTAs per SM on half the shared memory each
-  const int ctas_per_sm = bn <= 32 ? 2 : 1;
+  const int ctas_per_sm = (bn <= 32 && !pair) ? 2 : 1;
   const int smem_budget = ctas_per_sm == 2 ? 112 * 1024 : 227 * 1024;
   const int avail = smem_budget - 2048 - slab_total - 1024;
 
@@ -616,7 +683,8 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     const int rloads = (slabs + tg - 1) / tg;
     const int rtg = (slabs + rloads - 1) / rloads;
     const int resident_bytes = rloads * rtg * a.b_tap_bytes;
-    if (d->groups == 1 && a.tiles_n == 1 && resident_bytes <= 120 * 1024 && resident_bytes + 2 * a.a_stage_bytes <= avail) {
+    if (d->groups == 1 && a.tiles_n == 1 && resident_bytes <= (pair ? 160 : 120) * 1024 &&
+        resident_bytes + 2 * a.a_stage_bytes <= avail) {
       a.mode = 1; a.b_resident = 1; a.tg = rtg; a.b_stage_bytes = rtg * a.b_tap_bytes; a.b_region_bytes = resident_bytes;
       a.b_stages = 1;
       a.a_stages = (avail - resident_bytes) / a.a_stage_bytes;
@@ -640,7 +708,7 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   if (a.mode == 1) {
     a.ring_bytes = a.a_stages * a.a_stage_bytes + a.b_region_bytes;
   } else {
-    a.stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+    a.stage_bytes = A_STAGE_BYTES + a.bn_cta * BK * 2;
     a.stages = avail / a.stage_bytes;
     if (a.stages > MAX_A_STAGES) a.stages = MAX_A_STAGES;
     SIB_REQUIRE(a.stages >= 2, "sib_conv1d_bf16: shared memory budget too small");
@@ -650,9 +718,9 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   const int smem_bytes = a.ring_bytes + slab_total + 1024 /*barriers*/ + 1024 /*alignment slack*/;
   static const bool verbose = getenv("SIB_TC_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "[sib_conv1d_bf16] B%d T%d C%d->%d k%d g%d s%d: bn=%d mode=%d resident=%d a_stages=%d b_stages=%d "
+    fprintf(stderr, "[sib_conv1d_bf16] B%d T%d C%d->%d k%d g%d s%d: pair=%d bn=%d mode=%d resident=%d a_stages=%d b_stages=%d "
             "stages=%d nb=%d ahead=%d need_r=%d smem=%d tiles=%d\n", d->batch, d->t_out, d->c_in, d->c_out, d->n_taps,
-            d->groups, d->stride, bn, a.mode, a.b_resident, a.a_stages, a.b_stages, a.stages, a.nb, a.ahead, a.need_r,
+            d->groups, d->stride, (int)pair, bn, a.mode, a.b_resident, a.a_stages, a.b_stages, a.stages, a.nb, a.ahead, a.need_r,
             smem_bytes, a.total_tiles);
 
   const int s = d->stride;
@@ -687,7 +755,7 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     // weights: [groups][c_in/g / cc][n_taps][c_out/g][cc]; one (chunk, tap) slab = the K-major B operand of one MMA group
     const cuuint64_t dims[3] = {(cuuint64_t)cc, (cuuint64_t)cout_g, (cuuint64_t)d->groups * a.n_chunks * d->n_taps};
     const cuuint64_t strides[3] = {2, (cuuint64_t)cc * 2, (cuuint64_t)cout_g * cc * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)cc, (cuuint32_t)bn, (cuuint32_t)a.tg};
+    const cuuint32_t box[3] = {(cuuint32_t)cc, (cuuint32_t)a.bn_cta, (cuuint32_t)a.tg};
     if (int rc = encode_map(&map_b, w, 3, dims, strides, box, swz_of(row_bytes), "B")) return rc;
   }
   {
@@ -701,14 +769,14 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
                               (cuuint64_t)(residual ? d->r_batch_stride : d->y_batch_stride) * 2};
     if (int rc = encode_map(&map_r, residual ? residual : y, 3, dims, rs, box, swz_of(cw * 2), "R")) return rc;
   }
-  static int sm_count[64] = {0};
+  static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && sm_count[dev] == 0) {
-    int n = 0;
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    const void* fns[4] = {(const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU>,
-                          (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH>};
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    const void* fns[8] = {(const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, false>,
+                          (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, false>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH, false>,
+                          (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, true>,
+                          (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH, true>};
     for (const void* fn : fns) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) {
@@ -716,27 +784,27 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
         return SIB_ERR_CUDA;
       }
     }
-    sm_count[dev] = n > 0 ? n : 148;
+    attr_set[dev] = true;
   }
-  const int grid = a.total_tiles < nsm * ctas_per_sm ? a.total_tiles : nsm * ctas_per_sm;
+  // persistent grid: one CTA (two for the narrow layers) per SM, or one CTA pair per SM pair
+  const int slots = pair ? nsm / 2 : nsm * ctas_per_sm;
+  const int grid = (a.total_tiles < slots ? a.total_tiles : slots) * (pair ? 2 : 1);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   cudaError_t le = cudaSuccess;
+#define SIB_TC_LAUNCH(ACT)                                                                                              \
+  le = pair ? sib::launch_pdl_cluster(conv1d_bf16_tc_kernel<ACT, true>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
+                                      2u, map_a, map_b, map_y, map_y2, map_r, a)                                        \
+            : sib::launch_pdl(conv1d_bf16_tc_kernel<ACT, false>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
+                              map_a, map_b, map_y, map_y2, map_r, a)
   switch (d->post_act) {
-    case SIB_ACT_NONE:
-      le = sib::launch_pdl(conv1d_bf16_tc_kernel<SIB_ACT_NONE>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, map_a, map_b, map_y, map_y2, map_r, a);
-      break;
-    case SIB_ACT_GELU:
-      le = sib::launch_pdl(conv1d_bf16_tc_kernel<SIB_ACT_GELU>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, map_a, map_b, map_y, map_y2, map_r, a);
-      break;
-    case SIB_ACT_LRELU:
-      le = sib::launch_pdl(conv1d_bf16_tc_kernel<SIB_ACT_LRELU>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, map_a, map_b, map_y, map_y2, map_r, a);
-      break;
-    case SIB_ACT_TANH:
-      le = sib::launch_pdl(conv1d_bf16_tc_kernel<SIB_ACT_TANH>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, map_a, map_b, map_y, map_y2, map_r, a);
-      break;
+    case SIB_ACT_NONE: SIB_TC_LAUNCH(SIB_ACT_NONE); break;
+    case SIB_ACT_GELU: SIB_TC_LAUNCH(SIB_ACT_GELU); break;
+    case SIB_ACT_LRELU: SIB_TC_LAUNCH(SIB_ACT_LRELU); break;
+    case SIB_ACT_TANH: SIB_TC_LAUNCH(SIB_ACT_TANH); break;
     default:
       SIB_REQUIRE(false, "sib_conv1d_bf16: unknown post_act %d", d->post_act);
   }
+#undef SIB_TC_LAUNCH
   if (le != cudaSuccess) {
     sib::set_error("sib_conv1d_bf16: launch failed: %s", cudaGetErrorString(le));
     return SIB_ERR_CUDA;

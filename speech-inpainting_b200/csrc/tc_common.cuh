@@ -138,15 +138,32 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(desc_hi)
       : "memory");
 }
+// CTA-pair form (cta_group::2, issued by the leader CTA): M = 256 across both CTAs' TMEM; each CTA's shared memory
+// holds its own 128 A rows and its own half (N/2 rows) of B at the SAME offsets the leader's descriptors name.
+__device__ __forceinline__ void umma_bf16_lo_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                  uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(desc_hi)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t make_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 // n_taps x KS MMAs: tap j reads A at a_lo + j a_inc and B at b_lo + j b_inc (units of 16 bytes); the KS k-steps of a tap
 // are 32 bytes apart inside the swizzle row.  `accum` = 0 makes the very first MMA overwrite the accumulator.
-template <int KS>
+template <int KS, bool PAIR = false>
 __device__ __forceinline__ void umma_taps(uint32_t issuer, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_inc,
                                           uint32_t b_inc, int n_taps, uint32_t desc_hi, uint32_t idesc, uint32_t accum) {
+  auto mma = [&](uint32_t al, uint32_t bl, uint32_t acc) {
+    if (PAIR) umma_bf16_lo_pair(tmem_d, al, bl, desc_hi, idesc, acc);
+    else umma_bf16_lo(tmem_d, al, bl, desc_hi, idesc, acc);
+  };
   if (issuer) {
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) umma_bf16_lo(tmem_d, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, accum | (uint32_t)ks);
+    for (int ks = 0; ks < KS; ++ks) mma(a_lo + 2 * ks, b_lo + 2 * ks, accum | (uint32_t)ks);
   }
 #pragma unroll 1
   for (int j = 1; j < n_taps; ++j) {
@@ -154,16 +171,17 @@ __device__ __forceinline__ void umma_taps(uint32_t issuer, uint32_t tmem_d, uint
     b_lo += b_inc;
     if (issuer) {
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) umma_bf16_lo(tmem_d, a_lo + 2 * ks, b_lo + 2 * ks, desc_hi, idesc, 1u);
+      for (int ks = 0; ks < KS; ++ks) mma(a_lo + 2 * ks, b_lo + 2 * ks, 1u);
     }
   }
 }
+template <bool PAIR = false>
 __device__ __forceinline__ void umma_taps_ks(int ksteps, uint32_t issuer, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
                                              uint32_t a_inc, uint32_t b_inc, int n_taps, uint32_t desc_hi, uint32_t idesc,
                                              uint32_t accum) {
-  if (ksteps == 4) umma_taps<4>(issuer, tmem_d, a_lo, b_lo, a_inc, b_inc, n_taps, desc_hi, idesc, accum);
-  else if (ksteps == 2) umma_taps<2>(issuer, tmem_d, a_lo, b_lo, a_inc, b_inc, n_taps, desc_hi, idesc, accum);
-  else umma_taps<1>(issuer, tmem_d, a_lo, b_lo, a_inc, b_inc, n_taps, desc_hi, idesc, accum);
+  if (ksteps == 4) umma_taps<4, PAIR>(issuer, tmem_d, a_lo, b_lo, a_inc, b_inc, n_taps, desc_hi, idesc, accum);
+  else if (ksteps == 2) umma_taps<2, PAIR>(issuer, tmem_d, a_lo, b_lo, a_inc, b_inc, n_taps, desc_hi, idesc, accum);
+  else umma_taps<1, PAIR>(issuer, tmem_d, a_lo, b_lo, a_inc, b_inc, n_taps, desc_hi, idesc, accum);
 }
 
 // CTA-pair MMA (issued by the leader CTA only): M = 256 spans both CTAs' TMEM, B is split between their shared memories
