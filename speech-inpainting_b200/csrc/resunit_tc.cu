@@ -38,7 +38,8 @@ struct RuArgs {
   int need_b;                                            // second staging box per slot (accumulate input / y_act output)
   int nxs;                                               // x-tile ring depth (2..4): short tiles need the loads further ahead
   int slots;                                             // staging slots (2, or 1 when shared memory is tight)
-  int t1_bufs;                                           // intermediate tiles (2: epilogue 1 of tile i+1 overlaps conv2 of tile i)
+  int t1_bufs;                                           // intermediate tile ring (1..3)
+  int la, na1;                                           // conv1 runs `la` tiles ahead of conv2; acc1 ring = la + 1 buffers
   float slope_in, slope_mid, out_scale, act2_slope;
   int accumulate, has_y2;
   uint32_t desc_hi, idesc;
@@ -64,15 +65,15 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint64_t* x_full = bars;            // [4]
   uint64_t* x_empty = bars + 4;       // [4]
   uint64_t* act_done = bars + 8;      // [4]
-  uint64_t* acc1_full = bars + 12;    // [2]
-  uint64_t* acc1_empty = bars + 14;   // [2]
-  uint64_t* acc2_full = bars + 16;    // [2]
-  uint64_t* acc2_empty = bars + 18;   // [2]
-  uint64_t* t1_full = bars + 20;      // [2]
-  uint64_t* t1_empty = bars + 22;     // [2]
-  uint64_t* w_full = bars + 24;
-  uint64_t* res_bar = bars + 25;      // [4 quarters][3 slots]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 37);
+  uint64_t* acc1_full = bars + 12;    // [4]
+  uint64_t* acc1_empty = bars + 16;   // [4]
+  uint64_t* acc2_full = bars + 20;    // [2]
+  uint64_t* acc2_empty = bars + 22;   // [2]
+  uint64_t* t1_full = bars + 24;      // [4]
+  uint64_t* t1_empty = bars + 28;     // [4]
+  uint64_t* w_full = bars + 32;
+  uint64_t* res_bar = bars + 33;      // [4 quarters][3 slots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 45);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -87,15 +88,15 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_init(&x_empty[s], 1);
       mbar_init(&act_done[s], ACT_WARPS);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&acc1_full[s], 1);
       mbar_init(&acc1_empty[s], 4);
-      mbar_init(&acc2_full[s], 1);
-      mbar_init(&acc2_empty[s], 4);
-    }
-    for (int s = 0; s < 2; ++s) {
       mbar_init(&t1_full[s], 4);
       mbar_init(&t1_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc2_full[s], 1);
+      mbar_init(&acc2_empty[s], 4);
     }
     mbar_init(w_full, 1);
     for (int s = 0; s < 12; ++s) mbar_init(&res_bar[s], 1);
@@ -115,10 +116,24 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   sib::pdl_launch_dependents();
 
   const int n_my = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  auto tile_of = [&](int i, int& t0, int& b) {
-    const int tile = blockIdx.x + i * gridDim.x;
-    b = tile / p.tiles_m;
-    t0 = (tile - b * p.tiles_m) * p.R;
+  // tile i of this CTA = blockIdx.x + i * gridDim.x = (utterance b, row tile mt); every role walks the same sequence with
+  // add-and-wrap counters (two integer divisions per kernel instead of one ~40-instruction division per tile and warp:
+  // on the short k = 3 tiles the SM is instruction-issue bound, ncu 2.7 of 4 IPC)
+  struct TileCursor {
+    int b, mt, step_b, step_m, tiles_m, R;
+    __device__ __forceinline__ void next() {
+      mt += step_m;
+      b += step_b;
+      if (mt >= tiles_m) { mt -= tiles_m; ++b; }
+    }
+    __device__ __forceinline__ int t0() const { return mt * R; }
+  };
+  auto cursor0 = [&]() {
+    TileCursor c;
+    c.tiles_m = p.tiles_m; c.R = p.R;
+    c.b = (int)blockIdx.x / p.tiles_m; c.mt = (int)blockIdx.x - c.b * p.tiles_m;
+    c.step_b = (int)gridDim.x / p.tiles_m; c.step_m = (int)gridDim.x - c.step_b * p.tiles_m;
+    return c;
   };
 
   if (warp == 0) {
@@ -133,13 +148,12 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     int s = 0;
     uint32_t ph = 0;
-    for (int i = 0; i < n_my; ++i) {
-      int t0, b;
-      tile_of(i, t0, b);
+    TileCursor tc = cursor0();
+    for (int i = 0; i < n_my; ++i, tc.next()) {
       mbar_wait(&x_empty[s], ph ^ 1);
       if (issuer) {
         mbar_expect_tx(&x_full[s], (uint32_t)(p.xr * p.row_bytes));
-        tma_load_3d(sm_x + s * p.x_stage_bytes, &map_x, &x_full[s], 0, t0 - p.p2 - p.p1, b);
+        tma_load_3d(sm_x + s * p.x_stage_bytes, &map_x, &x_full[s], 0, tc.t0() - p.p2 - p.p1, tc.b);
       }
       if (++s == p.nxs) { s = 0; ph ^= 1; }
     }
@@ -154,37 +168,39 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t w_inc = (uint32_t)(p.tap_bytes >> 4);
     mbar_wait(w_full, 0);
     tc_fence_after();
-    int xs = 0;
-    uint32_t xph = 0;
-    auto conv1 = [&](int i) {
-      const int a = i & 1;
+    int xs = 0, a1 = 0, tb = 0;
+    uint32_t xph = 0, a1ph = 0, tbph = 0;
+    auto conv1 = [&]() {                       // next tile in order: x ring slot xs, accumulator a1
       mbar_wait(&act_done[xs], xph);
-      mbar_wait(&acc1_empty[a], (uint32_t)(((i >> 1) & 1) ^ 1));
+      mbar_wait(&acc1_empty[a1], a1ph ^ 1);
       tc_fence_after();
-      umma_taps_ks(p.ksteps, issuer, tmem_u + (uint32_t)(a * p.C), make_desc_lo(x_base + (uint32_t)(xs * p.x_stage_bytes)), w1_lo,
+      umma_taps_ks(p.ksteps, issuer, tmem_u + (uint32_t)(a1 * p.C), make_desc_lo(x_base + (uint32_t)(xs * p.x_stage_bytes)), w1_lo,
                    a1_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
       if (issuer) {
-        umma_commit(&acc1_full[a]);
+        umma_commit(&acc1_full[a1]);
         umma_commit(&x_empty[xs]);
       }
       if (++xs == p.nxs) { xs = 0; xph ^= 1; }
+      if (++a1 == p.na1) { a1 = 0; a1ph ^= 1; }
     };
     auto conv2 = [&](int i) {
       const int a = i & 1;
-      const int tb = p.t1_bufs == 2 ? (i & 1) : 0;
-      mbar_wait(&t1_full[tb], (uint32_t)(p.t1_bufs == 2 ? (i >> 1) & 1 : i & 1));
+      mbar_wait(&t1_full[tb], tbph);
       mbar_wait(&acc2_empty[a], (uint32_t)(((i >> 1) & 1) ^ 1));
       tc_fence_after();
-      umma_taps_ks(p.ksteps, issuer, tmem_u + (uint32_t)((2 + a) * p.C), make_desc_lo(t1_base + (uint32_t)(tb * p.t1_bytes)), w2_lo,
+      umma_taps_ks(p.ksteps, issuer, tmem_u + (uint32_t)((p.na1 + a) * p.C), make_desc_lo(t1_base + (uint32_t)(tb * p.t1_bytes)), w2_lo,
                    a2_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
       if (issuer) {
         umma_commit(&acc2_full[a]);
         umma_commit(&t1_empty[tb]);
       }
+      if (++tb == p.t1_bufs) { tb = 0; tbph ^= 1; }
     };
-    if (n_my > 0) conv1(0);
+    // conv1 runs `la` tiles ahead: the commit -> epilogue 1 -> intermediate tile -> conv2 chain of one tile (~2-3k clocks
+    // of barrier hand-offs) is then spread over la tiles instead of pacing every tile
+    for (int i = 0; i < p.la && i < n_my; ++i) conv1();
     for (int i = 0; i < n_my; ++i) {
-      if (i + 1 < n_my) conv1(i + 1);
+      if (i + p.la < n_my) conv1();
       conv2(i);
     }
   } else if (warp == 2 || warp == 3 || warp >= 12) {
@@ -203,7 +219,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         float f[8];
         unpack8(lds128(tile + (uint32_t)e * 16u), f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) f[u] = f[u] > 0.f ? f[u] : f[u] * slope;
+        for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], f[u] * slope);      // leaky-relu, 0 < slope < 1
         sts128(tile + (uint32_t)e * 16u, pack8(f));
       }
       fence_async_smem();
@@ -218,15 +234,15 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int chunks_per_row = p.row_bytes >> 4;
     const int swz_shift = p.row_bytes == 128 ? 0 : (p.row_bytes == 64 ? 1 : 2);
     const uint32_t swz = ((uint32_t)r >> swz_shift) & (uint32_t)(chunks_per_row - 1);
-    for (int i = 0; i < n_my; ++i) {
-      int t0, b;
-      tile_of(i, t0, b);
-      const int a = i & 1;
-      const int tb = p.t1_bufs == 2 ? (i & 1) : 0;
+    int a = 0, tb = 0;
+    uint32_t aph = 0, tbph = 0;
+    TileCursor tc = cursor0();
+    for (int i = 0; i < n_my; ++i, tc.next()) {
+      const int t0 = tc.t0();
       const uint32_t row_ptr = smem_u32(sm_t1 + tb * p.t1_bytes + r * p.row_bytes);
-      mbar_wait(&acc1_full[a], (uint32_t)((i >> 1) & 1));
+      mbar_wait(&acc1_full[a], aph);
       // conv2 of the tile that last used this intermediate buffer has read it
-      mbar_wait(&t1_empty[tb], (uint32_t)((p.t1_bufs == 2 ? (i >> 1) & 1 : i & 1) ^ 1));
+      mbar_wait(&t1_empty[tb], tbph ^ 1);
       tc_fence_after();
       const int tg = t0 - p.p2 + r;                            // global frame of this t1 row
       const bool inside = tg >= 0 && tg < p.T;
@@ -241,10 +257,9 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             f[u] += __uint_as_float(v[8 * h + u]);
-            f[u] = f[u] > 0.f ? f[u] : f[u] * p.slope_mid;
-            f[u] = inside ? f[u] : 0.f;
+            f[u] = fmaxf(f[u], f[u] * p.slope_mid);          // leaky-relu, 0 < slope < 1
           }
-          sts128(row_ptr + ((((uint32_t)col >> 3) ^ swz) << 4), pack8(f));
+          sts128(row_ptr + ((((uint32_t)col >> 3) ^ swz) << 4), inside ? pack8(f) : make_uint4(0u, 0u, 0u, 0u));
         }
       };
       for (int c0 = 0; c0 < p.C; c0 += 32) {                   // two TMEM loads in flight per wait
@@ -262,6 +277,8 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         mbar_arrive(&t1_full[tb]);
         mbar_arrive(&acc1_empty[a]);
       }
+      if (++a == p.na1) { a = 0; aph ^= 1; }
+      if (++tb == p.t1_bufs) { tb = 0; tbph ^= 1; }
     }
   } else {
     // ===================== epilogue 2: conv2 accumulator + bias + x (+ running sum) -> y (and lrelu(y)) ==========
@@ -273,20 +290,20 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t pre_bytes = (uint32_t)(1 + (p.accumulate ? 1 : 0)) * (uint32_t)box_bytes;
     const int rows_q = q < 3 ? 32 : p.tail_rows;               // rows of this quarter that belong to the tile (R = 96 + tail)
     uint64_t* my_res = res_bar + q * 3;
-    auto prefetch = [&](int i, int slot) {                     // lane 0 only
-      int t0, b;
-      tile_of(i, t0, b);
+    auto prefetch = [&](const TileCursor& c, int slot) {       // lane 0 only
+      const int t0 = c.t0(), b = c.b;
       mbar_expect_tx(&my_res[slot], pre_bytes);
       tma_load_3d(sm_sa + slot * p.stage_box_bytes + q * box_bytes, &map_res, &my_res[slot], 0, t0 + q * 32, b);
       if (p.accumulate)
         tma_load_3d(sm_sb + slot * p.stage_box_bytes + q * box_bytes, &map_y, &my_res[slot], 0, t0 + q * 32, b);
     };
-    if (lane == 0 && n_my > 0) prefetch(0, 0);
+    TileCursor tc = cursor0(), tn = cursor0();                 // this tile / the next one (prefetch target)
+    if (lane == 0 && n_my > 0) prefetch(tn, 0);
+    tn.next();
     int slot = 0;
     uint32_t res_phase_bits = 0;
-    for (int i = 0; i < n_my; ++i) {
-      int t0, b;
-      tile_of(i, t0, b);
+    for (int i = 0; i < n_my; ++i, tc.next(), tn.next()) {
+      const int t0 = tc.t0(), b = tc.b;
       const int a = i & 1;
       const int next_slot = slot + 1 == p.slots ? 0 : slot + 1;
       if (lane == 0 && p.slots >= 2) {
@@ -294,7 +311,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         // may still be draining while the next residual is already being fetched
         if (p.slots == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        if (i + 1 < n_my) prefetch(i + 1, next_slot);
+        if (i + 1 < n_my) prefetch(tn, next_slot);
       }
       __syncwarp();
       const uint32_t box_a = smem_u32(sm_sa + slot * p.stage_box_bytes + q * box_bytes + lane * p.row_bytes);
@@ -303,7 +320,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_wait(&my_res[slot], (res_phase_bits >> slot) & 1u);
       res_phase_bits ^= 1u << slot;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + a) * p.C);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((p.na1 + a) * p.C);
       auto emit16 = [&](const uint32_t (&v)[16], int c0) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -355,7 +372,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (p.slots == 1) {
           // single staging slot: refill it as soon as this tile's stores have been read out
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          if (i + 1 < n_my) prefetch(i + 1, 0);
+          if (i + 1 < n_my) prefetch(tn, 0);
         }
       }
       slot = next_slot;
@@ -411,7 +428,6 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
   a.accumulate = accumulate; a.has_y2 = has_y2;
   a.desc_hi = make_desc_hi(a.row_bytes);
   a.idesc = make_idesc_bf16(128, c);
-  a.tmem_cols = 4 * c < 32 ? 32 : 4 * c;
   // ring depths: prefer (4 x-tiles, 2 staging slots) inside the two-CTAs-per-SM budget, then the same inside one SM,
   // then shrink (3, 2 x-tiles; finally a single staging slot) until the resident weights fit
   const int fixed = 2 * a.w_bytes + 512 + 1024;
@@ -421,7 +437,7 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
   const int two_cta = 115 * 1024 - 1024, one_cta = 227 * 1024;
   a.nxs = 0;
   // (three staging slots are supported by the kernel but measured 5-8 % slower than two: not offered)
-  const int tries[7][3] = {{4, 2, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {3, 1, 1}, {2, 1, 2}, {2, 1, 1}};
+  const int tries[9][3] = {{4, 2, 3}, {3, 2, 3}, {4, 2, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {3, 1, 1}, {2, 1, 2}, {2, 1, 1}};
   for (int pass = 0; pass < 2 && a.nxs == 0; ++pass)
     for (const auto& tr : tries)
       if (need(tr[0], tr[1], tr[2]) <= (pass == 0 ? two_cta : one_cta) && (pass == 1 || tr[1] >= 2)) {
@@ -434,6 +450,17 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
     return SIB_ERR_UNSUPPORTED;
   }
   out->smem_bytes = need(a.nxs, a.slots, a.t1_bufs);
+  // lookahead of conv1 over conv2: bounded by the intermediate ring and the x ring; acc1 ring = la + 1 TMEM buffers
+  static const int force_la = getenv("SIB_RU_LA") ? atoi(getenv("SIB_RU_LA")) : 0;
+  a.la = a.t1_bufs >= 3 ? 2 : 1;
+  if (force_la >= 1 && force_la <= 3) a.la = force_la;
+  if (a.la > a.nxs - 1) a.la = a.nxs - 1 > 0 ? a.nxs - 1 : 1;
+  a.na1 = a.la + 1;
+  {
+    uint32_t cols = (uint32_t)((a.na1 + 2) * c), pw = 32;
+    while (pw < cols) pw <<= 1;
+    a.tmem_cols = pw;
+  }
   out->ctas_per_sm = out->smem_bytes <= 115 * 1024 - 1024 ? 2 : 1;
   return SIB_OK;
 }
@@ -458,6 +485,8 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
               "sib_resunit_bf16: pointers must be 16-byte aligned");
   SIB_REQUIRE(d->x_row_stride % 8 == 0 && d->x_batch_stride % 8 == 0 && d->y_row_stride % 8 == 0 && d->y_batch_stride % 8 == 0,
               "sib_resunit_bf16: strides must be multiples of 8 elements");
+  SIB_REQUIRE(d->slope_in > 0.f && d->slope_in <= 1.f && d->slope_mid > 0.f && d->slope_mid <= 1.f,
+              "sib_resunit_bf16: leaky-relu slopes must be in (0, 1] (max(x, slope x) form)");
   a.b1 = b1; a.b2 = b2;
   a.T = d->t; a.batch = d->batch;
   a.slope_in = d->slope_in; a.slope_mid = d->slope_mid; a.out_scale = d->out_scale; a.act2_slope = d->act2_slope;
@@ -507,8 +536,8 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
   const RuArgs args = a;
   static const bool verbose = getenv("SIB_TC_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "[sib_resunit_bf16] B%d T%d C%d k%d d%d acc=%d y2=%d: R=%d xr=%d nxs=%d slots=%d t1=%d smem=%d ctas/sm=%d tiles=%d\n",
-            d->batch, d->t, d->c, d->k, d->dilation, a.accumulate, a.has_y2, a.R, a.xr, a.nxs, a.slots, a.t1_bufs, pl.smem_bytes,
+    fprintf(stderr, "[sib_resunit_bf16] B%d T%d C%d k%d d%d acc=%d y2=%d: R=%d xr=%d nxs=%d slots=%d t1=%d la=%d smem=%d ctas/sm=%d tiles=%d\n",
+            d->batch, d->t, d->c, d->k, d->dilation, a.accumulate, a.has_y2, a.R, a.xr, a.nxs, a.slots, a.t1_bufs, a.la, pl.smem_bytes,
             pl.ctas_per_sm, a.total_tiles);
   const cudaError_t le = sib::launch_pdl(resunit_tc_kernel<0>, dim3(grid), dim3(NUM_THREADS), (size_t)pl.smem_bytes,
                                          static_cast<cudaStream_t>(stream), map_x, map_w1, map_w2, map_res, map_y, map_yt,
