@@ -17,21 +17,25 @@ __global__ void gather_frames_kernel(const float* __restrict__ src, int T, int D
     o[i] = s[i];
 }
 
-// One warp per query row.  MODE 0: argmax cosine similarity (torch.cosine_similarity, eps 1e-8);
-// MODE 1: argmin squared L2 distance.  Ties resolve to the lowest index (torch.argmax / np.argmin).
+// One CTA (8 warps) per query row; warp w scores centroids w, w+8, ... with the lanes striding the feature axis, so every
+// (row, centroid) score is the same sequence of fp32 operations whatever the launch shape.  MODE 0: argmax cosine
+// similarity (torch.cosine_similarity, eps 1e-8); MODE 1: argmin squared L2 distance.  Ties resolve to the lowest index
+// (torch.argmax / np.argmin) - within a warp by visiting k in increasing order, across warps in the final reduction.
 template <int MODE>
 __global__ void __launch_bounds__(256) assign_kernel(const float* __restrict__ v, const float* __restrict__ cb, int M,
                                                      int K, int Dm, int64_t* __restrict__ labels) {
-  const int lane = threadIdx.x & 31;
-  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ float s_best[8];
+  __shared__ int s_k[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int m = blockIdx.x;
   if (m >= M) return;
   const float* vr = v + (int64_t)m * Dm;
   float vn = 0.f;
   for (int c = lane; c < Dm; c += 32) vn += vr[c] * vr[c];
   vn = sqrtf(sib::warp_sum(vn));
   float best = MODE == 0 ? -INFINITY : INFINITY;
-  int best_k = 0;
-  for (int k = 0; k < K; ++k) {
+  int best_k = 0x7fffffff;
+  for (int k = w; k < K; k += 8) {
     const float* cr = cb + (int64_t)k * Dm;
     float dot = 0.f, cn = 0.f;
     for (int c = lane; c < Dm; c += 32) {
@@ -55,7 +59,19 @@ __global__ void __launch_bounds__(256) assign_kernel(const float* __restrict__ v
       if (score < best) { best = score; best_k = k; }
     }
   }
-  if (lane == 0) labels[m] = best_k;
+  if (lane == 0) { s_best[w] = best; s_k[w] = best_k; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = s_best[0];
+    int bk = s_k[0];
+    for (int i = 1; i < 8; ++i) {
+      const float sc = s_best[i];
+      const int sk = s_k[i];
+      const bool better = MODE == 0 ? (sc > b) : (sc < b);
+      if (better || (sc == b && sk < bk)) { b = sc; bk = sk; }
+    }
+    labels[m] = bk == 0x7fffffff ? 0 : bk;
+  }
 }
 
 __global__ void paste_centroids_kernel(float* __restrict__ mel, int Dm, int T, const float* __restrict__ cc,
@@ -171,7 +187,7 @@ extern "C" int sib_gather_frames_f32(const float* src, int batch, int t, int d, 
 extern "C" int sib_cos_argmax_f32(const float* v, const float* cc, int m, int k, int d, int64_t* labels,
                                   sib_stream_t stream) {
   SIB_REQUIRE(v && cc && labels && m > 0 && k > 0 && d > 0, "sib_cos_argmax_f32: bad argument");
-  assign_kernel<0><<<sib::ceil_div(m, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(v, cc, m, k, d, labels);
+  assign_kernel<0><<<m, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, cc, m, k, d, labels);
   SIB_CHECK_LAUNCH("sib_cos_argmax_f32");
   return SIB_OK;
 }
@@ -179,7 +195,7 @@ extern "C" int sib_cos_argmax_f32(const float* v, const float* cc, int m, int k,
 extern "C" int sib_l2_argmin_f32(const float* f, const float* mu, int m, int k, int d, int64_t* labels,
                                  sib_stream_t stream) {
   SIB_REQUIRE(f && mu && labels && m > 0 && k > 0 && d > 0, "sib_l2_argmin_f32: bad argument");
-  assign_kernel<1><<<sib::ceil_div(m, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(f, mu, m, k, d, labels);
+  assign_kernel<1><<<m, 256, 0, static_cast<cudaStream_t>(stream)>>>(f, mu, m, k, d, labels);
   SIB_CHECK_LAUNCH("sib_l2_argmin_f32");
   return SIB_OK;
 }

@@ -400,6 +400,24 @@ class CustomModel(_StateHolder):
         self._head = None
         return self
 
+    def forward_frames(self, input_values, attention_mask, pos_t, len_t, off_t, n_rows: int):
+        """final_layers applied ONLY to the frames [pos_b, pos_b + len_b) of every utterance: what predict.py:164-168
+        gathers out of the full `outputs` anyway.  LayerNorm and Linear are row-wise, so the gathered rows are
+        bit-identical to gather(forward(...)); the head runs on sum(len) rows instead of B*T.  Returns ([n_rows, D], T)."""
+        io = self.base_model._run(input_values, attention_mask)
+        h = io.out
+        B, T, H = h.shape
+        if self._head is None:
+            self._head = ops.pack_linear_weight(self._sd["final_layers.1.weight"])
+        rows = torch.empty(max(n_rows, 1), H, device=h.device, dtype=torch.float32)[:n_rows]
+        out = torch.empty(max(n_rows, 1), self.codebook_dim, device=h.device, dtype=torch.float32)[:n_rows]
+        if n_rows > 0:
+            ops.gather_frames(h, pos_t, len_t, off_t, rows)
+            nrm = torch.empty_like(rows)
+            ops.layernorm(rows, self._sd["final_layers.0.weight"], self._sd["final_layers.0.bias"], nrm, 1e-5)
+            ops.linear(nrm, self._head, self._sd["final_layers.1.bias"], out)
+        return out, T
+
     def forward(self, input_values, attention_mask=None):
         io = self.base_model._run(input_values, attention_mask)
         h = io.out

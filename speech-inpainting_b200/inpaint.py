@@ -100,29 +100,29 @@ class InformedInpainter:
             xn = torch.empty_like(x)
             ops.znorm(x, xn, lengths, 1e-7)
             x = xn
-        outputs = self.model(x, attention_mask)  # [B,T,80]  predict.py:163
-        T = outputs.shape[1]
-        for p, l in zip(pos, ln):
-            if p < 0 or p + l > T:
-                raise SibError(f"mask frames [{p},{p + l}) outside the {T} encoder frames")
         off, acc = [], 0
         for l in ln:
             off.append(acc)
             acc += l
         M = acc
+        T = self.model.base_model.config.feat_extract_output_length(N)
+        for p, l in zip(pos, ln):
+            if p < 0 or l < 0 or p + l > T:
+                raise SibError(f"mask frames [{p},{p + l}) outside the {T} encoder frames")
+        pos_t, len_t, off_t = _i32(pos, dev), _i32(ln, dev), _i32(off, dev)
+        # predict.py:163-168: outputs = model(inputs)[b, pos:pos+L]; the head (LayerNorm + Linear) is row-wise, so it is
+        # evaluated on the gathered frames only (bit-identical rows, sum(L) of them instead of B*T)
+        values, _ = self.model.forward_frames(x, attention_mask, pos_t, len_t, off_t, M)
         mel_dev = mel.to(dev, torch.float32, non_blocking=True).clone() if mel.is_cuda else mel.to(dev, torch.float32, non_blocking=True).contiguous()
         labels = torch.empty(max(M, 1), dtype=torch.int64, device=dev)[:M]
         if M > 0:
-            pos_t, len_t, off_t = _i32(pos, dev), _i32(ln, dev), _i32(off, dev)
-            values = torch.empty(M, outputs.shape[-1], device=dev, dtype=torch.float32)
-            ops.gather_frames(outputs, pos_t, len_t, off_t, values)       # predict.py:164-168
             ops.cos_argmax(values, self.cc, labels)                        # loss_fn.py:44-46
             ops.paste_centroids(mel_dev, self.cc, self.center, labels, pos_t, len_t, off_t)  # predict.py:184-187
         Tp = mel_dev.shape[2]
         feats = torch.empty(B, ops.extend_mel_len(Tp), mel_dev.shape[1], device=dev, dtype=torch.float32)
         ops.extend_mel(mel_dev, feats, frame_major=True)                   # predict.py:189
         y = self.generator.forward_frame_major(feats)                      # predict.py:203
-        res = SimpleNamespace(wave=y, labels=labels, mel=mel_dev, offsets=off, outputs=outputs)
+        res = SimpleNamespace(wave=y, labels=labels, mel=mel_dev, offsets=off, values=values)
         if return_int16:                                                   # predict.py:204-206
             res.int16 = torch.empty(y.shape, dtype=torch.int16, device=dev)
             ops.pack_int16(y, res.int16)
