@@ -23,6 +23,7 @@
 #ifndef SPEECH_INPAINTING_B200_H_
 #define SPEECH_INPAINTING_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -150,7 +151,9 @@ int sib_pack_int16_f32(const float* y, int16_t* out, int64_t n, sib_stream_t str
 /* a20: log-mel spectrogram (meldataset.py:49-79 / mel_dump.py:40-98): reflect pad, hann-1024 STFT,
  * sqrt(re^2+im^2+1e-9), mel basis [n_mels][513] (sparse rows), log(clamp(.,1e-5)). out [B,n_mels,frames]. */
 int sib_mel_spectrogram_f32(const float* wave, int batch, int n, int hop, int pad, const float* mel_basis,
-                            int n_mels, float* out, int frames, sib_stream_t stream);
+                            int n_mels, float* out, int frames, void* workspace /* sib_mel_workspace_bytes(n_mels) */,
+                            sib_stream_t stream);
+size_t sib_mel_workspace_bytes(int n_mels);
 
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core path (tcgen05 + TMA), see DESIGN.md.  Same contract as sib_conv1d_f32 with

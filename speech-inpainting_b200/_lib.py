@@ -68,7 +68,8 @@ _SIGS = {
     "sib_transpose_f32": ([_P, _P, _I, _I, _I, _P], _I),
     "sib_embed_concat_f32": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "sib_pack_int16_f32": ([_P, _P, _L, _P], _I),
-    "sib_mel_spectrogram_f32": ([_P, _I, _I, _I, _I, _P, _I, _P, _I, _P], _I),
+    "sib_mel_spectrogram_f32": ([_P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P], _I),
+    "sib_mel_workspace_bytes": ([_I], C.c_size_t),
     "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16": ([C.POINTER(ResUnitDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16_supported": ([_I, _I, _I, _I, _I], _I),

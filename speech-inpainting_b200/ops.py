@@ -366,8 +366,9 @@ def pack_int16(y, out):
 def mel_spectrogram(wave, basis, out, hop, pad):
     B, n = wave.shape
     _chk(wave, torch.float32, "wave"); _chk(basis, torch.float32, "basis"); _chk(out, torch.float32, "out")
-    _emit("sib_mel_spectrogram_f32", (_p(wave), B, n, hop, pad, _p(basis), basis.shape[0], _p(out), out.shape[2]),
-          keep=(wave, basis, out))
+    ws = torch.empty(int(_lib.lib().sib_mel_workspace_bytes(basis.shape[0])), dtype=torch.uint8, device=wave.device)
+    _emit("sib_mel_spectrogram_f32", (_p(wave), B, n, hop, pad, _p(basis), basis.shape[0], _p(out), out.shape[2], _p(ws)),
+          keep=(wave, basis, out, ws))
 
 
 def cast_to_bf16(x, out):

@@ -87,7 +87,7 @@ def test_state_dict_surface_on_cpu(sib):
 def test_c_abi_library_exports_every_declared_symbol(sib):
     """include/speech_inpainting_b200.h <-> libsib_b200.so <-> the ctypes binding (no compute calls)."""
     header = open(os.path.join(ROOT, "include", "speech_inpainting_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|long long|const char\*)\s+(sib_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|long long|size_t|const char\*)\s+(sib_\w+)\s*\(", header, flags=re.M))
     assert len(declared) >= 30
     lib_path = os.path.join(ROOT, "speech-inpainting_b200", "libsib_b200.so")
     if not os.path.exists(lib_path):
