@@ -22,6 +22,7 @@
 //               (coalesced, rows >= t_out clipped by the TMA unit).  The ring costs 16 KB per block and tensor, which
 //               leaves the bulk of shared memory to the operand rings (latency hiding of the weight stream).
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -567,15 +568,14 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   const int64_t k16 = (int64_t)d->n_taps * cin_g / UMMA_K;            // MMAs per tile
   auto tile_cost = [&](int cand) -> double {
     const int64_t tiles = (int64_t)tiles_m * (cout_g / cand) * d->batch * d->groups;
-    const int ctas = nsm * (cand <= 32 ? 2 : 1);
-    const int64_t rounds = (tiles + ctas - 1) / ctas;
+    const int64_t rounds = (tiles + nsm - 1) / nsm;   // (two CTAs per SM on the narrow layers share the SM: no extra credit)
     const double mma_cyc = cand / 2.0 > 32.0 + cand / 4.0 ? cand / 2.0 : 32.0 + cand / 4.0;
-    const double t_mma = (double)rounds * ((double)k16 * mma_cyc + 400.0);
     const double a_bytes = halo ? (double)(cin_g / cc) * rows_h * row_bytes : (double)d->n_taps * cin_g * BM * 2;
     const bool resident = halo && d->groups == 1 && cand == cout_g && (int64_t)d->n_taps * cin_g * cand * 2 <= 120 * 1024;
     const double b_bytes = resident ? 0.0 : (double)d->n_taps * cin_g * cand * 2;
-    const double t_l2 = (double)tiles * (a_bytes + b_bytes) / 5500.0;
-    return t_mma > t_l2 ? t_mma : t_l2;
+    // a tile takes the longer of its MMAs and its operand stream (~40 B/clk per SM when every SM pulls from L2)
+    const double t_tile = fmax((double)k16 * mma_cyc, (a_bytes + b_bytes) / 40.0) + 400.0;
+    return (double)rounds * t_tile;
   };
   // CTA-pair variant (cta_group::2): a pair owns 256 rows x bn, every CTA loads only bn/2 rows of each weight slab.
   // The pair MMA takes bn/2 clocks per k-step for twice the rows; per CTA the shared-memory port sees 4 KB of A +
@@ -586,12 +586,11 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
     const int clusters = nsm / 2;
     const int64_t rounds = (tiles + clusters - 1) / clusters;
     const double mma_cyc = cand / 2.0 > 32.0 + cand / 8.0 ? cand / 2.0 : 32.0 + cand / 8.0;
-    const double t_mma = (double)rounds * ((double)k16 * mma_cyc + 500.0);
-    const double a_bytes = 2.0 * (halo ? (double)(cin_g / cc) * rows_h * row_bytes : (double)d->n_taps * cin_g * BM * 2);
+    const double a_bytes = halo ? (double)(cin_g / cc) * rows_h * row_bytes : (double)d->n_taps * cin_g * BM * 2;   // per CTA
     const bool resident = halo && cand == cout_g && (int64_t)d->n_taps * cin_g * (cand / 2) * 2 <= 150 * 1024;
-    const double b_bytes = resident ? 0.0 : (double)d->n_taps * cin_g * cand * 2;
-    const double t_l2 = (double)tiles * (a_bytes + b_bytes) / 5500.0;
-    return t_mma > t_l2 ? t_mma : t_l2;
+    const double b_bytes = resident ? 0.0 : (double)d->n_taps * cin_g * (cand / 2) * 2;                              // per CTA
+    const double t_tile = fmax((double)k16 * mma_cyc, (a_bytes + b_bytes) / 40.0) + 500.0;
+    return (double)rounds * t_tile;
   };
   int bn = 0;
   bool pair = false;
@@ -606,11 +605,11 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
       const double c = tile_cost(cand);
       if (bn == 0 || c < best * 0.97) { bn = cand; best = c; }     // prefer the wider tile unless clearly slower
     }
-    // pair tiles: one group, 64-channel K rows, bn in {256, 128}
+    // pair tiles: one group, 64-channel K rows, bn in {256, 192, 128} (192 = 3 x 64 evens out the waves when c_out = 768)
     if (pair_mode != 0 && d->groups == 1 && cc == 64 && tb == 1 && d->t_out > BM) {
       int pbn = 0;
       double pbest = 0.0;
-      for (int cand = 256; cand >= 128; cand >>= 1) {   // (bn = 64 pairs measured 40 % slower than single CTAs)
+      for (int cand = 256; cand >= 128; cand -= 64) {   // 256 / 192 / 128 (bn = 64 pairs measured 40 % slower than single CTAs)
         if (cout_g % cand) continue;
         if (force_bn && cand != force_bn) continue;
         const double c = pair_cost(cand);
