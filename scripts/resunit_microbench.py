@@ -18,6 +18,7 @@ SHAPES = {
     "s4k11d5": (32, 88064, 32, 11, 5, True, True),
     "s3k3d1": (32, 44032, 64, 3, 1, False, False),
     "s3k7d3": (32, 44032, 64, 7, 3, False, False),
+    "s3k11d5": (32, 44032, 64, 11, 5, True, False),
 }
 
 

@@ -26,6 +26,8 @@ SHAPES = {
     "s2k11c2": (32, 22016, 128, 128, 11, 5, 1, True, True),
     "s3k3c1": (32, 44032, 64, 64, 3, 1, 1, False, False),
     "s3k7c2": (32, 44032, 64, 64, 7, 3, 1, True, True),
+    "s3k11c1": (32, 44032, 64, 64, 11, 5, 1, False, False),
+    "s3k11c2": (32, 44032, 64, 64, 11, 1, 1, True, True),
     "s4k3c1": (32, 88064, 32, 32, 3, 1, 1, False, False),
     "s4k11c2": (32, 88064, 32, 32, 11, 5, 1, True, True),
 }

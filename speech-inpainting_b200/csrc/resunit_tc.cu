@@ -40,14 +40,26 @@ struct RuArgs {
   int slots;                                             // staging slots (2, or 1 when shared memory is tight)
   int t1_bufs;                                           // intermediate tile ring (1..3)
   int la, na1;                                           // conv1 runs `la` tiles ahead of conv2; acc1 ring = la + 1 buffers
+  int c_cta;                                             // weight rows (output channels) this CTA holds per tap: C, or C/2 in pair mode
   float slope_in, slope_mid, out_scale, act2_slope;
   int accumulate, has_y2;
   uint32_t desc_hi, idesc;
   uint32_t tmem_cols;
 };
 
-template <int UNUSED = 0>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+template <bool PAIR>
+__device__ __forceinline__ void commit_u(uint64_t* bar) {
+  if (PAIR) umma_commit_pair(bar, (uint16_t)3);
+  else umma_commit(bar);
+}
+
+// PAIR: two CTAs (cluster of 2, cta_group::2) run two independent tiles in lock-step and split the OUTPUT CHANNELS of both
+// weight sets between their shared memories (C/2 rows per tap each), which is what lets C = 64, k = 11 (176 KB of weights)
+// stay resident.  The even CTA issues M = 256 MMAs for both; every hand-off towards the MMA warp (activated x tile,
+// intermediate tile, drained accumulators) is a remote arrive on the even CTA's barrier, every hand-off from it a
+// multicast commit.
+template <bool PAIR>
+__global__ void __launch_bounds__(NUM_THREADS, PAIR ? 1 : 2)
 resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                   const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
                   const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yt,
@@ -86,53 +98,76 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int s = 0; s < 4; ++s) {
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
-      mbar_init(&act_done[s], ACT_WARPS);
+      mbar_init(&act_done[s], (PAIR ? 2 : 1) * ACT_WARPS);
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&acc1_full[s], 1);
-      mbar_init(&acc1_empty[s], 4);
-      mbar_init(&t1_full[s], 4);
+      mbar_init(&acc1_empty[s], PAIR ? 8 : 4);
+      mbar_init(&t1_full[s], PAIR ? 8 : 4);
       mbar_init(&t1_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc2_full[s], 1);
-      mbar_init(&acc2_empty[s], 4);
+      mbar_init(&acc2_empty[s], PAIR ? 8 : 4);
     }
     mbar_init(w_full, 1);
     for (int s = 0; s < 12; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                   "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                   "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  // arrive on a barrier the MMA warp waits on: in pair mode that barrier lives in the even CTA
+  auto arrive_mma = [&](uint64_t* bar) {
+    if (PAIR) mbar_arrive_cluster(bar, 0);
+    else mbar_arrive(bar);
+  };
   sib::pdl_wait();                 // PDL: the prologue above overlapped the previous kernel's tail
   sib::pdl_launch_dependents();
 
-  const int n_my = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // work list: tile i of this CTA = first + i * step.  Pair mode: cluster c takes tile pairs c, c + #clusters, ...; CTA r of
+  // the pair runs tile 2 * pair + r (a missing odd tile is a masked duplicate of the last one: loads clamp, stores skip)
+  const int first = PAIR ? 2 * (int)(blockIdx.x >> 1) + (int)cta_rank : (int)blockIdx.x;
+  const int step = PAIR ? 2 * (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int units = PAIR ? (p.total_tiles + 1) / 2 : p.total_tiles;           // tiles or tile pairs
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_my = units > unit0 ? (units - 1 - unit0) / ustep + 1 : 0;
   // tile i of this CTA = blockIdx.x + i * gridDim.x = (utterance b, row tile mt); every role walks the same sequence with
   // add-and-wrap counters (two integer divisions per kernel instead of one ~40-instruction division per tile and warp:
   // on the short k = 3 tiles the SM is instruction-issue bound, ncu 2.7 of 4 IPC)
   struct TileCursor {
-    int b, mt, step_b, step_m, tiles_m, R;
+    int b, mt, step_b, step_m, tiles_m, R, batch;
     __device__ __forceinline__ void next() {
       mt += step_m;
       b += step_b;
       if (mt >= tiles_m) { mt -= tiles_m; ++b; }
     }
-    __device__ __forceinline__ int t0() const { return mt * R; }
+    __device__ __forceinline__ bool valid() const { return b < batch; }
+    __device__ __forceinline__ int bb() const { return b < batch ? b : batch - 1; }          // clamped for loads
+    __device__ __forceinline__ int t0() const { return (b < batch ? mt : tiles_m - 1) * R; }
   };
   auto cursor0 = [&]() {
     TileCursor c;
-    c.tiles_m = p.tiles_m; c.R = p.R;
-    c.b = (int)blockIdx.x / p.tiles_m; c.mt = (int)blockIdx.x - c.b * p.tiles_m;
-    c.step_b = (int)gridDim.x / p.tiles_m; c.step_m = (int)gridDim.x - c.step_b * p.tiles_m;
+    c.tiles_m = p.tiles_m; c.R = p.R; c.batch = p.batch;
+    c.b = first / p.tiles_m; c.mt = first - c.b * p.tiles_m;
+    c.step_b = step / p.tiles_m; c.step_m = step - c.step_b * p.tiles_m;
     return c;
   };
 
@@ -140,10 +175,16 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // ===================== TMA producer: weights once, then one raw x tile per output tile =====================
     const uint32_t issuer = elect_one_sync();
     if (issuer) {
-      mbar_expect_tx(w_full, (uint32_t)(2 * p.w_tx_bytes));
+      // pair: each CTA loads its half of the output channels; both halves complete on the even CTA's barrier
+      if (!PAIR || cta_rank == 0) mbar_expect_tx(w_full, (uint32_t)((PAIR ? 4 : 2) * p.w_tx_bytes));
       for (int l = 0; l < p.w_loads; ++l) {
-        tma_load_3d(sm_w1 + l * p.w_tg * p.tap_bytes, &map_w1, w_full, 0, 0, l * p.w_tg);
-        tma_load_3d(sm_w2 + l * p.w_tg * p.tap_bytes, &map_w2, w_full, 0, 0, l * p.w_tg);
+        if (PAIR) {
+          tma_load_3d_pair(sm_w1 + l * p.w_tg * p.tap_bytes, &map_w1, w_full, 0, (int)cta_rank * p.c_cta, l * p.w_tg);
+          tma_load_3d_pair(sm_w2 + l * p.w_tg * p.tap_bytes, &map_w2, w_full, 0, (int)cta_rank * p.c_cta, l * p.w_tg);
+        } else {
+          tma_load_3d(sm_w1 + l * p.w_tg * p.tap_bytes, &map_w1, w_full, 0, 0, l * p.w_tg);
+          tma_load_3d(sm_w2 + l * p.w_tg * p.tap_bytes, &map_w2, w_full, 0, 0, l * p.w_tg);
+        }
       }
     }
     int s = 0;
@@ -153,12 +194,12 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_wait(&x_empty[s], ph ^ 1);
       if (issuer) {
         mbar_expect_tx(&x_full[s], (uint32_t)(p.xr * p.row_bytes));
-        tma_load_3d(sm_x + s * p.x_stage_bytes, &map_x, &x_full[s], 0, tc.t0() - p.p2 - p.p1, tc.b);
+        tma_load_3d(sm_x + s * p.x_stage_bytes, &map_x, &x_full[s], 0, tc.t0() - p.p2 - p.p1, tc.bb());
       }
       if (++s == p.nxs) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
+  } else if (warp == 1 && (!PAIR || cta_rank == 0)) {
+    // ===================== MMA issuer: warp-uniform loop, one elected lane issues (pair: the even CTA) ===========
     const uint32_t issuer = elect_one_sync();
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t x_base = smem_u32(sm_x), t1_base = smem_u32(sm_t1);
@@ -174,11 +215,11 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_wait(&act_done[xs], xph);
       mbar_wait(&acc1_empty[a1], a1ph ^ 1);
       tc_fence_after();
-      umma_taps_ks(p.ksteps, issuer, tmem_u + (uint32_t)(a1 * p.C), make_desc_lo(x_base + (uint32_t)(xs * p.x_stage_bytes)), w1_lo,
+      umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)(a1 * p.C), make_desc_lo(x_base + (uint32_t)(xs * p.x_stage_bytes)), w1_lo,
                    a1_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
       if (issuer) {
-        umma_commit(&acc1_full[a1]);
-        umma_commit(&x_empty[xs]);
+        commit_u<PAIR>(&acc1_full[a1]);
+        commit_u<PAIR>(&x_empty[xs]);
       }
       if (++xs == p.nxs) { xs = 0; xph ^= 1; }
       if (++a1 == p.na1) { a1 = 0; a1ph ^= 1; }
@@ -188,11 +229,11 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_wait(&t1_full[tb], tbph);
       mbar_wait(&acc2_empty[a], (uint32_t)(((i >> 1) & 1) ^ 1));
       tc_fence_after();
-      umma_taps_ks(p.ksteps, issuer, tmem_u + (uint32_t)((p.na1 + a) * p.C), make_desc_lo(t1_base + (uint32_t)(tb * p.t1_bytes)), w2_lo,
+      umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)((p.na1 + a) * p.C), make_desc_lo(t1_base + (uint32_t)(tb * p.t1_bytes)), w2_lo,
                    a2_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
       if (issuer) {
-        umma_commit(&acc2_full[a]);
-        umma_commit(&t1_empty[tb]);
+        commit_u<PAIR>(&acc2_full[a]);
+        commit_u<PAIR>(&t1_empty[tb]);
       }
       if (++tb == p.t1_bufs) { tb = 0; tbph ^= 1; }
     };
@@ -224,10 +265,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&act_done[s]);
+      if (lane == 0) arrive_mma(&act_done[s]);
       if (++s == p.nxs) { s = 0; ph ^= 1; }
     }
-  } else if (warp < 8) {
+  } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue 1: conv1 accumulator -> lrelu -> bf16 A tile of conv2 =====================
     const int q = warp & 3;
     const int r = q * 32 + lane;                               // tile row == TMEM lane == t1-local row
@@ -274,13 +315,13 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&t1_full[tb]);
-        mbar_arrive(&acc1_empty[a]);
+        arrive_mma(&t1_full[tb]);
+        arrive_mma(&acc1_empty[a]);
       }
       if (++a == p.na1) { a = 0; aph ^= 1; }
       if (++tb == p.t1_bufs) { tb = 0; tbph ^= 1; }
     }
-  } else {
+  } else if (warp >= 8 && warp < 12) {
     // ===================== epilogue 2: conv2 accumulator + bias + x (+ running sum) -> y (and lrelu(y)) ==========
     const int q = warp & 3;
     const int chunks_per_row = p.row_bytes >> 4;
@@ -291,7 +332,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int rows_q = q < 3 ? 32 : p.tail_rows;               // rows of this quarter that belong to the tile (R = 96 + tail)
     uint64_t* my_res = res_bar + q * 3;
     auto prefetch = [&](const TileCursor& c, int slot) {       // lane 0 only
-      const int t0 = c.t0(), b = c.b;
+      const int t0 = c.t0(), b = c.bb();
       mbar_expect_tx(&my_res[slot], pre_bytes);
       tma_load_3d(sm_sa + slot * p.stage_box_bytes + q * box_bytes, &map_res, &my_res[slot], 0, t0 + q * 32, b);
       if (p.accumulate)
@@ -303,7 +344,8 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     int slot = 0;
     uint32_t res_phase_bits = 0;
     for (int i = 0; i < n_my; ++i, tc.next(), tn.next()) {
-      const int t0 = tc.t0(), b = tc.b;
+      const int t0 = tc.t0(), b = tc.bb();
+      const bool valid = tc.valid();
       const int a = i & 1;
       const int next_slot = slot + 1 == p.slots ? 0 : slot + 1;
       if (lane == 0 && p.slots >= 2) {
@@ -361,8 +403,8 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&acc2_empty[a]);
-        if (rows_q > 0) {
+        arrive_mma(&acc2_empty[a]);
+        if (rows_q > 0 && valid) {
           const uint8_t* src_a = sm_sa + slot * p.stage_box_bytes + q * box_bytes;
           const uint8_t* src_b = sm_sb + slot * p.stage_box_bytes + q * box_bytes;
           tma_store_3d(q < 3 ? &map_y : &map_yt, src_a, 0, t0 + q * 32, b);
@@ -380,19 +422,32 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
   }
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
 struct RuPlan {
   RuArgs a;
-  int smem_bytes, ctas_per_sm;
+  int smem_bytes, ctas_per_sm, pair;
 };
 
+int plan_resunit_mode(int c, int k, int dil, int accumulate, int has_y2, int pair, RuPlan* out);
+
+// single CTAs when the weights fit one SM's shared memory, CTA pairs (output channels split) when only half of them do
 int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out) {
+  static const int force_pair = getenv("SIB_RU_PAIR") ? atoi(getenv("SIB_RU_PAIR")) : -1;   // 0 never, 1 whenever legal
+  if (force_pair == 1 && c >= 32 && plan_resunit_mode(c, k, dil, accumulate, has_y2, 1, out) == SIB_OK) return SIB_OK;
+  if (plan_resunit_mode(c, k, dil, accumulate, has_y2, 0, out) == SIB_OK) return SIB_OK;
+  if (force_pair != 0 && c == 64) return plan_resunit_mode(c, k, dil, accumulate, has_y2, 1, out);
+  return SIB_ERR_UNSUPPORTED;
+}
+
+int plan_resunit_mode(int c, int k, int dil, int accumulate, int has_y2, int pair, RuPlan* out) {
   if (!(c == 64 || c == 32 || c == 16)) {
     sib::set_error("sib_resunit_bf16: c=%d unsupported (16 / 32 / 64; wider stages use sib_conv1d_bf16)", c);
     return SIB_ERR_UNSUPPORTED;
@@ -415,7 +470,9 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
   }
   a.row_bytes = c * 2;
   a.ksteps = c / 16;
-  a.tap_bytes = c * a.row_bytes;
+  a.c_cta = pair ? c / 2 : c;
+  a.tap_bytes = a.c_cta * a.row_bytes;
+  out->pair = pair;
   a.x_stage_bytes = (a.xr * a.row_bytes + 1023) / 1024 * 1024;
   a.t1_bytes = ((128 + k - 1) * a.row_bytes + 1023) / 1024 * 1024;
   // weights: as few TMA boxes as possible (<= 32 KB each), no padding taps when one box takes them all
@@ -427,7 +484,7 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
   a.need_b = (accumulate || has_y2) ? 1 : 0;
   a.accumulate = accumulate; a.has_y2 = has_y2;
   a.desc_hi = make_desc_hi(a.row_bytes);
-  a.idesc = make_idesc_bf16(128, c);
+  a.idesc = make_idesc_bf16(pair ? 256 : 128, c);
   // ring depths: prefer (4 x-tiles, 2 staging slots) inside the two-CTAs-per-SM budget, then the same inside one SM,
   // then shrink (3, 2 x-tiles; finally a single staging slot) until the resident weights fit
   const int fixed = 2 * a.w_bytes + 512 + 1024;
@@ -438,7 +495,7 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
   a.nxs = 0;
   // (three staging slots are supported by the kernel but measured 5-8 % slower than two: not offered)
   const int tries[9][3] = {{4, 2, 3}, {3, 2, 3}, {4, 2, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {3, 1, 1}, {2, 1, 2}, {2, 1, 1}};
-  for (int pass = 0; pass < 2 && a.nxs == 0; ++pass)
+  for (int pass = pair ? 1 : 0; pass < 2 && a.nxs == 0; ++pass)
     for (const auto& tr : tries)
       if (need(tr[0], tr[1], tr[2]) <= (pass == 0 ? two_cta : one_cta) && (pass == 1 || tr[1] >= 2)) {
         a.nxs = tr[0]; a.slots = tr[1]; a.t1_bufs = tr[2];
@@ -461,7 +518,7 @@ int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out)
     while (pw < cols) pw <<= 1;
     a.tmem_cols = pw;
   }
-  out->ctas_per_sm = out->smem_bytes <= 115 * 1024 - 1024 ? 2 : 1;
+  out->ctas_per_sm = (!pair && out->smem_bytes <= 115 * 1024 - 1024) ? 2 : 1;
   return SIB_OK;
 }
 
@@ -516,7 +573,7 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
     // weights in the sib_conv1d_bf16 layout [1][1 chunk][k][c_out][c_in]: one K-major slab per tap
     const cuuint64_t dims[3] = {(cuuint64_t)d->c, (cuuint64_t)d->c, (cuuint64_t)d->k};
     const cuuint64_t ws[3] = {2, (cuuint64_t)d->c * 2, (cuuint64_t)d->c * d->c * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)d->c, (cuuint32_t)d->c, (cuuint32_t)a.w_tg};
+    const cuuint32_t box[3] = {(cuuint32_t)d->c, (cuuint32_t)a.c_cta, (cuuint32_t)a.w_tg};
     if (int rc = encode_map(&map_w1, w1, 3, dims, ws, box, swz, who, "w1")) return rc;
     if (int rc = encode_map(&map_w2, w2, 3, dims, ws, box, swz, who, "w2")) return rc;
   }
@@ -524,24 +581,37 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)resunit_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      sib::set_error("sib_resunit_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return SIB_ERR_CUDA;
+    const void* fns[2] = {(const void*)resunit_tc_kernel<false>, (const void*)resunit_tc_kernel<true>};
+    for (const void* fn : fns) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) {
+        sib::set_error("sib_resunit_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return SIB_ERR_CUDA;
+      }
     }
     attr_set[dev] = true;
   }
-  const int slots = sm_count_of_current_device() * pl.ctas_per_sm;
-  const int grid = a.total_tiles < slots ? a.total_tiles : slots;
+  int grid;
+  if (pl.pair) {
+    const int clusters = sm_count_of_current_device() / 2, units = (a.total_tiles + 1) / 2;
+    grid = 2 * (units < clusters ? units : clusters);
+  } else {
+    const int slots = sm_count_of_current_device() * pl.ctas_per_sm;
+    grid = a.total_tiles < slots ? a.total_tiles : slots;
+  }
   const RuArgs args = a;
   static const bool verbose = getenv("SIB_TC_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "[sib_resunit_bf16] B%d T%d C%d k%d d%d acc=%d y2=%d: R=%d xr=%d nxs=%d slots=%d t1=%d la=%d smem=%d ctas/sm=%d tiles=%d\n",
-            d->batch, d->t, d->c, d->k, d->dilation, a.accumulate, a.has_y2, a.R, a.xr, a.nxs, a.slots, a.t1_bufs, a.la, pl.smem_bytes,
+    fprintf(stderr, "[sib_resunit_bf16] B%d T%d C%d k%d d%d acc=%d y2=%d: pair=%d R=%d xr=%d nxs=%d slots=%d t1=%d la=%d smem=%d ctas/sm=%d tiles=%d\n",
+            d->batch, d->t, d->c, d->k, d->dilation, a.accumulate, a.has_y2, pl.pair, a.R, a.xr, a.nxs, a.slots, a.t1_bufs, a.la, pl.smem_bytes,
             pl.ctas_per_sm, a.total_tiles);
-  const cudaError_t le = sib::launch_pdl(resunit_tc_kernel<0>, dim3(grid), dim3(NUM_THREADS), (size_t)pl.smem_bytes,
-                                         static_cast<cudaStream_t>(stream), map_x, map_w1, map_w2, map_res, map_y, map_yt,
-                                         map_y2, map_y2t, args);
+  const cudaError_t le =
+      pl.pair ? sib::launch_pdl_cluster(resunit_tc_kernel<true>, dim3(grid), dim3(NUM_THREADS), (size_t)pl.smem_bytes,
+                                        static_cast<cudaStream_t>(stream), 2u, map_x, map_w1, map_w2, map_res, map_y, map_yt,
+                                        map_y2, map_y2t, args)
+              : sib::launch_pdl(resunit_tc_kernel<false>, dim3(grid), dim3(NUM_THREADS), (size_t)pl.smem_bytes,
+                                static_cast<cudaStream_t>(stream), map_x, map_w1, map_w2, map_res, map_y, map_yt, map_y2,
+                                map_y2t, args);
   if (le != cudaSuccess) {
     sib::set_error("sib_resunit_bf16: launch failed: %s", cudaGetErrorString(le));
     return SIB_ERR_CUDA;

@@ -162,6 +162,10 @@ RU_CASES = [
     (2, 300, 64, 3, 1, True, True, 1.0 / 3),
     (2, 333, 64, 7, 3, False, True, 1.0),
     (2, 50, 64, 7, 1, False, False, 1.0),        # shorter than one tile
+    (2, 300, 64, 11, 5, False, False, 1.0),      # 176 KB of weights: CTA-pair variant (output channels split over two SMs)
+    (1, 300, 64, 11, 1, True, True, 1.0 / 3),    # odd tile count: the pair's second CTA runs a masked duplicate
+    (3, 119, 64, 11, 3, True, False, 1.0),
+    (8, 6000, 64, 11, 5, True, True, 1.0 / 3),   # 408 tiles: every persistent CTA pair loops over several tile pairs
     (2, 400, 16, 3, 1, False, False, 1.0),       # I_da last stage
     (2, 401, 16, 11, 5, True, True, 1.0 / 3),
 ]
