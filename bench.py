@@ -188,6 +188,7 @@ def profile_plans(sib, plans, detail=None):
     Run after the timed region; gives the dominant kernel's share and its achieved FLOP rate."""
     agg = {}
     stream = torch.cuda.current_stream().cuda_stream
+    prev_pdl = sib.ops.set_pdl(False)   # stream-ordered launches: consecutive kernels must not overlap under the events
     for plan in plans:
         evs = []
         for fn, args, name in plan.steps:
@@ -225,6 +226,7 @@ def profile_plans(sib, plans, detail=None):
                                    "gbs": round(by / ms_ / 1e6, 1)})
             elif detail is not None:
                 detail.append({"kernel": name, "ms": round(e0.elapsed_time(e1), 4)})
+    sib.ops.set_pdl(prev_pdl)
     return agg
 
 

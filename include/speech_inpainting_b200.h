@@ -43,6 +43,9 @@ int sib_abi_version(void);
 const char* sib_last_error(void);
 /* number of kernels this library has launched from the calling thread (bench `gpu_launches`) */
 long long sib_launch_count(void);
+/* Programmatic dependent launch of the tensor-core / LayerNorm kernels (on by default; SIB_NO_PDL=1 in the environment
+ * turns it off).  Returns the previous setting.  Off = plain stream-ordered launches, e.g. for per-kernel timing. */
+int sib_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------------------------------
  * Generic frame-major 1-D convolution / linear layer with fused epilogue.

@@ -49,6 +49,7 @@ _SIGS = {
     "sib_abi_version": ([], C.c_int),
     "sib_last_error": ([], C.c_char_p),
     "sib_launch_count": ([], C.c_longlong),
+    "sib_set_pdl": ([_I], _I),
     "sib_conv1d_f32": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P], _I),
     "sib_conv1d_cout1_f32": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P], _I),
     "sib_conv0_f32": ([_I, _P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], _I),

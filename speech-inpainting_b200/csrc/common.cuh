@@ -65,7 +65,8 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 // pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as this grid's CTAs retire.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled();   // api.cu: false when SIB_NO_PDL is set (A/B switch)
+bool pdl_enabled();   // api.cu: false when SIB_NO_PDL is set or after sib_set_pdl(0)
+void set_pdl(int on);
 
 // cluster_x > 1 launches thread-block clusters of that many CTAs along x (CTA pairs for cta_group::2 kernels)
 template <typename... KArgs, typename... Args>

@@ -103,6 +103,11 @@ def _emit(name, args, keep=()):
         _lib.check(rc, name)
 
 
+def set_pdl(enabled: bool) -> bool:
+    """Programmatic dependent launch on / off (returns the previous setting); off gives clean per-kernel timings."""
+    return bool(_lib.lib().sib_set_pdl(int(enabled)))
+
+
 def launch_count() -> int:
     return int(_lib.lib().sib_launch_count())
 

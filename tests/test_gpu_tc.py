@@ -230,3 +230,29 @@ def test_conv_cout1_bf16(sib, B, T, C, k):
     sib.ops.conv1d_cout1(to_frame_major(x).cuda().to(torch.bfloat16).contiguous(), w[0].t().contiguous().cuda(), b.cuda(), y,
                          k, k // 2, 0.01, sib.ops.ACT_TANH)
     assert max_abs(ref[:, 0], y.cpu()) < 2e-5
+
+
+def test_new_operators_fail_loudly(sib):
+    """Unsupported configurations of the fused operators raise SibError - nothing falls back to another path."""
+    ops = sib.ops
+    assert ops.resunit_supported(32, 11, 5) and ops.resunit_supported(64, 11, 5) and ops.resunit_supported(64, 3, 1, True, True)
+    assert not ops.resunit_supported(128, 3, 1)       # wider stages use the conv kernel
+    assert not ops.resunit_supported(64, 4, 1)        # even kernel sizes have no "same" padding
+    x = torch.zeros(1, 64, 128, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(1, 1, 3, 128, 128, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(128, device="cuda")
+    with pytest.raises(sib.SibError, match="unsupported"):
+        ops.resunit(x, w, b, w, b, torch.empty_like(x), 3, 1)
+    x32 = torch.zeros(1, 64, 32, device="cuda", dtype=torch.bfloat16)
+    w32 = torch.zeros(1, 1, 3, 32, 32, device="cuda", dtype=torch.bfloat16)
+    b32 = torch.zeros(32, device="cuda")
+    with pytest.raises(sib.SibError, match="in-place"):
+        ops.resunit(x32, w32, b32, w32, b32, x32, 3, 1)
+    with pytest.raises(sib.SibError, match="slopes"):
+        ops.resunit(x32, w32, b32, w32, b32, torch.empty_like(x32), 3, 1, slope_in=1.5)
+    with pytest.raises(sib.SibError):
+        ops.conv0_gn_stats(torch.zeros(1, 4000, device="cuda"), torch.zeros(512, 3, device="cuda"), None, 512, 3, 2, 100, 1e-5,
+                           torch.empty(1, 512, device="cuda"), torch.empty(1, 512, device="cuda"))
+    # PDL switch round-trips
+    prev = ops.set_pdl(False)
+    assert ops.set_pdl(prev) is False
