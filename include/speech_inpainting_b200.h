@@ -127,6 +127,11 @@ int sib_zero_ranges_f32(float* wave, int batch, int n, const int32_t* lo, const 
  * eps 1e-7, tail -> 0) ; eps 1e-5 reproduces F.layer_norm(x, x.shape) (hubert_feature_reader.py:53-54). */
 int sib_znorm_f32(const float* x, float* y, int batch, int n, const int32_t* lengths, float eps,
                   sib_stream_t stream);
+/* 8f row 1 (I_ea/predict.py:99-103): y = normalize(x with [lo[b], hi[b]) zeroed) * scale, where normalize is
+ * librosa.util.normalize (x / max|x|; rows whose peak is below FLT_MIN are left unscaled).  lo / hi nullable (no mask).
+ * Feeds sib_mel_spectrogram_f32(hop 441, pad 312) = get_mel (I_ea/dataset/mel_dump.py:96-98). */
+int sib_mask_peak_normalize_f32(const float* x, float* y, int batch, int n, const int32_t* lo, const int32_t* hi,
+                                float scale, sib_stream_t stream);
 /* a11: ragged gather of masked frames: out[off[b]+i, :] = src[b, pos[b]+i, :], i < len[b] (predict.py:164-168) */
 int sib_gather_frames_f32(const float* src, int batch, int t, int d, const int32_t* pos, const int32_t* len,
                           const int32_t* off, float* out, sib_stream_t stream);

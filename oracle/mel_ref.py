@@ -76,6 +76,23 @@ def feature_mel(y22: torch.Tensor) -> torch.Tensor:
     return mel_spectrogram(y22, hop_size=441, fmax=8000, pad=312)
 
 
+def peak_normalize(x: np.ndarray) -> np.ndarray:
+    """librosa.util.normalize(x) for a 1-D float32 signal (norm=inf, threshold=tiny, fill=None): x / max|x|, unchanged
+    when the peak is below the smallest normal float (librosa is absent: restated from its published algorithm;
+    oracle/make_golden.py stubs it the same way)."""
+    x = np.asarray(x, dtype=np.float32)
+    peak = np.abs(x).max() if x.size else np.float32(0)
+    return x if peak < np.finfo(np.float32).tiny else (x / peak).astype(np.float32)
+
+
+def masked_feature_mel(wave22: np.ndarray, lo: int, hi: int) -> torch.Tensor:
+    """I_ea/predict.py:99-104: wave_22_masked[start:end] = 0; normalize(.) * 0.95; get_mel -> [1, 80, T']."""
+    w = np.array(wave22, dtype=np.float32, copy=True)
+    w[lo:hi] = 0
+    w = (peak_normalize(w) * np.float32(0.95)).astype(np.float32)
+    return feature_mel(torch.from_numpy(w)[None])
+
+
 def mel_l1(y_a: torch.Tensor, y_b: torch.Tensor, sampling_rate=22050) -> float:
     """mel-L1 acceptance metric: F.l1_loss of hop-256 log-mels with fmax=None
     (I_ea/hifi_gan/train.py:224-227 uses fmax_for_loss = null)."""

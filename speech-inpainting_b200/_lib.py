@@ -60,6 +60,7 @@ _SIGS = {
     "sib_attention_f32": ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
     "sib_zero_padded_frames_f32": ([_P, _P, _I, _I, _I, _P], _I),
     "sib_zero_ranges_f32": ([_P, _I, _I, _P, _P, _F, _P], _I),
+    "sib_mask_peak_normalize_f32": ([_P, _P, _I, _I, _P, _P, _F, _P], _I),
     "sib_znorm_f32": ([_P, _P, _I, _I, _P, _F, _P], _I),
     "sib_gather_frames_f32": ([_P, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "sib_cos_argmax_f32": ([_P, _P, _I, _I, _I, _P, _P], _I),

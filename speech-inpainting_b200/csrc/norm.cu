@@ -394,6 +394,42 @@ __global__ void zero_ranges_kernel(float* __restrict__ wave, int n, const int32_
   }
 }
 
+// Feature front-end of I_ea (predict.py:99-103): zero [lo, hi) of the 22.05 kHz wave, then librosa.util.normalize
+// (x / max|x|, rows whose peak is below the smallest normal float are left as they are) times `scale` (0.95).
+// One CTA per utterance; the masked samples never count towards the peak and come out as exact zeros.
+__global__ void __launch_bounds__(1024) mask_peak_normalize_kernel(const float* __restrict__ x, float* __restrict__ y, int n,
+                                                                   const int32_t* __restrict__ lo,
+                                                                   const int32_t* __restrict__ hi, float scale) {
+  __shared__ float red[32];
+  __shared__ float bc;
+  const int b = blockIdx.x;
+  const float* xb = x + (int64_t)b * n;
+  float* yb = y + (int64_t)b * n;
+  int l = 0, h = 0;
+  if (lo && hi) {   // numpy slice semantics, as sib_zero_ranges_f32
+    l = lo[b]; h = hi[b];
+    if (l < 0) l += n;
+    if (h < 0) h += n;
+    l = min(max(l, 0), n);
+    h = min(max(h, 0), n);
+  }
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (i < l || i >= h) m = fmaxf(m, fabsf(xb[i]));
+  m = sib::warp_max(m);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.f;
+    t = sib::warp_max(t);
+    if (lane == 0) bc = t;
+  }
+  __syncthreads();
+  const float peak = bc >= 1.17549435e-38f ? bc : 1.0f;   // np.finfo(np.float32).tiny
+  for (int i = threadIdx.x; i < n; i += blockDim.x) yb[i] = (i >= l && i < h) ? 0.f : (xb[i] / peak) * scale;
+}
+
 template <typename TY>
 __global__ void zero_padded_frames_kernel(TY* __restrict__ h, const int32_t* __restrict__ key_len, int T, int C) {
   const int b = blockIdx.y;
@@ -563,6 +599,15 @@ extern "C" int sib_zero_ranges_f32(float* wave, int batch, int n, const int32_t*
   dim3 grid(min(sib::ceil_div(n, 256), 64), batch);
   zero_ranges_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(wave, n, lo, hi, add_eps);
   SIB_CHECK_LAUNCH("sib_zero_ranges_f32");
+  return SIB_OK;
+}
+
+extern "C" int sib_mask_peak_normalize_f32(const float* x, float* y, int batch, int n, const int32_t* lo, const int32_t* hi,
+                                           float scale, sib_stream_t stream) {
+  SIB_REQUIRE(x && y && batch > 0 && n > 0, "sib_mask_peak_normalize_f32: bad argument");
+  SIB_REQUIRE((lo == nullptr) == (hi == nullptr), "sib_mask_peak_normalize_f32: lo and hi must both be given or both be null");
+  mask_peak_normalize_kernel<<<batch, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, lo, hi, scale);
+  SIB_CHECK_LAUNCH("sib_mask_peak_normalize_f32");
   return SIB_OK;
 }
 

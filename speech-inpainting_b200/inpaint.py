@@ -80,12 +80,20 @@ class InformedInpainter:
         self.device = dev
 
     def __call__(self, wave16, mel, mask_pos, mask_len, apply_mask: bool = True, normalize: bool = True,
-                 attention_mask=None, return_int16: bool = False):
+                 attention_mask=None, return_int16: bool = False, wave22=None, zero22=None):
         """wave16 [B,N] float32 (host or device), mel [B,80,T'] (hop-441 log-mel of the masked 22 kHz wave),
         mask_pos/mask_len: per-utterance frame index / length (ints or sequences).
+        Instead of a precomputed `mel` (pass None) the 22.05 kHz rendition `wave22` [B,S] and its zero ranges `zero22`
+        (list of (lo, hi), `iea_mask_indices(...)["zero22"]`) can be given: the feature front-end of predict.py:99-104
+        (zero-mask, normalize * 0.95, get_mel) then runs on the device too.
         Returns namespace(wave [B,1,S], labels [sum L] int64, mel [B,80,T'] inpainted, offsets)."""
         dev = self.device
         B, N = wave16.shape
+        if mel is None:
+            if wave22 is None:
+                raise SibError("either mel or wave22 must be given")
+            from .mel import masked_feature_mel
+            mel = masked_feature_mel(wave22.to(dev, non_blocking=True), zero22)
         pos = [int(p) for p in (mask_pos if hasattr(mask_pos, "__len__") else [mask_pos] * B)]
         ln = [int(l) for l in (mask_len if hasattr(mask_len, "__len__") else [mask_len] * B)]
         if len(pos) != B or len(ln) != B:

@@ -66,6 +66,23 @@ def get_mel(x, hop_size=441):
     return mel_spectrogram(x, 1024, 80, 22050, hop_size, 1024, 0, 8000, pad=312)
 
 
+def masked_feature_mel(wave22, zero22=None, scale=0.95):
+    """The feature front-end of I_ea/predict.py:99-104 on the device: zero [lo, hi) of every 22.05 kHz utterance
+    (`zero22` = list of (lo, hi) or None), `normalize(.) * 0.95` (librosa.util.normalize), `get_mel`.
+    wave22 [B, S] float32 (host or CUDA) -> log-mel [B, 80, S // 441]."""
+    dev = wave22.device if wave22.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    x = wave22.to(dev, torch.float32, non_blocking=True).contiguous()
+    lo = hi = None
+    if zero22 is not None:
+        if len(zero22) != x.shape[0]:
+            raise SibError("zero22 must have one (lo, hi) pair per utterance")
+        lo = torch.as_tensor([int(r[0]) for r in zero22], dtype=torch.int32).to(dev)
+        hi = torch.as_tensor([int(r[1]) for r in zero22], dtype=torch.int32).to(dev)
+    y = torch.empty_like(x)
+    ops.mask_peak_normalize(x, y, lo, hi, scale)
+    return get_mel(y)
+
+
 def mel_l1(y_a, y_b, sampling_rate=22050) -> float:
     """mel-L1 acceptance metric (hop 256, fmax=None; I_ea/hifi_gan/train.py:224-227)."""
     ma = mel_spectrogram(y_a, sampling_rate=sampling_rate, fmax=None)

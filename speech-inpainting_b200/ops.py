@@ -303,6 +303,13 @@ def zero_ranges(wave, lo, hi, add_eps=0.0):
     _emit("sib_zero_ranges_f32", (_p(wave), B, n, _p(lo), _p(hi), add_eps), keep=(wave, lo, hi))
 
 
+def mask_peak_normalize(x, y, lo=None, hi=None, scale=0.95):
+    """y = librosa.util.normalize(x with [lo, hi) zeroed) * scale per utterance (predict.py:99-103)."""
+    B, n = x.shape
+    _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y"); _chk(lo, torch.int32, "lo"); _chk(hi, torch.int32, "hi")
+    _emit("sib_mask_peak_normalize_f32", (_p(x), _p(y), B, n, _p(lo), _p(hi), scale), keep=(x, y, lo, hi))
+
+
 def znorm(x, y, lengths=None, eps=1e-7):
     B, n = x.shape
     _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y"); _chk(lengths, torch.int32, "lengths")

@@ -303,3 +303,33 @@ def test_plan_replay_and_cuda_graph(sib):
     gen2.use_cuda_graph = True
     gen2.load_state_dict(make_generator_params(cfg, 1, "unit"))
     assert torch.equal(y1, gen2(x)) and torch.equal(y1, gen2(x))
+
+
+def test_informed_inpainting_from_wave22(sib):
+    """The pipeline fed with the 22.05 kHz rendition instead of a precomputed mel equals the pipeline
+    fed with the oracle's mel of the same masked, normalised signal."""
+    from oracle import glue_ref, mel_ref
+    from oracle.params import HifiCfg, HubertCfg, make_codebook, make_generator_params, make_head_params, make_hubert_params
+    ocfg, gcfg = HubertCfg.tiny(False), HifiCfg.tiny()
+    sd = make_hubert_params(ocfg, 1234, prefix="base_model.")
+    sd.update(make_head_params(ocfg.hidden_size, 80))
+    gp = make_generator_params(gcfg, 1234, "unit")
+    C = make_codebook(80, 100)
+    g = torch.Generator().manual_seed(5)
+    B, N = 2, 32000
+    wave16 = 0.1 * torch.randn(B, N, generator=g)
+    wave22 = (0.1 * torch.randn(B, N * 22050 // 16000, generator=g)).clamp(-1, 1)
+    idx = [glue_ref.iea_mask_indices(0.9, 1.1), glue_ref.iea_mask_indices(0.2, 0.6)]
+    pos, ln = [i["mask_pos"] for i in idx], [i["mask_len"] for i in idx]
+    model = sib.CustomModel(80, "base", False, config=_hub_cfg(sib, ocfg)).to("cuda")
+    model.load_state_dict(sd)
+    gen = sib.Generator(sib.AttrDict(gcfg.as_attrdict())).to("cuda")
+    gen.load_state_dict(gp)
+    pipe = sib.InformedInpainter(model, gen, C)
+    res = pipe(wave16, None, pos, ln, wave22=wave22, zero22=[i["zero22"] for i in idx])
+    mel_ref_ = torch.cat([mel_ref.masked_feature_mel(wave22[b].numpy(), *idx[b]["zero22"]) for b in range(B)])
+    res2 = pipe(wave16, mel_ref_, pos, ln)
+    assert torch.equal(res.labels, res2.labels)
+    assert snr_db(res2.wave.cpu(), res.wave.cpu()) > 60
+    with pytest.raises(sib.SibError, match="mel or wave22"):
+        pipe(wave16, None, pos, ln)

@@ -270,3 +270,28 @@ def test_errors_are_loud(sib):
     xd = torch.zeros(1, 8, 16, device="cuda")
     with pytest.raises(sib.SibError, match="groups"):
         sib.ops.conv1d(xd, xd, None, xd.clone(), [0], groups=3)
+
+
+def test_masked_feature_mel_front_end(sib):
+    """predict.py:99-104 on the device (22 kHz zero-mask -> normalize * 0.95 -> get_mel) vs the oracle."""
+    from oracle import glue_ref, mel_ref
+    g = torch.Generator().manual_seed(11)
+    B, S = 3, 44100
+    wave = (0.2 * torch.randn(B, S, generator=g)).clamp(-1, 1)
+    wave[2] = 0.0                                             # silent utterance: normalize leaves it untouched
+    ranges = [glue_ref.iea_mask_indices(0.9, 1.1)["zero22"], (0, 0), (100, 5000)]
+    xd = wave.cuda()
+    yd = torch.empty_like(xd)
+    lo = torch.tensor([r[0] for r in ranges], dtype=torch.int32).cuda()
+    hi = torch.tensor([r[1] for r in ranges], dtype=torch.int32).cuda()
+    sib.ops.mask_peak_normalize(xd, yd, lo, hi, 0.95)
+    for b in range(B):
+        w = wave[b].numpy().copy()
+        w[ranges[b][0]:ranges[b][1]] = 0
+        ref = (mel_ref.peak_normalize(w) * np.float32(0.95)).astype(np.float32)
+        assert np.array_equal(ref, yd[b].cpu().numpy()), f"utterance {b}: masked / normalised samples differ"   # bit exact
+    mel = sib.masked_feature_mel(wave, ranges)
+    assert mel.shape == (B, 80, S // 441)
+    for b in range(2):
+        ref = mel_ref.masked_feature_mel(wave[b].numpy(), *ranges[b])
+        assert max_abs(ref[0], mel[b].cpu()) < 2e-3 and float((ref[0] - mel[b].cpu()).abs().mean()) < 2e-5

@@ -146,3 +146,19 @@ def test_znorm_and_int16_oracle():
     assert max_abs(glue_ref.fairseq_layer_norm(x[0]), torch.nn.functional.layer_norm(x[0], x[0].shape)) == 0
     y = torch.tensor([[[0.5, -0.5, 0.99999, -1.0, 3.0e-5]]])
     assert hifigan_ref.to_int16(y).tolist() == [16384, -16384, 32767, -32768, 0]
+
+
+def test_feature_front_end_oracle():
+    """predict.py:99-104 restated: the mask is applied before the peak normalisation and silent input stays silent."""
+    from oracle import glue_ref, mel_ref
+    rng = np.random.default_rng(0)
+    w = (0.3 * rng.standard_normal(22050)).astype(np.float32)
+    lo, hi = glue_ref.iea_mask_indices(0.4, 0.6)["zero22"]
+    assert (lo, hi) == (int(0.4 * 16000) * 22050 // 16000, int(0.6 * 16000) * 22050 // 16000)
+    n = mel_ref.peak_normalize(w)
+    assert np.isclose(np.abs(n).max(), 1.0) and np.array_equal(mel_ref.peak_normalize(np.zeros(8, np.float32)), np.zeros(8, np.float32))
+    m = mel_ref.masked_feature_mel(w, lo, hi)
+    assert m.shape == (1, 80, 22050 // 441)
+    # frames whose 1024-sample window lies entirely inside the zeroed range are log(1e-5 clamp) silence
+    f = (lo + 1024 + 312) // 441 + 1
+    assert torch.allclose(m[0, :, f], torch.full((80,), float(np.log(1e-5))), atol=1e-3)
