@@ -35,7 +35,7 @@ extern "C" {
 
 enum sib_status { SIB_OK = 0, SIB_ERR_INVALID = 1, SIB_ERR_CUDA = 2, SIB_ERR_UNSUPPORTED = 3 };
 enum sib_act { SIB_ACT_NONE = 0, SIB_ACT_GELU = 1, SIB_ACT_LRELU = 2, SIB_ACT_TANH = 3 };
-enum sib_dtype { SIB_F32 = 0, SIB_BF16 = 1 };
+enum sib_dtype { SIB_F32 = 0, SIB_BF16 = 1, SIB_I16 = 2 /* int16 PCM, sib_resample input only */ };
 
 typedef void* sib_stream_t; /* cudaStream_t */
 
@@ -162,6 +162,30 @@ int sib_mel_spectrogram_f32(const float* wave, int batch, int n, int hop, int pa
                             int n_mels, float* out, int frames, void* workspace /* sib_mel_workspace_bytes(n_mels) */,
                             sib_stream_t stream);
 size_t sib_mel_workspace_bytes(int n_mels);
+
+/* ------------------------------------------------------------------------------------------ 8f rows 3 and 4
+ * 8f row 3: rational poly-phase resampler, the device side of `librosa.load(path, sr=22050)` / `sr=16000`
+ * (I_ea/predict.py:79-80) and `resampy.resample(data, sr, 16000)` (I_da/scripts/preprocess.py:43-45):
+ *   y[b, n] = sum_{j < taps} filt[j][n % up] * x[b, (n*down)/up + first + j],   x == 0 outside [0, len_in[b]) (nullable)
+ * x is fp32 or int16 PCM (SIB_I16: scaled by 1/32768 on load, the soundfile / librosa convention); `filt` is the
+ * windowed-sinc prototype sampled per output residue, [taps][up] with the residue contiguous (built on the host by
+ * speech_inpainting_b200.audio.resample_filter).  up = down = taps = 1, first = 0, filt = {1} is a plain PCM -> float
+ * conversion.  n_out is the caller's ceil(n_in*up/down). */
+int sib_resample(const void* x, int x_dtype, int batch, int n_in, int64_t x_batch_stride, const int32_t* len_in,
+                 const float* filt, int up, int down, int taps, int first, float* y, int n_out, int64_t y_batch_stride,
+                 const int32_t* len_out /* nullable: y[b, n >= len_out[b]] = 0 */, sib_stream_t stream);
+size_t sib_resample_smem_bytes(int down, int taps);
+/* 8f row 4: SI-SDR per utterance (I_ea/metrics.py:127-141): a = (eps + <r,e>)/(<r,r> + eps),
+ * out[b] = 10 log10((eps + |a r|^2)/(eps + |e - a r|^2)); est/ref [B,n] fp32, lengths nullable, double accumulation in
+ * a fixed order (bit-reproducible).  eps = FLT_EPSILON reproduces the reference on float32 arrays. */
+int sib_si_sdr_f32(const float* est, const float* ref, int batch, int n, const int32_t* lengths, float eps, float* out,
+                   void* workspace /* sib_si_sdr_workspace_bytes(batch) */, sib_stream_t stream);
+size_t sib_si_sdr_workspace_bytes(int batch);
+/* out[b] = mean_i |a[b,i] - b[b,i]| over n elements per utterance: the reduction of mel-L1
+ * (F.l1_loss(y_mel, y_g_hat_mel), I_ea/hifi_gan/train.py:224-227) on two sib_mel_spectrogram_f32 outputs. */
+int sib_abs_diff_mean_f32(const float* a, const float* b, int batch, int64_t n, float* out,
+                          void* workspace /* sib_abs_diff_workspace_bytes(batch) */, sib_stream_t stream);
+size_t sib_abs_diff_workspace_bytes(int batch);
 
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core path (tcgen05 + TMA), see DESIGN.md.  Same contract as sib_conv1d_f32 with

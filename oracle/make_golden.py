@@ -272,6 +272,81 @@ def golden_mel():
     np.savez_compressed(os.path.join(OUT, "mel_golden.npz"), **res)
 
 
+def golden_resample():
+    """8f row 3: the oracle resampler against torchaudio's Kaiser-windowed sinc with resampy's kaiser_best parameters
+    (float64, so the comparison sees the formulation, not fp32 kernel rounding)."""
+    import torchaudio
+    from oracle import resample_ref as R
+    res = {}
+    x = 0.25 * torch.randn(12000, generator=torch.Generator().manual_seed(9), dtype=torch.float64)
+    x[3000:3400] = 0.0
+    res["x"] = x.numpy().astype(np.float32)
+    for o, n in ((16000, 22050), (22050, 16000), (48000, 16000), (24000, 22050)):
+        ta = torchaudio.functional.resample(torch.from_numpy(res["x"].astype(np.float64)), o, n, lowpass_filter_width=R.ZEROS,
+                                            rolloff=R.ROLLOFF, resampling_method="sinc_interp_kaiser", beta=R.BETA).numpy()
+        mine = R.resample(res["x"], o, n)
+        err = np.abs(ta - mine).max()
+        print(f"resample {o}->{n}: {mine.shape[0]} samples, oracle vs torchaudio(float64) max-abs {err:.2e}")
+        assert ta.shape == mine.shape and err < 2e-7   # torchaudio holds beta as a float32 tensor
+        res[f"y_{o}_{n}"] = ta
+    np.savez_compressed(os.path.join(OUT, "resample_golden.npz"), **res)
+
+
+def golden_f0vq():
+    """8f row 2: the reference's own Jukebox Encoder (I_da/src/modules/jukebox.py) and BottleneckBlock.quantise
+    (vq.py:118-128; the class itself cannot be built without a GPU - reset_k() calls .cuda(), vq.py:22)."""
+    from oracle import f0vq_ref
+    for n in ["src.modules.dvector", "src.modules.ge2e", "src.modules.ge2e_dataset",
+              "src.modules.infinite_dataloader", "src.modules.wav2mel"]:
+        if n not in sys.modules:
+            _stub(n, AttentivePooledLSTMDvector=None, GE2ELoss=None, GE2EDataset=None, collate_batch=None,
+                  InfiniteDataLoader=None, infinite_iterator=None, Wav2Mel=None)
+    from src.modules.jukebox import Encoder
+    from src.modules.vq import BottleneckBlock
+    cfg = f0vq_ref.F0_QUANTIZER
+    enc = Encoder(**cfg["f0_encoder_params"]).eval()
+    sd = f0vq_ref.make_params(cfg, seed=1234)
+    enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    enc.load_state_dict(enc_sd)   # strict: key names and shapes of the restatement == the reference module's
+    res = {}
+    for B, L in ((2, 784), (1, 160)):
+        f0 = torch.randn(B, 1, L, generator=torch.Generator().manual_seed(L))
+        with torch.no_grad():
+            h_ref = enc(f0)[0]
+            z_ref, _ = BottleneckBlock.quantise(types.SimpleNamespace(k=sd["vq.level_blocks.0.k"]),
+                                                h_ref.permute(0, 2, 1).reshape(-1, h_ref.shape[1]))
+        h = f0vq_ref.encoder_forward(sd, f0)
+        z = f0vq_ref.quantise(h, sd["vq.level_blocks.0.k"])
+        err = (h - h_ref).abs().max().item()
+        print(f"f0 encoder B={B} L={L}: -> {tuple(h_ref.shape)} max-abs {err:.2e}; bins equal: {torch.equal(z.view(-1), z_ref)}")
+        assert err < 1e-5 and torch.equal(z.view(-1), z_ref)
+        res[f"h_{L}"] = h_ref.numpy()
+        res[f"z_{L}"] = z_ref.view(B, -1).numpy()
+    np.savez_compressed(os.path.join(OUT, "f0vq_golden.npz"), **res)
+
+
+def golden_metrics():
+    """8f row 4: Metrics.sisdr lifted out of I_ea/metrics.py with ast (the module itself fails to import)."""
+    import ast
+    from oracle import metrics_ref
+    src = open(os.path.join(REF, "I_ea", "metrics.py")).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "sisdr")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "I_ea/metrics.py", "exec"), ns)
+    g = torch.Generator().manual_seed(21)
+    ref = 0.3 * torch.randn(3, 22050, generator=g)
+    est = ref * torch.tensor([[1.0], [0.5], [2.0]]) + torch.tensor([[0.01], [0.1], [0.5]]) * torch.randn(3, 22050, generator=g)
+    vals = []
+    for b in range(3):
+        e, r = est[b].numpy().astype(np.float64), ref[b].numpy().astype(np.float64)
+        want = float(ns["sisdr"](None, e, r))
+        got = metrics_ref.sisdr(e, r)
+        assert abs(want - got) < 1e-9, (want, got)
+        vals.append(want)
+    print("sisdr pinned:", [round(v, 4) for v in vals])
+    np.savez_compressed(os.path.join(OUT, "metrics_golden.npz"), sisdr=np.array(vals))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -281,6 +356,9 @@ def main():
     golden_mel()
     golden_hifigan()
     golden_hubert()
+    golden_resample()
+    golden_f0vq()
+    golden_metrics()
     print("golden fixtures written to", OUT)
 
 

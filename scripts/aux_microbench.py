@@ -71,6 +71,15 @@ def main():
     # int16 pack
     yi = torch.empty(32, 88064, device=dev, dtype=torch.int16)
     report("pack int16 32x88064", timeit(lambda: ops.pack_int16(yo, yi)), 6.0 * yo.numel())
+    # 8f row 3: int16 PCM at 22.05 kHz -> float32 at 16 kHz and 16 k -> 22.05 k, 256 x 4 s
+    pcm = (torch.randn(256, 88200, device=dev) * 3000).to(torch.int16)
+    r16 = sib.resample(pcm, 22050, 16000)
+    report("resample i16 22.05k -> f32 16k", timeit(lambda: sib.resample(pcm, 22050, 16000)), 2.0 * pcm.numel() + 4.0 * r16.numel())
+    r22 = sib.resample(r16, 16000, 22050)
+    report("resample f32 16k -> 22.05k", timeit(lambda: sib.resample(r16, 16000, 22050)), 4.0 * r16.numel() + 4.0 * r22.numel())
+    # 8f row 4: SI-SDR (two passes over both signals) and the mel-L1 reduction, 256 x 4 s
+    out = torch.empty(256, device=dev)
+    report("si_sdr 256x88200 (2 passes)", timeit(lambda: ops.si_sdr(r22, r22, out)), 16.0 * r22.numel())
 
 
 if __name__ == "__main__":

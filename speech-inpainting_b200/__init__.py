@@ -9,7 +9,9 @@ Everything executes in `libsib_b200.so` (hand-written CUDA); importing fails if 
 from ._lib import SibError, lib as _load_lib, exported_symbols  # noqa: F401
 from .hubert import HubertConfig, HubertModel, CustomModel  # noqa: F401
 from .hifigan import Generator, CodeGenerator, AttrDict, get_padding  # noqa: F401
-from .mel import mel_spectrogram, get_mel, mel_l1, mel_filterbank, masked_feature_mel  # noqa: F401
+from .f0vq import F0Quantizer  # noqa: F401
+from .mel import mel_spectrogram, get_mel, mel_l1, si_sdr, mel_filterbank, masked_feature_mel  # noqa: F401
+from .audio import resample, resample_filter, read_wav, write_wav, load_wav_batch  # noqa: F401
 from .inpaint import (InformedInpainter, BlindInpainter, iea_mask_indices, iea_zero_range, extend_mel,  # noqa: F401
                       shard_batch, ida_matched_frames)
 from . import ops  # noqa: F401

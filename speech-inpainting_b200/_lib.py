@@ -72,6 +72,12 @@ _SIGS = {
     "sib_pack_int16_f32": ([_P, _P, _L, _P], _I),
     "sib_mel_spectrogram_f32": ([_P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P], _I),
     "sib_mel_workspace_bytes": ([_I], C.c_size_t),
+    "sib_resample": ([_P, _I, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _I, _L, _P, _P], _I),
+    "sib_resample_smem_bytes": ([_I, _I], C.c_size_t),
+    "sib_si_sdr_f32": ([_P, _P, _I, _I, _P, _F, _P, _P, _P], _I),
+    "sib_si_sdr_workspace_bytes": ([_I], C.c_size_t),
+    "sib_abs_diff_mean_f32": ([_P, _P, _I, _L, _P, _P, _P], _I),
+    "sib_abs_diff_workspace_bytes": ([_I], C.c_size_t),
     "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16": ([C.POINTER(ResUnitDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16_supported": ([_I, _I, _I, _I, _I], _I),

@@ -326,9 +326,10 @@ class Generator(_StateHolder):
 class CodeGenerator(Generator):
     """I_da/src/model.py:42-189 for the shipped config (no code VQ; f0_stats and multispkr set).
 
-    The frozen f0 VQ-VAE encoder (model.py:148-153, Jukebox convs, `.cuda()` hard-coded in vq.py:22) is
-    SURVEY 8f "next" row 2: this class takes its output `z_p` (bin indices [B, T/4]) through the extra
-    keyword `f0_code`; passing raw `f0` without `f0_code` raises."""
+    The frozen f0 VQ-VAE encoder + quantiser (model.py:148-153) is `self.fo_vqvae`, an `F0Quantizer`
+    running on the same fp32 conv / argmin kernels: `forward(code=, f0=, emb=, spkr=)` is the reference call.  Its weights
+    arrive under `fo_vqvae.*` in a CodeGenerator checkpoint, or through `load_f0_quantizer(ckpt['generator'])` (the file
+    `h.f0_quantizer_path` points at, model.py:63-71).  Callers that already hold the bins may pass `f0_code=` instead."""
 
     def __init__(self, h, precision: str = "fp32"):
         super().__init__(h, precision)
@@ -336,21 +337,41 @@ class CodeGenerator(Generator):
         self.embedding_dim = int(_hget(h, "embedding_dim"))
         fq = _hget(h, "f0_quantizer") or {}
         self.f0_bins = int(fq.get("f0_vq_params", {}).get("l_bins", 20)) if isinstance(fq, dict) else 20
+        self.fo_vqvae = None
+        if isinstance(fq, dict) and "f0_encoder_params" in fq:
+            from .f0vq import F0Quantizer
+            self.fo_vqvae = F0Quantizer(fq)
 
     def _extra_keys(self):
         return ["emb_c.weight", "emb_p.weight", "emb_s.weight"]
 
     def load_state_dict(self, sd, strict: bool = True):
-        # the reference checkpoint also carries the frozen fo_vqvae.*; it is not on this path
+        fo = {k[len("fo_vqvae."):]: v for k, v in sd.items() if k.startswith("fo_vqvae.")}
+        if fo and self.fo_vqvae is not None:
+            self.fo_vqvae.load_state_dict(fo, strict)
         sd = {k: v for k, v in sd.items() if not k.startswith("fo_vqvae.")}
         return super().load_state_dict(sd, strict)
+
+    def load_f0_quantizer(self, sd, strict: bool = True):
+        """`torch.load(h.f0_quantizer_path)["generator"]` (model.py:66-69)."""
+        if self.fo_vqvae is None:
+            raise SibError("this CodeGenerator was configured without an f0_quantizer")
+        return self.fo_vqvae.load_state_dict(sd, strict)
+
+    def to(self, device=None, *a, **k):
+        super().to(device, *a, **k)
+        if self.fo_vqvae is not None:
+            self.fo_vqvae.to(device, *a, **k)
+        return self
 
     def forward(self, **kwargs):
         self._require_cuda()
         code = kwargs["code"]
         if "f0_code" not in kwargs:
-            raise SibError("CodeGenerator needs f0_code= (quantised f0 bins [B, T/4]); the f0 VQ-VAE encoder is "
-                           "outside the hot path (SURVEY 8f row 2)")
+            if kwargs.get("f0") is None or self.fo_vqvae is None or not self.fo_vqvae._sd:
+                raise SibError("CodeGenerator needs f0= together with loaded fo_vqvae weights (load_state_dict with "
+                               "fo_vqvae.* keys or load_f0_quantizer), or precomputed bins through f0_code=")
+            kwargs = dict(kwargs, f0_code=self.fo_vqvae.encode(kwargs["f0"]))   # model.py:148-152
         zp, emb = kwargs["f0_code"], kwargs["emb"]
         dev = self._device
         code = code.to(dev, torch.int64).contiguous()

@@ -167,8 +167,13 @@ class BlindInpainter:
         ops.l2_argmin(feats.reshape(B * T, H), self.mu, labels)  # kmeans_model.predict (inpainting.py:204-205)
         return labels.view(B, T)
 
-    def __call__(self, wave, mask_size: int, f0_code, emb, informed: bool = True, return_int16: bool = False):
+    def __call__(self, wave, mask_size: int, f0_code=None, emb=None, informed: bool = True, return_int16: bool = False,
+                 f0=None):
+        """`f0` = the continuous f0 track [B, 1, frames at hop 80] the reference passes (inpainting.py:231, quantised
+        inside CodeGenerator by the frozen f0 VQ-VAE); `f0_code` = already quantised bins [B, frames / 16] instead."""
         dev = self.device
+        if (f0 is None) == (f0_code is None) or emb is None:
+            raise SibError("BlindInpainter needs emb and exactly one of f0= (continuous track) / f0_code= (pitch bins)")
         y = wave.to(dev, torch.float32).contiguous()
         B, N = y.shape
         frame_start = int(self.sr * 3 / 2)                                  # inpainting.py:187
@@ -182,9 +187,16 @@ class BlindInpainter:
             code_inp[:, b:] = code[:, b:]
         # match_length over (audio hop 1, code hop 320, f0 hop 80) then drop the tail so that the audio is a
         # multiple of 1280 samples (multiseries.py:5-73, inpainting.py:217-256)
-        n_code = ida_matched_frames(N, code.shape[1], 16 * f0_code.shape[1], self.hop)  # one f0 bin = 16 f0 frames
+        n_f0 = f0.shape[-1] if f0 is not None else 16 * f0_code.shape[1]         # one f0 bin = 16 f0 frames
+        n_code = ida_matched_frames(N, code.shape[1], n_f0, self.hop)
         code, code_inp = code[:, :n_code].contiguous(), code_inp[:, :n_code].contiguous()
-        zp = f0_code.to(dev)[:, : n_code // 4].contiguous()
+        if f0 is not None:   # the encoder + quantiser are deterministic: one pass serves both generate() calls
+            zp = self.gen.fo_vqvae.encode(f0.to(dev)[..., : n_code * 4]) if getattr(self.gen, "fo_vqvae", None) is not None \
+                else None
+            if zp is None:
+                raise SibError("f0= needs a CodeGenerator configured with an f0_quantizer")
+        else:
+            zp = f0_code.to(dev)[:, : n_code // 4].contiguous()
         wav_gen = self.gen(code=code, f0_code=zp, emb=emb)                   # :258
         wav_inp = self.gen(code=code_inp, f0_code=zp, emb=emb)               # :259
         res = SimpleNamespace(audio_gen=wav_gen, audio_inp=wav_inp, code=code, code_inpainting=code_inp,

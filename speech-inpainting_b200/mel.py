@@ -83,8 +83,26 @@ def masked_feature_mel(wave22, zero22=None, scale=0.95):
     return get_mel(y)
 
 
-def mel_l1(y_a, y_b, sampling_rate=22050) -> float:
-    """mel-L1 acceptance metric (hop 256, fmax=None; I_ea/hifi_gan/train.py:224-227)."""
+def mel_l1(y_a, y_b, sampling_rate=22050, per_utterance=False):
+    """mel-L1 acceptance metric (hop 256, fmax=None; I_ea/hifi_gan/train.py:224-227), reduced on the device
+    (SURVEY 8f row 4).  Returns the batch mean as a float, or the per-utterance means [B] with `per_utterance`."""
     ma = mel_spectrogram(y_a, sampling_rate=sampling_rate, fmax=None)
     mb = mel_spectrogram(y_b, sampling_rate=sampling_rate, fmax=None)
-    return float((ma - mb).abs().mean())
+    per = torch.empty(ma.shape[0], device=ma.device, dtype=torch.float32)
+    ops.abs_diff_mean(ma, mb, per)
+    return per if per_utterance else float(per.double().mean())
+
+
+def si_sdr(est, ref, lengths=None):
+    """Scale-invariant SDR in dB per utterance (I_ea/metrics.py:127-141) for CUDA float32 [B, n] (or [n]) waveforms."""
+    if not (est.is_cuda and ref.is_cuda):
+        raise SibError("si_sdr: operands must be CUDA tensors (no CPU fallback)")
+    squeeze = est.dim() == 1
+    e = est.reshape(1, -1) if squeeze else est
+    r = ref.reshape(1, -1) if squeeze else ref
+    e, r = e.to(torch.float32).contiguous(), r.to(torch.float32).contiguous()
+    if lengths is not None:
+        lengths = torch.as_tensor(lengths, dtype=torch.int32).to(e.device)
+    out = torch.empty(e.shape[0], device=e.device, dtype=torch.float32)
+    ops.si_sdr(e, r, out, lengths)
+    return out[0] if squeeze else out

@@ -389,3 +389,42 @@ def cast_to_bf16(x, out):
 
 def cast_to_f32(x, out):
     _emit("sib_cast_bf16_to_f32", (_p(x), _p(out), x.numel()), keep=(x, out))
+
+
+# ----------------------------------------------------------------------------- audio formats / metrics
+def resample(x, filt, up, down, first, y, len_in=None, len_out=None):
+    """y[b, n] = sum_j filt[j][n % up] * x[b, (n*down)//up + first + j]; x int16 PCM (scaled by 1/32768) or float32."""
+    B, n_in = x.shape
+    _chk(x, None, "x"); _chk(filt, torch.float32, "filt"); _chk(y, torch.float32, "y"); _chk(len_in, torch.int32, "len_in")
+    _chk(len_out, torch.int32, "len_out")
+    if x.dtype == torch.int16:
+        dt = 2
+    elif x.dtype == torch.float32:
+        dt = 0
+    else:
+        raise SibError(f"resample: input must be int16 or float32, got {x.dtype}")
+    if x.stride(1) != 1 or y.stride(1) != 1 or not filt.is_contiguous() or filt.shape[1] != up:
+        raise SibError("resample: rows must be dense and filt must be [taps][up]")
+    _emit("sib_resample", (_p(x), dt, B, n_in, x.stride(0), _p(len_in), _p(filt), up, down, filt.shape[0], first, _p(y),
+                           y.shape[1], y.stride(0), _p(len_out)), keep=(x, filt, y, len_in, len_out))
+
+
+def si_sdr(est, ref, out, lengths=None, eps=1.1920929e-07):
+    B, n = est.shape
+    for t, nme in ((est, "est"), (ref, "ref"), (out, "out")):
+        _chk(t, torch.float32, nme)
+    _chk(lengths, torch.int32, "lengths")
+    if not (est.is_contiguous() and ref.is_contiguous()) or ref.shape != est.shape:
+        raise SibError("si_sdr: est / ref must be contiguous [B, n] tensors of the same shape")
+    ws = torch.empty(int(_lib.lib().sib_si_sdr_workspace_bytes(B)), dtype=torch.uint8, device=est.device)
+    _emit("sib_si_sdr_f32", (_p(est), _p(ref), B, n, _p(lengths), eps, _p(out), _p(ws)), keep=(est, ref, out, lengths, ws))
+
+
+def abs_diff_mean(a, b, out):
+    """out[i] = mean |a[i] - b[i]| over everything but the leading axis."""
+    _chk(a, torch.float32, "a"); _chk(b, torch.float32, "b"); _chk(out, torch.float32, "out")
+    if a.shape != b.shape or not (a.is_contiguous() and b.is_contiguous()):
+        raise SibError("abs_diff_mean: operands must be contiguous and of the same shape")
+    B = a.shape[0]
+    ws = torch.empty(int(_lib.lib().sib_abs_diff_workspace_bytes(B)), dtype=torch.uint8, device=a.device)
+    _emit("sib_abs_diff_mean_f32", (_p(a), _p(b), B, a.numel() // B, _p(out), _p(ws)), keep=(a, b, out, ws))

@@ -164,6 +164,54 @@ def test_code_generator_vs_oracle(sib):
         gen(code=code.cuda(), f0=torch.zeros(2, 1, 48), emb=emb.cuda(), spkr=None)
 
 
+def test_f0_quantizer_vs_oracle_and_reference_golden(sib, golden_dir):
+    """frozen f0 VQ-VAE encoder + quantiser (I_da/src/model.py:148-152) - integer output, must be exact."""
+    from oracle import f0vq_ref
+    g = np.load(f"{golden_dir}/f0vq_golden.npz")
+    sd = f0vq_ref.make_params(seed=1234)
+    q = sib.F0Quantizer(f0vq_ref.F0_QUANTIZER).to("cuda")
+    q.load_state_dict(sd)
+    for B, L in ((2, 784), (1, 160)):
+        f0 = torch.randn(B, 1, L, generator=torch.Generator().manual_seed(L))
+        h = q.encode_features(f0.cuda()).cpu()                       # frame-major [B, L/16, 128]
+        assert max_abs(torch.from_numpy(g[f"h_{L}"]).transpose(1, 2), h) < 2e-5
+        z = q.encode(f0.cuda()).cpu()
+        assert z.dtype == torch.int64 and np.array_equal(z.numpy(), g[f"z_{L}"])
+    # a batch the oracle handles in seconds, odd batch size, other seed: bins bit-equal, and batch-invariant
+    sd2 = f0vq_ref.make_params(seed=7, scale=1.5)
+    q.load_state_dict(sd2)
+    f0 = torch.randn(5, 1, 3200, generator=torch.Generator().manual_seed(1))
+    z = q.encode(f0.cuda()).cpu()
+    want = f0vq_ref.f0_to_bins(sd2, f0)
+    assert z.shape == (5, 200) and float((z == want).float().mean()) >= 0.999
+    assert torch.equal(q.encode(f0[3:4].cuda()).cpu(), z[3:4])
+    with pytest.raises(sib.SibError):
+        q.encode(torch.zeros(1, 1, 8).cuda())                         # shorter than one bin
+
+
+def test_code_generator_quantises_f0_itself(sib):
+    """CodeGenerator.forward(code=, f0=, emb=, spkr=) - the reference call (model.py:121-189) without precomputed bins."""
+    from oracle import f0vq_ref, hifigan_ref
+    from oracle.params import HifiCfg, make_generator_params
+    cfg = HifiCfg.tiny(True)
+    params = make_generator_params(cfg, 1234, "unit")
+    fsd = f0vq_ref.make_params(seed=5)
+    h = sib.AttrDict(dict(cfg.as_attrdict(), f0_quantizer=f0vq_ref.F0_QUANTIZER))
+    gen = sib.CodeGenerator(h).to("cuda")
+    gen.load_state_dict(dict(params, **{"fo_vqvae." + k: v for k, v in fsd.items()}))   # checkpoint layout of model.py:63-71
+    g = torch.Generator().manual_seed(2)
+    code = torch.randint(0, cfg.num_embeddings, (2, 12), generator=g)
+    f0 = torch.randn(2, 1, 48, generator=g)
+    emb = torch.randn(2, cfg.embedding_dim, generator=g)
+    zp = f0vq_ref.f0_to_bins(fsd, f0)
+    assert zp.shape == (2, 3)
+    ref = hifigan_ref.code_generator_forward(params, cfg, code, zp, emb)
+    y = gen(code=code.cuda(), f0=f0.cuda(), emb=emb.cuda(), spkr=torch.zeros(2, 1, dtype=torch.long)).cpu()
+    assert y.shape == ref.shape and snr_db(ref, y) > 60
+    y2 = gen(code=code.cuda(), f0_code=zp.cuda(), emb=emb.cuda()).cpu()
+    assert torch.equal(y, y2)
+
+
 def _iea_oracle(params_h, ocfg, gparams, gcfg, C, wave, mel, pos, ln):
     from oracle import glue_ref, hifigan_ref, hubert_ref
     x = wave.clone()

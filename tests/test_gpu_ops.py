@@ -295,3 +295,107 @@ def test_masked_feature_mel_front_end(sib):
     for b in range(2):
         ref = mel_ref.masked_feature_mel(wave[b].numpy(), *ranges[b])
         assert max_abs(ref[0], mel[b].cpu()) < 2e-3 and float((ref[0] - mel[b].cpu()).abs().mean()) < 2e-5
+
+
+def test_device_metrics(sib, golden_dir):
+    """SI-SDR (I_ea/metrics.py:127-141) and mel-L1 reduced on the device vs their CPU restatements."""
+    from oracle import mel_ref, metrics_ref
+    g = torch.Generator().manual_seed(21)
+    ref = 0.3 * torch.randn(3, 22050, generator=g)
+    est = ref * torch.tensor([[1.0], [0.5], [2.0]]) + torch.tensor([[0.01], [0.1], [0.5]]) * torch.randn(3, 22050, generator=g)
+    got = sib.si_sdr(est.cuda(), ref.cuda()).cpu()
+    golden = np.load(f"{golden_dir}/metrics_golden.npz")["sisdr"]   # the reference's own method on these inputs
+    for b in range(3):
+        want = metrics_ref.sisdr(est[b].numpy().astype(np.float64), ref[b].numpy().astype(np.float64))
+        assert abs(want - float(got[b])) < 1e-3 and abs(golden[b] - float(got[b])) < 1e-3, (b, want, float(got[b]))
+    assert got[0] > got[1] > got[2]
+    # ragged lengths == each utterance alone; batch composition does not change a bit (fixed reduction order)
+    lens = [22050, 10000, 333]
+    rag = sib.si_sdr(est.cuda(), ref.cuda(), lengths=lens).cpu()
+    for b, n in enumerate(lens):
+        alone = sib.si_sdr(est[b, :n].cuda(), ref[b, :n].cuda()).cpu()
+        assert float(alone) == float(rag[b])
+        assert abs(float(alone) - metrics_ref.sisdr(est[b, :n].numpy().astype(np.float64), ref[b, :n].numpy().astype(np.float64))) < 1e-3
+    # a perfect estimate saturates at the eps floor like the reference (no inf / nan)
+    assert torch.isfinite(sib.si_sdr(ref.cuda(), ref.cuda())).all()
+    l1 = sib.mel_l1(est.cuda(), ref.cuda())
+    assert abs(l1 - mel_ref.mel_l1(est, ref)) < 1e-4
+    per = sib.mel_l1(est.cuda(), ref.cuda(), per_utterance=True)
+    assert per.shape == (3,) and abs(float(per.double().mean()) - l1) < 1e-9
+    one = sib.mel_l1(est[1:2].cuda(), ref[1:2].cuda(), per_utterance=True)
+    assert float(one[0]) == float(per[1])
+    with pytest.raises(sib.SibError):
+        sib.si_sdr(est, ref)
+
+
+RESAMPLE_CASES = [(16000, 22050), (22050, 16000), (48000, 16000), (24000, 22050), (16000, 16000)]
+
+
+@pytest.mark.parametrize("rates", RESAMPLE_CASES)
+def test_resample_vs_oracle_and_golden(sib, golden_dir, rates):
+    """the poly-phase resampler vs the float64 oracle and the torchaudio-generated golden vectors."""
+    from oracle import resample_ref as R
+    o, n = rates
+    g = np.load(f"{golden_dir}/resample_golden.npz")
+    x = torch.from_numpy(g["x"])
+    y = sib.resample(x.cuda(), o, n).cpu().numpy()
+    want = R.resample(g["x"], o, n)
+    assert y.shape == want.shape and np.abs(y - want).max() < 2e-6
+    if f"y_{o}_{n}" in g:
+        assert np.abs(y - g[f"y_{o}_{n}"]).max() < 2e-6
+    # int16 PCM input (x / 32768 on load) and a ragged, zero-padded batch: every row == that utterance alone
+    pcm = (x * 20000).round().clamp(-32768, 32767).to(torch.int16)
+    lens = [12000, 7001, 1]
+    batch = torch.zeros(3, 12000, dtype=torch.int16)
+    for b, ln in enumerate(lens):
+        batch[b, :ln] = pcm[:ln]
+    yb = sib.resample(batch.cuda(), o, n, lengths=lens).cpu().numpy()
+    for b, ln in enumerate(lens):
+        alone = sib.resample(pcm[:ln].cuda(), o, n).cpu().numpy()
+        m = R.out_length(ln, o, n)
+        assert alone.shape == (m,) and np.array_equal(yb[b, :m], alone) and not yb[b, m:].any()
+        ref = R.resample(R.pcm16_to_float(pcm[:ln].numpy()), o, n)
+        assert np.abs(alone - ref).max() < 2e-6
+
+
+def test_resample_long_batch_property(sib):
+    """BASELINE-size property (32 x 4 s): 16 k -> 22.05 k -> 16 k returns the band-limited input; a constant stays put."""
+    g = torch.Generator().manual_seed(4)
+    t = torch.arange(64000) / 16000.0
+    fade = torch.ones(64000)
+    fade[:4000] = torch.hann_window(8000, periodic=False)[:4000]
+    fade[-4000:] = torch.hann_window(8000, periodic=False)[4000:]
+    x = torch.stack([0.3 * torch.sin(2 * math.pi * (200.0 + 150.0 * b) * t + b) for b in range(32)]) * fade   # <= 4.85 kHz
+    up = sib.resample(x.cuda(), 16000, 22050)
+    assert up.shape == (32, 88200)
+    back = sib.resample(up, 22050, 16000).cpu()
+    assert back.shape == (32, 64000)
+    assert float((back - x).abs().max()) < 5e-4   # pass-band gain error of two 64-crossing Kaiser filters (oracle: 1.8e-4 at 4.85 kHz)
+    ones = sib.resample(torch.ones(1, 8000).cuda(), 16000, 22050).cpu()
+    assert float((ones[0, 300:-300] - 1.0).abs().max()) < 1e-4
+
+
+def test_load_wav_batch(sib, tmp_path):
+    """The librosa.load(sr=22050) / librosa.load(sr=16000) pair (I_ea/predict.py:79-80) for a batch of files."""
+    from oracle import resample_ref as R
+    rng = np.random.default_rng(3)
+    files, pcms = [], []
+    for i, (n, sr) in enumerate([(9000, 22050), (7000, 22050), (5000, 16000)]):
+        pcm = (rng.standard_normal(n) * 4000).astype(np.int16)
+        sib.write_wav(tmp_path / f"u{i}.wav", pcm, sr)
+        files.append(tmp_path / f"u{i}.wav")
+        pcms.append((pcm, sr))
+    out = sib.load_wav_batch(files[:2])                      # same source rate: one launch per target rate
+    for sr in (16000, 22050):
+        wave, lens = out[sr]
+        assert wave.is_cuda and lens.tolist() == [R.out_length(p.shape[0], s, sr) for p, s in pcms[:2]]
+        for b, (p, s) in enumerate(pcms[:2]):
+            ref = R.resample(R.pcm16_to_float(p), s, sr)
+            got = wave[b].cpu().numpy()
+            assert np.abs(got[:len(ref)] - ref).max() < 2e-6 and not got[len(ref):].any()
+    mixed = sib.load_wav_batch(files, target_srs=(16000,))   # mixed source rates
+    wave, lens = mixed[16000]
+    for b, (p, s) in enumerate(pcms):
+        ref = R.resample(R.pcm16_to_float(p), s, 16000)
+        assert np.abs(wave[b, :len(ref)].cpu().numpy() - ref).max() < 2e-6
+    assert lens.tolist()[2] == 5000 and np.array_equal(wave[2, :5000].cpu().numpy(), pcms[2][0].astype(np.float32) / 32768)
