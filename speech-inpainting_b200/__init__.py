@@ -13,7 +13,7 @@ from .f0vq import F0Quantizer  # noqa: F401
 from .mel import mel_spectrogram, get_mel, mel_l1, si_sdr, mel_filterbank, masked_feature_mel  # noqa: F401
 from .audio import resample, resample_filter, read_wav, write_wav, load_wav_batch  # noqa: F401
 from .inpaint import (InformedInpainter, BlindInpainter, iea_mask_indices, iea_zero_range, extend_mel,  # noqa: F401
-                      shard_batch, ida_matched_frames)
+                      shard_batch, ida_matched_frames, predict_files)
 from . import ops  # noqa: F401
 
 __version__ = "0.1.0"

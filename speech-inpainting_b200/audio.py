@@ -162,7 +162,7 @@ def load_wav_batch(paths, target_srs=(16000, 22050), device=None):
     stage = torch.zeros(B, n_max, dtype=torch.int16 if mono16 else torch.float32).pin_memory()
     for i, (pcm, _) in enumerate(files):
         if mono16:
-            stage[i, :pcm.shape[0]] = torch.from_numpy(np.ascontiguousarray(pcm[:, 0]))
+            stage[i, :pcm.shape[0]] = torch.from_numpy(np.array(pcm[:, 0]))
         else:   # librosa.to_mono: mean over channels of the float signal
             stage[i, :pcm.shape[0]] = torch.from_numpy((pcm.astype(np.float32) / 32768.0).mean(axis=1))
     dev = stage.to(device, non_blocking=True)

@@ -205,3 +205,45 @@ class BlindInpainter:
             res.int16 = torch.empty(wav_inp.shape, dtype=torch.int16, device=dev)
             ops.pack_int16(wav_inp, res.int16)
         return res
+
+
+def predict_files(pipe: InformedInpainter, wave_paths, start_sec: float, end_sec: float, save_dir=None):
+    """`predict(...)` of I_ea/predict.py:66-207 from wave files to wave files, for a batch of utterances:
+    `librosa.load(path, sr=22050)` + `librosa.load(path, sr=16000)` (:79-80) through the device resampler, the host
+    integer mask arithmetic (:85-90, 99-100), the 22 kHz feature front-end (:99-104), the informed pipeline (:133-203)
+    and the int16 conversion (:204-206).  Files are grouped by sample count; every group is one batched pass.
+    With `save_dir`, `<save_dir>/<stem>/{masked,inpainted}.wav` are written (:134, :207; 16 kHz / 22.05 kHz PCM-16).
+
+    Returns a list (in the order of `wave_paths`) of namespaces(int16 [S], labels, mask_pos, mask_len)."""
+    import os
+    from .audio import load_wav_batch, write_wav
+    paths = [os.fspath(p) for p in wave_paths]
+    idx = iea_mask_indices(start_sec, end_sec)
+    both = load_wav_batch(paths, (16000, 22050), pipe.device)
+    (w16, n16), (w22, n22) = both[16000], both[22050]
+    results = [None] * len(paths)
+    shapes = list(zip(n16.tolist(), n22.tolist()))
+    for n, s22 in sorted(set(shapes)):
+        rows = [i for i, v in enumerate(shapes) if v == (n, s22)]
+        x16 = w16[rows, :n].contiguous()
+        x22 = w22[rows, :s22].contiguous()
+        res = pipe(x16, None, idx["mask_pos"], idx["mask_len"], wave22=x22, zero22=[idx["zero22"]] * len(rows),
+                   return_int16=True)
+        masked16 = None
+        if save_dir is not None:
+            lo, hi = idx["zero16"]
+            m = x16.clone()
+            ops.zero_ranges(m, _i32([lo] * len(rows), pipe.device), _i32([hi] * len(rows), pipe.device))
+            masked16 = torch.empty(m.shape, dtype=torch.int16, device=pipe.device)
+            ops.pack_int16(m, masked16)
+        L = idx["mask_len"]
+        pcm = res.int16.reshape(len(rows), -1).cpu()
+        for j, i in enumerate(rows):
+            results[i] = SimpleNamespace(int16=pcm[j], labels=res.labels[j * L:(j + 1) * L].cpu(), mask_pos=idx["mask_pos"],
+                                         mask_len=L)
+            if save_dir is not None:
+                out = os.path.join(os.fspath(save_dir), os.path.splitext(os.path.basename(paths[i]))[0])
+                os.makedirs(out, exist_ok=True)
+                write_wav(os.path.join(out, "masked.wav"), masked16[j].cpu(), 16000)
+                write_wav(os.path.join(out, "inpainted.wav"), pcm[j], 22050)
+    return results

@@ -381,3 +381,41 @@ def test_informed_inpainting_from_wave22(sib):
     assert snr_db(res2.wave.cpu(), res.wave.cpu()) > 60
     with pytest.raises(sib.SibError, match="mel or wave22"):
         pipe(wave16, None, pos, ln)
+
+
+def test_predict_files_wav_to_wav(sib, tmp_path):
+    """I_ea/predict.py:66-207 from files to files (SURVEY 8f rows 1 + 3): wav -> device resampler -> feature mel ->
+    informed pipeline -> inpainted.wav; equals the pipeline fed with the oracle's resampled signals."""
+    from oracle import glue_ref, resample_ref as R
+    from oracle.params import HifiCfg, HubertCfg, make_codebook, make_generator_params, make_head_params, make_hubert_params
+    ocfg, gcfg = HubertCfg.tiny(False), HifiCfg.tiny()
+    sd = make_hubert_params(ocfg, 1234, prefix="base_model.")
+    sd.update(make_head_params(ocfg.hidden_size, 80))
+    model = sib.CustomModel(80, "base", False, config=_hub_cfg(sib, ocfg)).to("cuda")
+    model.load_state_dict(sd)
+    gen = sib.Generator(sib.AttrDict(gcfg.as_attrdict())).to("cuda")
+    gen.load_state_dict(make_generator_params(gcfg, 1234, "unit"))
+    pipe = sib.InformedInpainter(model, gen, make_codebook(80, 100))
+    rng = np.random.default_rng(11)
+    t = np.arange(44100) / 22050.0
+    files, pcms = [], []
+    for i, n in enumerate((44100, 44100, 33075)):     # two utterances of 2 s and one of 1.5 s, 22.05 kHz PCM-16 on disk
+        pcm = (3000 * np.sin(2 * np.pi * (180 + 40 * i) * t[:n]) + 800 * rng.standard_normal(n)).astype(np.int16)
+        sib.write_wav(tmp_path / f"utt{i}.wav", pcm, 22050)
+        files.append(tmp_path / f"utt{i}.wav")
+        pcms.append(pcm)
+    out = sib.predict_files(pipe, files, 0.5, 0.7, save_dir=tmp_path / "pred")
+    idx = glue_ref.iea_mask_indices(0.5, 0.7)
+    for i, pcm in enumerate(pcms):
+        w22 = R.pcm16_to_float(pcm)
+        w16 = R.resample(w22, 22050, 16000)
+        ref = pipe(torch.from_numpy(w16.astype(np.float32))[None], None, idx["mask_pos"], idx["mask_len"],
+                   wave22=torch.from_numpy(w22.astype(np.float32))[None], zero22=[idx["zero22"]], return_int16=True)
+        assert torch.equal(out[i].labels, ref.labels.cpu())
+        a, b = out[i].int16.float(), ref.int16.reshape(-1).cpu().float()
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 2          # resampler rounding (2e-6) -> <= 2 LSB
+        back, sr = sib.read_wav(tmp_path / "pred" / f"utt{i}" / "inpainted.wav")
+        assert sr == 22050 and np.array_equal(back[:, 0], out[i].int16.numpy())
+        masked, sr = sib.read_wav(tmp_path / "pred" / f"utt{i}" / "masked.wav")
+        lo, hi = idx["zero16"]
+        assert sr == 16000 and not masked[lo:hi].any() and masked[:lo].any() and masked.shape[0] == len(w16)
