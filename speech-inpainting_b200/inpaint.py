@@ -63,7 +63,52 @@ def ida_matched_frames(n_samples: int, n_code: int, n_f0: int, hop: int = 320) -
 
 
 def _i32(v, dev):
-    return torch.as_tensor(v, dtype=torch.int32).to(dev)
+    return _i32_many([v], dev)[0]
+
+
+class _PinnedRing:
+    """Small ring of pinned int32 staging buffers: index vectors (mask positions / lengths / offsets / zero ranges) go to
+    the device with ONE non-blocking copy per call.  A pageable-memory copy would block the host until everything queued
+    before it on the stream has finished, i.e. stall the launch loop once per step."""
+
+    def __init__(self, slots: int = 8):
+        self.bufs, self.events, self.i = [None] * slots, [None] * slots, 0
+
+    def upload(self, flat: torch.Tensor, dev):
+        k = self.i % len(self.bufs)
+        self.i += 1
+        if self.events[k] is not None:
+            self.events[k].synchronize()       # copy issued `slots` uploads ago: long finished
+        if self.bufs[k] is None or self.bufs[k].numel() < flat.numel():
+            self.bufs[k] = torch.empty(max(1024, flat.numel()), dtype=torch.int32).pin_memory()
+        host = self.bufs[k][: flat.numel()]
+        host.copy_(flat)
+        out = torch.empty(flat.numel(), dtype=torch.int32, device=dev)
+        out.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+        return out
+
+
+_rings = {}
+
+
+def _i32_many(rows, dev):
+    """Python int sequences -> int32 device vectors, one pinned, non-blocking upload for all of them."""
+    dev = torch.device(dev)
+    if dev.type != "cuda":
+        raise SibError("index vectors must go to a CUDA device (no CPU fallback)")
+    flat = torch.as_tensor([int(v) for r in rows for v in r], dtype=torch.int32)
+    ring = _rings.setdefault((dev.index, torch.cuda.current_stream(dev).cuda_stream), _PinnedRing())
+    if flat.numel() == 0:
+        return [torch.empty(0, dtype=torch.int32, device=dev) for _ in rows]
+    d = ring.upload(flat, dev)
+    out, o = [], 0
+    for r in rows:
+        out.append(d[o:o + len(r)])
+        o += len(r)
+    return out
 
 
 class InformedInpainter:
@@ -100,24 +145,24 @@ class InformedInpainter:
             raise SibError("mask_pos / mask_len must have one entry per utterance")
         x = wave16.to(dev, torch.float32, non_blocking=True).clone() if wave16.is_cuda else wave16.to(dev, torch.float32, non_blocking=True)
         x = x.contiguous()
-        if apply_mask:  # predict.py:133
-            rng = [iea_zero_range(p, l) for p, l in zip(pos, ln)]
-            ops.zero_ranges(x, _i32([r[0] for r in rng], dev), _i32([r[1] for r in rng], dev))
-        if normalize:   # predict.py:136-141 (processor: do_normalize=True, eps 1e-7)
-            lengths = None if attention_mask is None else attention_mask.sum(-1).to(dev, torch.int32)
-            xn = torch.empty_like(x)
-            ops.znorm(x, xn, lengths, 1e-7)
-            x = xn
         off, acc = [], 0
         for l in ln:
             off.append(acc)
             acc += l
         M = acc
+        rng = [iea_zero_range(p, l) for p, l in zip(pos, ln)]
+        pos_t, len_t, off_t, lo_t, hi_t = _i32_many([pos, ln, off, [r[0] for r in rng], [r[1] for r in rng]], dev)
+        if apply_mask:  # predict.py:133
+            ops.zero_ranges(x, lo_t, hi_t)
+        if normalize:   # predict.py:136-141 (processor: do_normalize=True, eps 1e-7)
+            lengths = None if attention_mask is None else attention_mask.sum(-1).to(dev, torch.int32)
+            xn = torch.empty_like(x)
+            ops.znorm(x, xn, lengths, 1e-7)
+            x = xn
         T = self.model.base_model.config.feat_extract_output_length(N)
         for p, l in zip(pos, ln):
             if p < 0 or l < 0 or p + l > T:
                 raise SibError(f"mask frames [{p},{p + l}) outside the {T} encoder frames")
-        pos_t, len_t, off_t = _i32(pos, dev), _i32(ln, dev), _i32(off, dev)
         # predict.py:163-168: outputs = model(inputs)[b, pos:pos+L]; the head (LayerNorm + Linear) is row-wise, so it is
         # evaluated on the gathered frames only (bit-identical rows, sum(L) of them instead of B*T)
         values, _ = self.model.forward_frames(x, attention_mask, pos_t, len_t, off_t, M)
@@ -135,6 +180,66 @@ class InformedInpainter:
             res.int16 = torch.empty(y.shape, dtype=torch.int16, device=dev)
             ops.pack_int16(y, res.int16)
         return res
+
+
+    def stream(self, batches, depth: int = 2):
+        """Pipelined serving loop over an iterable of HOST batches (pinned memory recommended) - the micro-batch executor
+        BASELINE config 5 needs (1024 x 10 s does not fit one pass): while batch i computes on the current stream, a copy
+        stream uploads batch i+1 into one of `depth` device slots and a third one downloads the int16 result of batch i-1.
+
+        Each batch is a dict(wave16=[B,N] f32, mel=[B,80,T'] f32, mask_pos=, mask_len=) (same meaning as `__call__`).
+        Yields, in order, namespace(int16 = pinned host [B,1,S] int16, labels = host int64) once that batch's download has
+        completed; the host buffers are recycled after `depth` further batches."""
+        from collections import deque
+        dev = self.device
+        compute = torch.cuda.current_stream(dev)
+        # separate upload and download streams: in one in-order copy stream the upload of batch i+1 would queue behind the
+        # download of batch i, which waits for compute i - no overlap at all
+        copy, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        slots, hosts, pending = [None] * depth, [None] * (depth + 1), deque()
+
+        def finish(item):
+            fin, res, h_pcm, h_lab = item
+            fin.synchronize()
+            return SimpleNamespace(int16=h_pcm, labels=h_lab, device_result=res)
+
+        for i, b in enumerate(batches):
+            wave, mel = b["wave16"], b["mel"]
+            sl = slots[i % depth]
+            if sl is None or sl.wave.shape != wave.shape or sl.mel.shape != mel.shape:
+                sl = slots[i % depth] = SimpleNamespace(wave=torch.empty(wave.shape, device=dev, dtype=torch.float32),
+                                                        mel=torch.empty(mel.shape, device=dev, dtype=torch.float32), free=None)
+                # the allocator may hand out memory that earlier work on the compute stream is still using: order the
+                # first upload into a fresh slot after everything queued there so far
+                sl.free = torch.cuda.Event()
+                sl.free.record(compute)
+            with torch.cuda.stream(copy):
+                if sl.free is not None:
+                    copy.wait_event(sl.free)          # the compute that last read this slot has finished
+                sl.wave.copy_(wave, non_blocking=True)
+                sl.mel.copy_(mel, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            compute.wait_event(ready)
+            res = self(sl.wave, sl.mel, b["mask_pos"], b["mask_len"], return_int16=True)
+            done = torch.cuda.Event()
+            done.record(compute)
+            sl.free = done
+            hb = hosts[i % (depth + 1)]
+            if hb is None or hb[0].shape != res.int16.shape or hb[1].shape != res.labels.shape:
+                hb = hosts[i % (depth + 1)] = (torch.empty(res.int16.shape, dtype=torch.int16).pin_memory(),
+                                               torch.empty(res.labels.shape, dtype=torch.int64).pin_memory())
+            with torch.cuda.stream(down):
+                down.wait_event(done)
+                hb[0].copy_(res.int16, non_blocking=True)
+                hb[1].copy_(res.labels, non_blocking=True)
+                fin = torch.cuda.Event()
+                fin.record(down)
+            pending.append((fin, res, hb[0], hb[1]))   # `res` keeps the device buffers alive until the download is done
+            while len(pending) >= depth:
+                yield finish(pending.popleft())
+        while pending:
+            yield finish(pending.popleft())
 
 
 class BlindInpainter:

@@ -419,3 +419,31 @@ def test_predict_files_wav_to_wav(sib, tmp_path):
         masked, sr = sib.read_wav(tmp_path / "pred" / f"utt{i}" / "masked.wav")
         lo, hi = idx["zero16"]
         assert sr == 16000 and not masked[lo:hi].any() and masked[:lo].any() and masked.shape[0] == len(w16)
+
+
+def test_stream_pipeline_matches_direct_calls(sib):
+    """InformedInpainter.stream (upload / compute / download overlapped over `depth` slots) returns, in order, exactly
+    what one direct call per batch returns - including when slots and host buffers are recycled."""
+    from oracle.params import HifiCfg, HubertCfg, make_codebook, make_generator_params, make_head_params, make_hubert_params
+    ocfg, gcfg = HubertCfg.tiny(False), HifiCfg.tiny()
+    sd = make_hubert_params(ocfg, 1234, prefix="base_model.")
+    sd.update(make_head_params(ocfg.hidden_size, 80))
+    model = sib.CustomModel(80, "base", False, config=_hub_cfg(sib, ocfg)).to("cuda")
+    model.load_state_dict(sd)
+    gen = sib.Generator(sib.AttrDict(gcfg.as_attrdict())).to("cuda")
+    gen.load_state_dict(make_generator_params(gcfg, 1234, "unit"))
+    pipe = sib.InformedInpainter(model, gen, make_codebook(80, 100))
+    g = torch.Generator().manual_seed(8)
+    batches = []
+    for i in range(5):
+        batches.append({"wave16": (0.1 * torch.randn(3, 16000, generator=g)).pin_memory(),
+                        "mel": torch.randn(3, 80, 50, generator=g).pin_memory(),
+                        "mask_pos": [5 + i, 20, 31], "mask_len": [10, 3 + i, 0]})
+    direct = [pipe(b["wave16"], b["mel"], b["mask_pos"], b["mask_len"], return_int16=True) for b in batches]
+    direct = [(r.int16.cpu().clone(), r.labels.cpu().clone()) for r in direct]
+    for depth in (1, 2, 3):
+        n = 0
+        for out, (pcm, lab) in zip(pipe.stream(iter(batches), depth=depth), direct):
+            assert torch.equal(out.int16, pcm) and torch.equal(out.labels, lab)   # checked before the buffers are recycled
+            n += 1
+        assert n == len(batches)
