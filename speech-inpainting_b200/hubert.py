@@ -9,6 +9,8 @@ All arithmetic runs in libsib_b200.so; there is no PyTorch fallback.
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from types import SimpleNamespace
 
@@ -159,6 +161,10 @@ class HubertModel(_StateHolder):
         self._prefix = key_prefix
         self._plans = {}
         self.use_cuda_graph = False
+        # independent half-batch chains through the transformer stack (ops.Plan.chain).  Measured on B200 at 32 x 4 s: two chains
+        # 11.15-11.33 ms per step against 10.97-11.04 for one (the persistent GEMMs own every SM, so the second chain only
+        # adds smaller, less efficient tiles) - kept as an A/B switch, off by default
+        self.transformer_chains = int(os.environ.get("SIB_HUBERT_CHAINS", "1")) if precision == "bf16" else 1
 
     # ---- state
     def _expected_keys(self):
@@ -288,29 +294,21 @@ class HubertModel(_StateHolder):
             att = torch.empty(B, T, H, **f32)
             ff = torch.empty(B, T, cfg.intermediate_size, **f32)
             nrm = torch.empty(B, T, H, **f32)
-            M = B * T
-            for l in range(n_layers):
-                b = f"encoder.layers.{l}."
-                ob, f2b = self._w(b + "attention.out_proj.bias"), self._w(b + "feed_forward.output_dense.bias")
-                f1b = self._w(b + "feed_forward.intermediate_dense.bias")
-                ln1 = (self._w(b + "layer_norm.weight"), self._w(b + "layer_norm.bias"))
-                ln2 = (self._w(b + "final_layer_norm.weight"), self._w(b + "final_layer_norm.bias"))
-                if cfg.do_stable_layer_norm:  # HF:525-548
-                    ops.layernorm(h, ln1[0], ln1[1], nrm, eps)
-                    ops.linear(nrm.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
-                    ops.attention(qkv, io.key_len, att, cfg.num_attention_heads)
-                    ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, h.view(M, H), residual=h.view(M, H))
-                    ops.layernorm(h, ln2[0], ln2[1], nrm, eps)
-                    ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
-                    ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, h.view(M, H), residual=h.view(M, H))
-                else:  # HF:388-405
-                    ops.linear(h.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
-                    ops.attention(qkv, io.key_len, att, cfg.num_attention_heads)
-                    ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, tmp.view(M, H))
-                    ops.layernorm(tmp, ln1[0], ln1[1], nrm, eps, residual=h)
-                    ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
-                    ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, tmp.view(M, H))
-                    ops.layernorm(tmp, ln2[0], ln2[1], h, eps, residual=nrm)
+            # Two independent half-batch chains through the transformer stack (every op is row- or utterance-wise): the
+            # GEMMs of 32 x 199 frames are 1.0 - 4.1 waves of tiles, so a single chain leaves most SMs idle during each
+            # kernel's last wave; the other chain's kernel fills them (ops.Plan.chain).  Same buffers, disjoint row ranges.
+            halves = [(0, B)]
+            if self.transformer_chains > 1 and B >= 2 * self.transformer_chains and not padded:
+                nc = self.transformer_chains
+                halves = [(B * c // nc, B * (c + 1) // nc) for c in range(nc)]
+                plan.fork()
+            for l in range(n_layers):   # layer-major order: the host feeds both streams alternately
+                for c, (b0, b1) in enumerate(halves):
+                    with plan.chain(c):
+                        self._record_layer(l, P, h[b0:b1], qkv[b0:b1], att[b0:b1], ff[b0:b1], nrm[b0:b1], tmp[b0:b1],
+                                           None if io.key_len is None else io.key_len[b0:b1], eps)
+            if len(halves) > 1:
+                plan.join()
             if cfg.do_stable_layer_norm and n_layers == cfg.num_hidden_layers:
                 ops.layernorm(h, self._w("encoder.layer_norm.weight"), self._w("encoder.layer_norm.bias"), h, eps)  # HF:613
             if bf16:
@@ -323,6 +321,34 @@ class HubertModel(_StateHolder):
         if self.use_cuda_graph:
             plan.capture()
         return io
+
+    def _record_layer(self, l, P, h, qkv, att, ff, nrm, tmp, key_len, eps):
+        """Transformer layer l (HF:388-405 post-LN / HF:525-548 pre-LN) on a contiguous batch range of the plan's buffers."""
+        cfg = self.config
+        Bc, T, H = h.shape
+        M = Bc * T
+        if True:
+            b = f"encoder.layers.{l}."
+            ob, f2b = self._w(b + "attention.out_proj.bias"), self._w(b + "feed_forward.output_dense.bias")
+            f1b = self._w(b + "feed_forward.intermediate_dense.bias")
+            ln1 = (self._w(b + "layer_norm.weight"), self._w(b + "layer_norm.bias"))
+            ln2 = (self._w(b + "final_layer_norm.weight"), self._w(b + "final_layer_norm.bias"))
+            if cfg.do_stable_layer_norm:  # HF:525-548
+                ops.layernorm(h, ln1[0], ln1[1], nrm, eps)
+                ops.linear(nrm.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
+                ops.attention(qkv, key_len, att, cfg.num_attention_heads)
+                ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, h.view(M, H), residual=h.view(M, H))
+                ops.layernorm(h, ln2[0], ln2[1], nrm, eps)
+                ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
+                ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, h.view(M, H), residual=h.view(M, H))
+            else:  # HF:388-405
+                ops.linear(h.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
+                ops.attention(qkv, key_len, att, cfg.num_attention_heads)
+                ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, tmp.view(M, H))
+                ops.layernorm(tmp, ln1[0], ln1[1], nrm, eps, residual=h)
+                ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
+                ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, tmp.view(M, H))
+                ops.layernorm(tmp, ln2[0], ln2[1], h, eps, residual=nrm)
 
     def _key_len(self, attention_mask, N):
         """HF:690-700: valid frames per utterance from the sample-level attention mask."""

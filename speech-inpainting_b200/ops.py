@@ -46,12 +46,22 @@ def _dt(t):
 
 
 class Plan:
-    """Recorded launch list of one forward pass over static buffers."""
+    """Recorded launch list of one forward pass over static buffers.
+
+    Steps may be tagged with a chain id (`with plan.chain(c):`).  Chain 0 runs on the caller's stream, chain c > 0 on a side
+    stream of the plan; `fork()` / `join()` mark where the side chains branch off and come back (events, no host sync).
+    Independent chains - e.g. the two half-batches of the transformer stack - let the tail of one kernel (a partial last
+    wave of tiles) overlap the head of the other chain's kernel instead of leaving SMs idle."""
 
     def __init__(self):
         self.steps = []   # (cfunc, args-without-stream, name)
+        self.chains = []  # chain id per step
+        self.marks = {}   # step index -> list of "fork" / "join" executed before that step
         self.keep = []    # tensors / descs that must outlive the plan
         self.graph = None
+        self._chain = 0
+        self._side = {}   # chain id -> torch.cuda.Stream
+        self._n_chains = 1
 
     @contextlib.contextmanager
     def record(self):
@@ -62,40 +72,104 @@ class Plan:
         finally:
             _active_plan = prev
 
+    @contextlib.contextmanager
+    def chain(self, c: int):
+        prev, self._chain = self._chain, c
+        self._n_chains = max(self._n_chains, c + 1)
+        try:
+            yield self
+        finally:
+            self._chain = prev
+
+    def fork(self):
+        self.marks.setdefault(len(self.steps), []).append("fork")
+
+    def join(self):
+        self.marks.setdefault(len(self.steps), []).append("join")
+
+    def _launch_all(self, multi_stream: bool):
+        main = torch.cuda.current_stream()
+        s_main = main.cuda_stream
+        if not multi_stream or self._n_chains == 1:
+            for fn, args, name in self.steps:
+                rc = fn(*args, s_main)
+                if rc:
+                    _lib.check(rc, name)
+            return
+        for c in range(1, self._n_chains):
+            if c not in self._side:
+                self._side[c] = torch.cuda.Stream(main.device)
+        handles = {0: s_main, **{c: st.cuda_stream for c, st in self._side.items()}}
+        for i, ((fn, args, name), c) in enumerate(zip(self.steps, self.chains)):
+            for m in self.marks.get(i, ()):
+                if m == "fork":
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    for st in self._side.values():
+                        st.wait_event(ev)
+                else:
+                    for st in self._side.values():
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        main.wait_event(ev)
+            rc = fn(*args, handles[c])
+            if rc:
+                _lib.check(rc, name)
+        for m in self.marks.get(len(self.steps), ()):   # a join after the last step
+            if m == "join":
+                for st in self._side.values():
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    main.wait_event(ev)
+
     def run(self):
         if self.graph is not None:
             self.graph.replay()
             return
-        s = _stream()
-        for fn, args, name in self.steps:
-            rc = fn(*args, s)
-            if rc:
-                _lib.check(rc, name)
+        self._launch_all(multi_stream=_multi_chain_enabled())
 
     def capture(self):
-        """Capture the launch list into a CUDA graph (launch-bound inner loops, one replay per forward)."""
+        """Capture the launch list into a CUDA graph (launch-bound inner loops, one replay per forward); chains are
+        serialised into the capturing stream."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            self.run()  # warm-up outside capture (sets func attributes)
+            self._launch_all(multi_stream=False)  # warm-up outside capture (sets func attributes)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            s = _stream()
-            for fn, args, name in self.steps:
-                rc = fn(*args, s)
-                if rc:
-                    _lib.check(rc, name)
+            self._launch_all(multi_stream=False)
         self.graph = g
 
     def __len__(self):
         return len(self.steps)
 
 
+_chains_on = None
+
+
+def _multi_chain_enabled() -> bool:
+    global _chains_on
+    if _chains_on is None:
+        import os
+        _chains_on = os.environ.get("SIB_CHAINS", "1") != "0"
+    return _chains_on
+
+
+def set_multi_chain(enabled: bool) -> bool:
+    """Run independent plan chains on separate streams (default) or serialise them on the caller's stream (A/B switch,
+    also SIB_CHAINS=0).  Returns the previous setting."""
+    global _chains_on
+    prev = _multi_chain_enabled()
+    _chains_on = bool(enabled)
+    return prev
+
+
 def _emit(name, args, keep=()):
     fn = getattr(_lib.lib(), name)
     if _active_plan is not None:
         _active_plan.steps.append((fn, args, name))
+        _active_plan.chains.append(_active_plan._chain)
         _active_plan.keep.extend(keep)
         return
     rc = fn(*args, _stream())
