@@ -189,7 +189,9 @@ size_t sib_abs_diff_workspace_bytes(int batch);
 
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core path (tcgen05 + TMA), see DESIGN.md.  Same contract as sib_conv1d_f32 with
- * bf16 x / w / y / residual, fp32 bias and accumulation, no pre-activation (producers write y_act instead).
+ * bf16 x / w / y / residual, fp32 bias and accumulation.  Pre-activation: leaky-relu only (slope in (0, 1]) and only when
+ * the kernel runs in its halo mode (stride 1, > 1 evenly spaced taps): the landed A tile is activated in place in shared
+ * memory; sib_conv1d_bf16_pre_act_supported() tells - otherwise producers write the activated tensor (y_act) instead.
  * w layout: [groups][c_in/g / cc][n_taps][c_out/g][cc] - one K-major slab per (channel chunk, tap); cc from
  * sib_conv1d_bf16_kblock.
  * Requires c_in/groups % 16 == 0, c_out/groups % 8 == 0.  stride > 1: valid convolution, groups = 1, dense rows, and
@@ -214,6 +216,7 @@ typedef struct sib_resunit_desc {
 int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const void* w1, const float* b1, const void* w2,
                      const float* b2, void* y, void* y_act /* nullable */, sib_stream_t stream);
 int sib_resunit_bf16_supported(int c, int k, int dilation, int accumulate, int has_y_act);
+int sib_conv1d_bf16_pre_act_supported(const sib_conv_desc* d);
 
 /* K-block geometry the kernel uses for c_in/groups: cc channels x tb taps per pipeline stage (cc*tb = 64). */
 int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb);

@@ -24,6 +24,12 @@ SHAPES = {
     "s2k3c1": (32, 22016, 128, 128, 3, 1, 1, False, False),
     "s2k3c2": (32, 22016, 128, 128, 3, 1, 1, True, True),
     "s2k11c2": (32, 22016, 128, 128, 11, 5, 1, True, True),
+    "s2k3c2n": (32, 22016, 128, 128, 3, 1, 1, True, False),     # second conv of a unit whose consumer activates its own input
+    "s2k7c2n": (32, 22016, 128, 128, 7, 1, 1, True, False),
+    "s2k11c2n": (32, 22016, 128, 128, 11, 1, 1, True, False),
+    "s1k3c2n": (32, 2752, 256, 256, 3, 1, 1, True, False),
+    "s1k7c2n": (32, 2752, 256, 256, 7, 1, 1, True, False),
+    "s1k11c2n": (32, 2752, 256, 256, 11, 1, 1, True, False),
     "s3k3c1": (32, 44032, 64, 64, 3, 1, 1, False, False),
     "s3k7c2": (32, 44032, 64, 64, 7, 3, 1, True, True),
     "s3k11c1": (32, 44032, 64, 64, 11, 5, 1, False, False),

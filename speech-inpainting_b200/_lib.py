@@ -81,6 +81,7 @@ _SIGS = {
     "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16": ([C.POINTER(ResUnitDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16_supported": ([_I, _I, _I, _I, _I], _I),
+    "sib_conv1d_bf16_pre_act_supported": ([C.POINTER(ConvDesc)], _I),
     "sib_conv1d_bf16_kblock": ([_I, C.POINTER(C.c_int), C.POINTER(C.c_int)], _I),
     "sib_layernorm": ([_P, _I, _P, _I, _P, _P, _P, _I, _L, _I, _F, _I, _P], _I),
     "sib_attention": ([_P, _I, _P, _P, _I, _I, _I, _I, _P], _I),

@@ -35,6 +35,10 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;                 // two per TMEM lane quarter: latency hiding in the epilogue
 constexpr int EPI_WARP0 = 4;                     // warps 0-3: A producer, MMA issuer, B producer, spare
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
+// CTA-pair kernels run one CTA per SM: room for four more warps that help warp 3 with the in-place pre-activation of the
+// A tiles (one warp alone paced the tensor-bound k = 7 / 11 convs); single-CTA kernels keep two CTAs per SM and one warp.
+constexpr int PAIR_ACT_WARP0 = EPI_WARP0 + NUM_EPI_WARPS, PAIR_EXTRA_ACT_WARPS = 4;
+constexpr int NUM_THREADS_PAIR = NUM_THREADS + 32 * PAIR_EXTRA_ACT_WARPS;
 
 struct TcArgs {
   // epilogue
@@ -63,6 +67,8 @@ struct TcArgs {
   int a_sub_bytes, b_sub_bytes;  // bytes of one (tap) sub-tile of A / B inside a stage
   uint32_t desc_hi;              // SBO / version / swizzle bits of the smem matrix descriptor (bits 32..63)
   uint32_t idesc;
+  int pre_act;                   // halo mode: leaky-relu(pre_slope) applied in place to every landed A tile (warp 3)
+  float pre_slope;
   int tap_row[SIB_MAX_TAPS];     // row coordinate delta per tap
   int tap_ch[SIB_MAX_TAPS];      // channel coordinate delta per tap (stride-s view)
 };
@@ -116,7 +122,7 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 // read both shared memories and write both TMEMs.  Per CTA the B bytes (TMA writes, L2 traffic, MMA operand reads)
 // halve, and with half the columns per CTA twice as many weight sets stay resident.
 template <int POST_ACT, bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS, PAIR ? 1 : 2)
+__global__ void __launch_bounds__(PAIR ? NUM_THREADS_PAIR : NUM_THREADS, PAIR ? 1 : 2)
 conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y2,
                       const __grid_constant__ CUtensorMap map_r, const __grid_constant__ TcArgs p) {
@@ -133,7 +139,8 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint64_t* tmem_full_bar = b_empty + MAX_B_STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint64_t* res_bar = tmem_empty_bar + 2;            // [4 pairs][MAX_NB]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4 * MAX_NB);
+  uint64_t* a_act = res_bar + 4 * MAX_NB;            // [MAX_A_STAGES] A tile activated (pre_act only)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_act + MAX_A_STAGES);
 
   // warp index through a shuffle: the compiler then knows that every role branch below is warp-uniform
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -145,6 +152,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     for (int s = 0; s < MAX_A_STAGES; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
+      mbar_init(&a_act[s], PAIR ? 2 * (1 + PAIR_EXTRA_ACT_WARPS) : 1);   // one arrive per activation warp (of both CTAs)
     }
     for (int s = 0; s < MAX_B_STAGES; ++s) {
       mbar_init(&b_full[s], 1);
@@ -211,9 +219,15 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int cc = 0; cc < p.n_chunks; ++cc) {
           mbar_wait(&a_empty[stage], phase ^ 1);
           if (issuer) {
-            // pair: both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
-            if (!PAIR || cta_rank == 0) mbar_expect_tx(&a_full[stage], (uint32_t)((PAIR ? 2 : 1) * p.rows_h * row_bytes_k));
-            tma_ld<PAIR>(smem + stage * p.a_stage_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc, t0 + p.off0, b);
+            if (PAIR && p.pre_act) {
+              // every CTA activates its own tile first: the box completes on the CTA's OWN barrier
+              mbar_expect_tx(&a_full[stage], (uint32_t)(p.rows_h * row_bytes_k));
+              tma_load_3d(smem + stage * p.a_stage_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc, t0 + p.off0, b);
+            } else {
+              // pair: both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
+              if (!PAIR || cta_rank == 0) mbar_expect_tx(&a_full[stage], (uint32_t)((PAIR ? 2 : 1) * p.rows_h * row_bytes_k));
+              tma_ld<PAIR>(smem + stage * p.a_stage_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc, t0 + p.off0, b);
+            }
           }
           if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
@@ -303,7 +317,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t b_res_lo = make_desc_lo(b_base);                                   // resident weights: walk the slabs
         uint32_t accum = 0;
         for (int cc = 0; cc < p.n_chunks; ++cc) {
-          mbar_wait(&a_full[stage], phase);
+          mbar_wait(p.pre_act ? &a_act[stage] : &a_full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           uint32_t a_lo = make_desc_lo(smem_base + (uint32_t)(stage * p.a_stage_bytes));
           if (p.b_resident) {
@@ -349,7 +363,41 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= EPI_WARP0) {
+  } else if ((warp == 3 || warp >= PAIR_ACT_WARP0) && p.pre_act && p.mode == 1) {
+    // ===================== pre-activation: leaky-relu in place on every landed A halo tile =====================
+    // The MMA cannot transform its operand, but it can be handed a transformed tile (generic-proxy stores +
+    // fence.proxy.async).  bf16x2 arithmetic: slope * x = x * hi + x * lo with hi + lo = slope to ~2^-17 (no slope bias
+    // from rounding 0.1 to bf16), then max(x, slope * x) (0 < slope <= 1).  Zero-filled halo rows stay zero.
+    const uint32_t n16 = (uint32_t)(p.rows_h * row_bytes_k) >> 4;
+    const uint32_t act_threads = PAIR ? 32u * (1 + PAIR_EXTRA_ACT_WARPS) : 32u;
+    const uint32_t act_tid = (uint32_t)((warp == 3 ? 0 : warp - PAIR_ACT_WARP0 + 1) * 32 + lane);
+    const __nv_bfloat16 s_hi = __float2bfloat16_rn(p.pre_slope);
+    const __nv_bfloat16 s_lo = __float2bfloat16_rn(p.pre_slope - __bfloat162float(s_hi));
+    const __nv_bfloat162 hi2 = __halves2bfloat162(s_hi, s_hi), lo2 = __halves2bfloat162(s_lo, s_lo);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+      for (int cc = 0; cc < p.n_chunks; ++cc) {
+        mbar_wait(&a_full[stage], phase);
+        const uint32_t base = smem_u32(smem + stage * p.a_stage_bytes);
+#pragma unroll 4
+        for (uint32_t e = act_tid; e < n16; e += act_threads) {
+          uint4 v = lds128(base + e * 16u);
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) h[u] = __hmax2(h[u], __hfma2(h[u], lo2, __hmul2(h[u], hi2)));
+          sts128(base + e * 16u, v);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(&a_act[stage], 0);   // the leader's MMA warp waits for both CTAs' tiles
+          else mbar_arrive(&a_act[stage]);
+        }
+        if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < PAIR_ACT_WARP0) {
     // ===================== epilogue: warps (q, q+4) share TMEM lanes / tile rows [32q, 32q+32) ============
     // and split the 16-column chunks of every block between them; warp `half == 0` drives the TMA traffic.
     const int q = warp & 3;
@@ -521,15 +569,15 @@ extern "C" int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb) {
   return SIB_ERR_UNSUPPORTED;
 }
 
-extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void* w, const float* bias,
-                               const void* residual, void* y, void* y_act, sib_stream_t stream) {
+static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w, const float* bias,
+                            const void* residual, void* y, void* y_act, sib_stream_t stream, bool dry_run) {
   SIB_REQUIRE(d && x && w && y, "sib_conv1d_bf16: null argument");
   SIB_REQUIRE(d->batch > 0 && d->t_in > 0 && d->t_out > 0 && d->c_in > 0 && d->c_out > 0, "sib_conv1d_bf16: empty shape");
   SIB_REQUIRE(d->groups > 0 && d->c_in % d->groups == 0 && d->c_out % d->groups == 0,
               "sib_conv1d_bf16: groups=%d must divide c_in=%d and c_out=%d", d->groups, d->c_in, d->c_out);
   SIB_REQUIRE(d->n_taps > 0 && d->n_taps <= SIB_MAX_TAPS, "sib_conv1d_bf16: n_taps=%d out of range", d->n_taps);
-  SIB_REQUIRE(d->pre_act == SIB_ACT_NONE, "sib_conv1d_bf16: pre-activation is not available on the TMA path; "
-                                          "have the producer write the activated tensor (y_act)");
+  SIB_REQUIRE(d->pre_act == SIB_ACT_NONE || (d->pre_act == SIB_ACT_LRELU && d->pre_slope > 0.f && d->pre_slope <= 1.f),
+              "sib_conv1d_bf16: pre-activation must be none or leaky-relu with a slope in (0, 1]");
   const int cin_g = d->c_in / d->groups, cout_g = d->c_out / d->groups;
   int cc, tb;
   if (int rc = sib_conv1d_bf16_kblock(cin_g, &cc, &tb)) return rc;
@@ -704,6 +752,14 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
       }
     }
   }
+  a.pre_act = d->pre_act == SIB_ACT_LRELU ? 1 : 0;
+  a.pre_slope = d->pre_slope;
+  if (a.pre_act && a.mode != 1) {
+    sib::set_error("sib_conv1d_bf16: pre-activation needs the halo mode (stride 1, > 1 evenly spaced taps, tile fits); "
+                   "have the producer write the activated tensor (y_act) for this layer");
+    return SIB_ERR_UNSUPPORTED;
+  }
+  if (dry_run) return SIB_OK;
   if (a.mode == 1) {
     a.ring_bytes = a.a_stages * a.a_stage_bytes + a.b_region_bytes;
   } else {
@@ -791,7 +847,7 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   cudaError_t le = cudaSuccess;
 #define SIB_TC_LAUNCH(ACT)                                                                                              \
-  le = pair ? sib::launch_pdl_cluster(conv1d_bf16_tc_kernel<ACT, true>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
+  le = pair ? sib::launch_pdl_cluster(conv1d_bf16_tc_kernel<ACT, true>, dim3(grid), dim3(NUM_THREADS_PAIR), (size_t)smem_bytes, cs, \
                                       2u, map_a, map_b, map_y, map_y2, map_r, a)                                        \
             : sib::launch_pdl(conv1d_bf16_tc_kernel<ACT, false>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
                               map_a, map_b, map_y, map_y2, map_r, a)
@@ -810,4 +866,16 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
   }
   SIB_CHECK_LAUNCH("sib_conv1d_bf16");
   return SIB_OK;
+}
+
+extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void* w, const float* bias,
+                               const void* residual, void* y, void* y_act, sib_stream_t stream) {
+  return conv1d_bf16_impl(d, x, w, bias, residual, y, y_act, stream, false);
+}
+
+// 1 if sib_conv1d_bf16 would run this descriptor with its leaky-relu pre-activation (halo mode selected), else 0
+extern "C" int sib_conv1d_bf16_pre_act_supported(const sib_conv_desc* d) {
+  if (!d || d->pre_act != SIB_ACT_LRELU) return 0;
+  void* fake = reinterpret_cast<void*>(uintptr_t(4096));   // alignment checks only: nothing is dereferenced in a dry run
+  return conv1d_bf16_impl(d, fake, fake, nullptr, nullptr, fake, nullptr, nullptr, true) == SIB_OK ? 1 : 0;
 }

@@ -11,6 +11,7 @@ re-layout of ConvTranspose1d and the transposition into kernel layouts happen on
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 
 import torch
@@ -61,6 +62,9 @@ class Generator(_StateHolder):
         self._plans = {}
         self.use_cuda_graph = False
         self.use_fused_resunits = True   # bf16 arm: fused ResBlock1 units on the narrow stages (A/B switch)
+        # bf16 arm: unfused convs apply the leaky-relu that precedes them to their A tile in shared memory, so producers
+        # stop writing an activated copy of every tensor (A/B switch, SIB_SMEM_PREACT=0)
+        self.use_smem_preact = os.environ.get("SIB_SMEM_PREACT", "1") != "0"
 
     # ---- state
     def _conv_names(self):
@@ -132,9 +136,10 @@ class Generator(_StateHolder):
 
     # ---- plan (bf16 / tcgen05 arm)
     def _build_plan_bf16(self, B: int, Tm: int, frame_major_in: bool):
-        """Same graph as `_build_plan`, bf16 activations.  The TMA-fed kernel cannot transform its A operand, so
-        every leaky_relu that precedes a conv (models.py:37,39,109,119) is produced by the PREVIOUS kernel's
-        epilogue: convs1 write only lrelu(y); ConvTranspose / convs2 write y (residual stream) and lrelu(y)."""
+        """Same graph as `_build_plan`, bf16 activations.  The TMA-fed MMA cannot transform its A operand on the fly, so a
+        leaky_relu that precedes a conv (models.py:37,39,109,119) is either applied by the consumer to its landed A tile
+        in shared memory (fused units; `sib_conv1d_bf16` in halo mode with `use_smem_preact`) or produced by the PREVIOUS
+        kernel's epilogue as a second output lrelu(y) (`y_act`); convs1 write only lrelu(t1)."""
         P, dev = self._pack(), self._device
         f32 = dict(device=dev, dtype=torch.float32)
         b16 = dict(device=dev, dtype=torch.bfloat16)
@@ -163,27 +168,44 @@ class Generator(_StateHolder):
             ops.conv1d(xb, P["conv_pre.w"], self._sd["conv_pre.bias"], cur_act, ops.conv_taps(7, 1, 3),
                        post_act=ops.ACT_LRELU, post_slope=LRELU_SLOPE)
             t_in = Tm
+            # Which consumers activate their own input?  Fused units do (raw x in); an unfused conv does when the tcgen05
+            # kernel can apply the leaky-relu to its A tile in shared memory (halo mode); conv_post has a pre-slope of its
+            # own.  Producers write an activated copy (y_act) only for the consumers that are left.
+            pre = self.use_smem_preact
+            c_prev = [self.c0] + chans[:-1]
+            t_prev = [Tm] + lens[:-1]
+            ups_pa = [pre and i > 0 and ops.conv_pre_act_supported(B, t_prev[i], c_prev[i], u * chans[i], P[f"ups.{i}.taps"],
+                                                                   LRELU_SLOPE) for i, u in enumerate(self.upsample_rates)]
+            cur, cur_act = None, cur_act     # conv_pre wrote lrelu(y) only (nobody needs its raw output)
             for i, u in enumerate(self.upsample_rates):
                 C_, L_ = chans[i], lens[i]
                 last_stage = i == self.num_upsamples - 1
+                next_needs_act = (not pre) if last_stage else (not ups_pa[i + 1])
                 up, up_act = view(UP, L_, C_), view(UPA, L_, C_)
                 xs, xs_act = (view(XS0, L_, C_), view(XS0A, L_, C_)) if i % 2 == 0 else (view(XS1, L_, C_), view(XS1A, L_, C_))
                 # Narrow stages (C <= 64) run fused ResBlock1 units (sib_resunit_bf16: lrelu -> conv1 -> lrelu -> conv2 ->
-                # + x in one kernel, raw x in, y out) wherever the unit's weights fit in shared memory; a fused unit
-                # needs no activated copy of its input, so y_act / up_act are only written for unfused consumers.
-                fused = []
+                # + x in one kernel, raw x in, y out) wherever the unit's weights fit in shared memory.
+                fused, self_act = [], []
                 for j, (rk, dils) in enumerate(zip(self.rb_kernels, self.rb_dilations)):
-                    row = [False] * len(dils)
+                    row, srow = [False] * len(dils), [False] * len(dils)
                     for m in reversed(range(len(dils))):
                         last_m = m == len(dils) - 1
-                        # a unit writes lrelu(y) only for an unfused consumer (next unit / next stage / conv_post)
-                        need_act = (j == self.num_kernels - 1) if last_m else (not row[m + 1])
+                        # a unit writes lrelu(y) only for a consumer that cannot activate its own input
+                        need_act = (j == self.num_kernels - 1 and next_needs_act) if last_m else (not srow[m + 1])
                         row[m] = (self.resblock == "1" and self.use_fused_resunits and
                                   ops.resunit_supported(C_, rk, dils[m], last_m and j > 0, need_act))
+                        srow[m] = row[m] or (pre and ops.conv_pre_act_supported(
+                            B, L_, C_, C_, ops.conv_taps(rk, dils[m], get_padding(rk, dils[m])), LRELU_SLOPE))
                     fused.append(row)
-                need_up_act = not all(f[0] for f in fused)
-                ops.conv1d(cur_act, P[f"ups.{i}.w"], P[f"ups.{i}.b"], up.view(B, t_in, u * C_), P[f"ups.{i}.taps"],
-                           y_act=up_act.view(B, t_in, u * C_) if need_up_act else None, act2_slope=LRELU_SLOPE)
+                    self_act.append(srow)
+                need_up_act = not all(sa[0] for sa in self_act)
+                if ups_pa[i]:   # lrelu(0.1) of models.py:110 on the raw output of the previous stage, in shared memory
+                    ops.conv1d(cur, P[f"ups.{i}.w"], P[f"ups.{i}.b"], up.view(B, t_in, u * C_), P[f"ups.{i}.taps"],
+                               pre_slope=LRELU_SLOPE, y_act=up_act.view(B, t_in, u * C_) if need_up_act else None,
+                               act2_slope=LRELU_SLOPE)
+                else:
+                    ops.conv1d(cur_act, P[f"ups.{i}.w"], P[f"ups.{i}.b"], up.view(B, t_in, u * C_), P[f"ups.{i}.taps"],
+                               y_act=up_act.view(B, t_in, u * C_) if need_up_act else None, act2_slope=LRELU_SLOPE)
                 for j, (rk, dils) in enumerate(zip(self.rb_kernels, self.rb_dilations)):
                     n = i * self.num_kernels + j
                     last_j = j == self.num_kernels - 1
@@ -191,13 +213,13 @@ class Generator(_StateHolder):
                     for m, dl in enumerate(dils):
                         last_m = m == len(dils) - 1
                         if last_m:
-                            dst, dst_act = xs, (xs_act if last_j else None)
+                            dst, dst_act = xs, (xs_act if (last_j and next_needs_act) else None)
                             # the next consumer of xs is lrelu(0.1)->ups[i+1] or lrelu(0.01)->conv_post
                             slope2 = 0.01 if last_stage else LRELU_SLOPE
                         else:
                             dst, dst_act = (view(PA, L_, C_), view(PAA, L_, C_)) if m % 2 == 0 else (view(PB, L_, C_), view(PBA, L_, C_))
                             slope2 = LRELU_SLOPE
-                            if fused[j][m + 1]:
+                            if self_act[j][m + 1]:
                                 dst_act = None      # the consumer activates its own input tile
                         acc = last_m and j > 0
                         scale = (1.0 / self.num_kernels) if (last_m and last_j) else 1.0
@@ -208,21 +230,26 @@ class Generator(_StateHolder):
                                         slope_in=LRELU_SLOPE, slope_mid=LRELU_SLOPE, act2_slope=slope2)
                         else:
                             kw = dict(accumulate=acc, out_scale=scale, residual=xcur, y_act=dst_act, act2_slope=slope2)
+                            # first conv of the unit: raw x + in-kernel leaky-relu, or the producer's activated copy
+                            src, pkw = (xcur, dict(pre_slope=LRELU_SLOPE)) if self_act[j][m] else (xcur_act, {})
                             if self.resblock == "1":
                                 t1 = view(T1, L_, C_)
-                                ops.conv1d(xcur_act, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
-                                           t1, ops.conv_taps(rk, dl, get_padding(rk, dl)), post_act=ops.ACT_LRELU, post_slope=LRELU_SLOPE)
+                                ops.conv1d(src, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
+                                           t1, ops.conv_taps(rk, dl, get_padding(rk, dl)), post_act=ops.ACT_LRELU,
+                                           post_slope=LRELU_SLOPE, **pkw)
                                 ops.conv1d(t1, P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
                                            dst, ops.conv_taps(rk, 1, get_padding(rk, 1)), **kw)
                             else:
-                                ops.conv1d(xcur_act, P[f"resblocks.{n}.convs.{m}.w"], self._sd[f"resblocks.{n}.convs.{m}.bias"],
-                                           dst, ops.conv_taps(rk, dl, get_padding(rk, dl)), **kw)
+                                ops.conv1d(src, P[f"resblocks.{n}.convs.{m}.w"], self._sd[f"resblocks.{n}.convs.{m}.bias"],
+                                           dst, ops.conv_taps(rk, dl, get_padding(rk, dl)), **kw, **pkw)
                         xcur, xcur_act = dst, dst_act
-                cur_act = xs_act
+                cur, cur_act = xs, (xs_act if next_needs_act else None)
                 t_in = L_
             io.y = torch.empty(B, 1, lens[-1], **f32)
-            # cur_act already holds lrelu(x, 0.01): conv_post reads it with an identity pre-activation (slope 1)
-            ops.conv1d_cout1(cur_act, P["conv_post.w"], self._sd["conv_post.bias"], io.y.view(B, lens[-1]), 7, 3, 1.0, ACT_TANH)
+            if pre:   # lrelu(0.01) of models.py:119 as conv_post's own pre-activation on the raw stage output
+                ops.conv1d_cout1(cur, P["conv_post.w"], self._sd["conv_post.bias"], io.y.view(B, lens[-1]), 7, 3, 0.01, ACT_TANH)
+            else:     # cur_act already holds lrelu(x, 0.01): identity pre-activation (slope 1)
+                ops.conv1d_cout1(cur_act, P["conv_post.w"], self._sd["conv_post.bias"], io.y.view(B, lens[-1]), 7, 3, 1.0, ACT_TANH)
         io.plan = plan
         if self.use_cuda_graph:
             plan.capture()

@@ -288,6 +288,12 @@ def conv1d(x, w, bias, y, taps, *, stride=1, groups=1, residual=None, y_act=None
         raise SibError(f"unsupported dtype {x.dtype}")
 
 
+def conv_pre_act_supported(batch, t, c_in, c_out, taps, pre_slope=0.1) -> bool:
+    """Whether the tcgen05 conv can apply leaky-relu to its A tile in shared memory for this (stride-1) layer."""
+    d = make_desc(batch, t, t, c_in, c_out, taps, pre_slope=pre_slope)
+    return bool(_lib.lib().sib_conv1d_bf16_pre_act_supported(C.byref(d)))
+
+
 def resunit_supported(c: int, k: int, dilation: int, accumulate: bool = False, has_y_act: bool = False) -> bool:
     return bool(_lib.lib().sib_resunit_bf16_supported(c, k, dilation, int(accumulate), int(has_y_act)))
 

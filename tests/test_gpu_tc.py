@@ -256,3 +256,53 @@ def test_new_operators_fail_loudly(sib):
     # PDL switch round-trips
     prev = ops.set_pdl(False)
     assert ops.set_pdl(prev) is False
+
+
+PRE_ACT_CASES = [
+    # B, T, C_in, C_out, k, dil  (stride 1, "same" padding): single CTAs, CTA pairs, resident and streamed weights, N tiles
+    (2, 300, 128, 128, 3, 1),
+    (3, 1000, 128, 128, 7, 5),
+    (2, 2000, 128, 128, 11, 3),
+    (2, 700, 256, 256, 11, 5),
+    (2, 517, 256, 256, 3, 3),
+    (2, 640, 256, 1024, 3, 1),     # poly-phase upsampling conv: several N tiles per halo tile
+    (2, 900, 64, 64, 7, 1),
+    (2, 900, 32, 32, 3, 3),        # tap-blocked K rows (cc = 32)
+]
+
+
+@pytest.mark.parametrize("case", PRE_ACT_CASES)
+def test_conv1d_bf16_pre_activation_in_shared_memory(sib, case):
+    """leaky-relu applied to the landed A tile inside the kernel == conv of the activated tensor (models.py:37,109)."""
+    B, T, Cin, Cout, k, d = case
+    pad = (k * d - d) // 2
+    x = _bf(_rand(B, Cin, T, seed=11))
+    w = _bf(_rand(Cout, Cin, k, seed=12, scale=1.0 / math.sqrt(Cin * k)))
+    b = _rand(Cout, seed=13, scale=0.1)
+    taps = sib.ops.conv_taps(k, d, pad)
+    assert sib.ops.conv_pre_act_supported(B, T, Cin, Cout, taps)
+    xa = _bf(F.leaky_relu(x, 0.1))                      # what the producer's y_act output would hold
+    ref = to_frame_major(F.conv1d(xa, w, b, dilation=d, padding=pad))
+    wk = sib.ops.to_kmajor_bf16(sib.ops.pack_conv_weight(w.cuda()))
+    xd = to_frame_major(x).to(torch.bfloat16).cuda()
+    y = torch.full((B, T, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    sib.ops.conv1d(xd, wk, b.cuda(), y, taps, pre_slope=0.1)
+    # the in-kernel activation rounds slope * x twice (bf16 product + bf16 correction): within one bf16 ulp of xa
+    _close(ref, y.float().cpu(), f"pre-act {case}")
+    # and it matches the y_act route bit for bit wherever x >= 0 everywhere (identity on non-negative inputs)
+    xp = x.abs()
+    y1 = torch.empty_like(y)
+    y2 = torch.empty_like(y)
+    xpd = to_frame_major(xp).to(torch.bfloat16).cuda()
+    sib.ops.conv1d(xpd, wk, b.cuda(), y1, taps, pre_slope=0.1)
+    sib.ops.conv1d(xpd, wk, b.cuda(), y2, taps)
+    assert torch.equal(y1, y2)
+
+
+def test_conv1d_bf16_pre_activation_rejected_outside_halo_mode(sib):
+    x = torch.zeros(1, 256, 768, dtype=torch.bfloat16, device="cuda")
+    w = sib.ops.to_kmajor_bf16(sib.ops.pack_linear_weight(torch.zeros(768, 768, device="cuda")))
+    y = torch.empty(1, 256, 768, dtype=torch.bfloat16, device="cuda")
+    assert not sib.ops.conv_pre_act_supported(1, 256, 768, 768, [0])
+    with pytest.raises(sib.SibError, match="halo"):
+        sib.ops.conv1d(x, w, None, y, [0], pre_slope=0.1)
