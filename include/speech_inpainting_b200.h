@@ -139,6 +139,10 @@ int sib_gather_frames_f32(const float* src, int batch, int t, int d, const int32
 int sib_cos_argmax_f32(const float* v, const float* cc, int m, int k, int d, int64_t* labels, sib_stream_t stream);
 /* a17: labels[m] = argmin_k ||f[m]-mu[k]||^2 (sklearn KMeans.predict, inpainting.py:204-205) */
 int sib_l2_argmin_f32(const float* f, const float* mu, int m, int k, int d, int64_t* labels, sib_stream_t stream);
+/* a10 head on the gathered frames (I_ea/model.py:75-78,88 Linear(H, 80) after LayerNorm): y[m,:] = x[m,:] @ w + bias for a
+ * NARROW output (n <= 128), w [k][n] (= sib_conv1d_f32 layout of a linear layer); one CTA per row. */
+int sib_linear_skinny_f32(const float* x, const float* w, const float* bias, float* y, int m, int k, int n,
+                          sib_stream_t stream);
 /* a13: mel[b,:,pos[b]+i] = cc[labels[off[b]+i]] + center, i < len[b]; mel is channels-first [B,D,T] (predict.py:184-187) */
 int sib_paste_centroids_f32(float* mel, int batch, int d, int t, const float* cc, const float* center,
                             const int64_t* labels, const int32_t* pos, const int32_t* len, const int32_t* off,

@@ -270,3 +270,52 @@ extern "C" int sib_cast_bf16_to_f32(const void* in, float* out, int64_t n, sib_s
   SIB_CHECK_LAUNCH("sib_cast_bf16_to_f32");
   return SIB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-wise linear layer with a narrow output, y[m, :] = x[m, :] @ w + b (w [K][N], N <= 128): the head of CustomModel
+// (I_ea/model.py:75-78,88: Linear(H, 80)) on the sum(L) gathered mask frames.  M is a few hundred rows, so the tiled
+// GEMM kernels would run on a handful of CTAs; here one CTA owns one row, KSPLIT groups of N threads stride the
+// reduction axis (coalesced w rows, L2-resident) and the partial sums meet in shared memory in a fixed order.
+namespace {
+constexpr int SK_MAXN = 128, SK_THREADS = 512;
+__global__ void __launch_bounds__(SK_THREADS) linear_skinny_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                  const float* __restrict__ bias, float* __restrict__ y,
+                                                                  int K, int N) {
+  extern __shared__ float sk_smem[];
+  float* xs = sk_smem;                 // [K]
+  float* part = sk_smem + K;           // [ksplit][N]
+  const int m = blockIdx.x;
+  const float* xr = x + (int64_t)m * K;
+  for (int k = threadIdx.x; k < K; k += SK_THREADS) xs[k] = xr[k];
+  __syncthreads();
+  const int ksplit = SK_THREADS / N;   // >= 4 for N <= 128
+  const int grp = threadIdx.x / N, n = threadIdx.x - grp * N;
+  if (grp < ksplit) {
+    float a0 = 0.f, a1 = 0.f;
+    int k = grp;
+    for (; k + ksplit < K; k += 2 * ksplit) {
+      a0 = fmaf(xs[k], __ldg(w + (int64_t)k * N + n), a0);
+      a1 = fmaf(xs[k + ksplit], __ldg(w + (int64_t)(k + ksplit) * N + n), a1);
+    }
+    if (k < K) a0 = fmaf(xs[k], __ldg(w + (int64_t)k * N + n), a0);
+    part[grp * N + n] = a0 + a1;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float acc = bias ? bias[threadIdx.x] : 0.f;
+    for (int g = 0; g < ksplit; ++g) acc += part[g * N + threadIdx.x];
+    y[(int64_t)m * N + threadIdx.x] = acc;
+  }
+}
+}  // namespace
+
+extern "C" int sib_linear_skinny_f32(const float* x, const float* w, const float* bias, float* y, int m, int k, int n,
+                                     sib_stream_t stream) {
+  SIB_REQUIRE(x && w && y && m > 0 && k > 0 && n > 0, "sib_linear_skinny_f32: bad argument");
+  SIB_REQUIRE(n <= SK_MAXN, "sib_linear_skinny_f32: n=%d > %d (use sib_conv1d_f32 for wide outputs)", n, SK_MAXN);
+  const size_t smem = ((size_t)k + (size_t)(SK_THREADS / n) * n) * sizeof(float);
+  SIB_REQUIRE(smem <= 48 * 1024, "sib_linear_skinny_f32: k=%d too large", k);
+  linear_skinny_kernel<<<m, SK_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, k, n);
+  SIB_CHECK_LAUNCH("sib_linear_skinny_f32");
+  return SIB_OK;
+}

@@ -376,6 +376,74 @@ __global__ void __launch_bounds__(1024) znorm_kernel(const float* __restrict__ x
   for (int i = threadIdx.x; i < n; i += blockDim.x) yb[i] = i < len ? (xb[i] - mean) * rstd : 0.f;
 }
 
+// Cluster variant: an utterance is shared by a thread-block cluster of ZN_CL CTAs (one CTA per utterance leaves a 32-utterance
+// batch on 32 of 148 SMs).  Every thread keeps its PER samples in registers, so the waveform is read from HBM exactly once;
+// the two reductions (sum, centred sum of squares) meet through distributed shared memory in a fixed order.
+constexpr int ZN_CL = 8;
+template <int PER>
+__global__ void __cluster_dims__(ZN_CL, 1, 1) __launch_bounds__(1024)
+znorm_cluster_kernel(const float* __restrict__ x, float* __restrict__ y, int n, const int32_t* __restrict__ lengths, float eps) {
+  __shared__ float red[32];
+  __shared__ float part[2];
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int b = blockIdx.x / ZN_CL;
+  const float* xb = x + (int64_t)b * n;
+  float* yb = y + (int64_t)b * n;
+  const int len = lengths ? min(max(lengths[b], 0), n) : n;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  auto cluster_sync = [] {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  };
+  // sum over the cluster: block reduction -> part[slot] of every CTA -> all CTAs add the ZN_CL partials in rank order
+  auto cluster_sum = [&](float v, int slot) {
+    v = sib::warp_sum(v);
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      float t = red[lane];               // 1024 threads = 32 warps
+      t = sib::warp_sum(t);
+      if (lane == 0) part[slot] = t;
+    }
+    cluster_sync();
+    float tot = 0.f;
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(&part[slot]);
+#pragma unroll
+    for (uint32_t r = 0; r < ZN_CL; ++r) {
+      uint32_t remote;
+      float pv;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pv) : "r"(remote) : "memory");
+      tot += pv;
+    }
+    return tot;
+  };
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = (j * ZN_CL + (int)rank) * 1024 + (int)threadIdx.x;   // interleaved slices: coalesced per CTA
+    v[j] = i < len ? xb[i] : 0.f;
+    s += v[j];
+  }
+  const float mean = cluster_sum(s, 0) / (float)max(len, 1);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = (j * ZN_CL + (int)rank) * 1024 + (int)threadIdx.x;
+    const float dlt = v[j] - mean;
+    q += i < len ? dlt * dlt : 0.f;
+  }
+  const float rstd = rsqrtf(cluster_sum(q, 1) / (float)max(len, 1) + eps);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = (j * ZN_CL + (int)rank) * 1024 + (int)threadIdx.x;
+    if (i < n) yb[i] = i < len ? (v[j] - mean) * rstd : 0.f;
+  }
+  cluster_sync();   // no CTA leaves while a peer may still read its partials
+}
+
 __global__ void zero_ranges_kernel(float* __restrict__ wave, int n, const int32_t* __restrict__ lo,
                                    const int32_t* __restrict__ hi, float add_eps) {
   const int b = blockIdx.y;
@@ -588,7 +656,16 @@ extern "C" int sib_gn_finalize_f32(const float* partial, int batch, int n_tiles,
 extern "C" int sib_znorm_f32(const float* x, float* y, int batch, int n, const int32_t* lengths, float eps,
                              sib_stream_t stream) {
   SIB_REQUIRE(x && y && batch > 0 && n > 0, "sib_znorm_f32: bad argument");
-  znorm_kernel<<<batch, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, lengths, eps);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t per_cluster_pass = (int64_t)ZN_CL * 1024;
+  if ((int64_t)batch * ZN_CL <= 0x7fffffff && n <= 32 * per_cluster_pass) {
+    // registers hold the whole slice: 8 / 16 / 32 samples per thread cover 4 / 8 / 16 s at 16 kHz
+    if (n <= 8 * per_cluster_pass) znorm_cluster_kernel<8><<<batch * ZN_CL, 1024, 0, s>>>(x, y, n, lengths, eps);
+    else if (n <= 16 * per_cluster_pass) znorm_cluster_kernel<16><<<batch * ZN_CL, 1024, 0, s>>>(x, y, n, lengths, eps);
+    else znorm_cluster_kernel<32><<<batch * ZN_CL, 1024, 0, s>>>(x, y, n, lengths, eps);
+  } else {
+    znorm_kernel<<<batch, 1024, 0, s>>>(x, y, n, lengths, eps);
+  }
   SIB_CHECK_LAUNCH("sib_znorm_f32");
   return SIB_OK;
 }

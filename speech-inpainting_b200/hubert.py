@@ -441,7 +441,10 @@ class CustomModel(_StateHolder):
             ops.gather_frames(h, pos_t, len_t, off_t, rows)
             nrm = torch.empty_like(rows)
             ops.layernorm(rows, self._sd["final_layers.0.weight"], self._sd["final_layers.0.bias"], nrm, 1e-5)
-            ops.linear(nrm, self._head, self._sd["final_layers.1.bias"], out)
+            if self.codebook_dim <= 128 and H <= 8192:   # a few hundred rows x 80 outputs: one CTA per row
+                ops.linear_skinny(nrm, self._head, self._sd["final_layers.1.bias"], out)
+            else:
+                ops.linear(nrm, self._head, self._sd["final_layers.1.bias"], out)
         return out, T
 
     def forward(self, input_values, attention_mask=None):

@@ -321,6 +321,17 @@ def linear(x2d, w, bias, y2d, *, residual=None, **kw):
            residual=None if residual is None else residual.unsqueeze(0), **kw)
 
 
+def linear_skinny(x2d, w, bias, y2d):
+    """x2d [M,K] fp32 @ packed w [1][1][K][N] (+bias) -> y2d [M,N] for N <= 128: one CTA per row (few-hundred-row heads)."""
+    M, K = x2d.shape
+    N = y2d.shape[1]
+    for t, nme in ((x2d, "x"), (w, "w"), (bias, "bias"), (y2d, "y")):
+        _chk(t, torch.float32, nme)
+    if not (x2d.is_contiguous() and y2d.is_contiguous() and w.is_contiguous()) or w.numel() != K * N:
+        raise SibError("linear_skinny: operands must be contiguous and w must hold K x N values")
+    _emit("sib_linear_skinny_f32", (_p(x2d), _p(w), _p(bias), _p(y2d), M, K, N), keep=(x2d, w, bias, y2d))
+
+
 def conv1d_cout1(x, w, bias, y, k, pad, pre_slope, post_act):
     B, T, Cc = x.shape
     _chk(x, None, "x"); _chk(y, torch.float32, "y")

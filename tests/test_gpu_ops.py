@@ -174,6 +174,17 @@ def test_znorm_and_zero_ranges(sib):
     assert max_abs(glue_ref.processor_znorm(x, lengths), y.cpu()) < 2e-5
     sib.ops.znorm(x.cuda(), y, None, 1e-5)
     assert max_abs(glue_ref.fairseq_layer_norm(x[0]), y[0].cpu()) < 2e-5
+    # every kernel variant (8 / 16 / 32 samples per thread in the 8-CTA cluster kernel, one-CTA fallback), ragged lengths,
+    # and batch invariance: an utterance normalises to the same bits alone or inside a batch
+    for n in (64000, 96000, 160000, 300000, 777):
+        xx = 0.1 * _rand(4, n, seed=n) + 0.02
+        ll = torch.tensor([n, n // 2 + 3, 1, n - 1], dtype=torch.int32)
+        yy = torch.empty(4, n, device="cuda")
+        sib.ops.znorm(xx.cuda(), yy, ll.cuda(), 1e-7)
+        assert max_abs(glue_ref.processor_znorm(xx, ll), yy.cpu()) < 3e-5, n
+        y1 = torch.empty(1, n, device="cuda")
+        sib.ops.znorm(xx[1:2].cuda().contiguous(), y1, ll[1:2].cuda(), 1e-7)
+        assert torch.equal(y1[0], yy[1])
     # zero ranges: bit exact, numpy slice semantics incl. empty / clamped ranges
     lo, hi = [14480, 31000, 500], [17599, 40000, 400]
     xd = x.clone().cuda()
@@ -400,3 +411,20 @@ def test_load_wav_batch(sib, tmp_path):
         ref = R.resample(R.pcm16_to_float(p), s, 16000)
         assert np.abs(wave[b, :len(ref)].cpu().numpy() - ref).max() < 2e-6
     assert lens.tolist()[2] == 5000 and np.array_equal(wave[2, :5000].cpu().numpy(), pcms[2][0].astype(np.float32) / 32768)
+
+
+def test_linear_skinny_head(sib):
+    """CustomModel head (Linear(H, 80), I_ea/model.py:75-78) on gathered frames: row-wise kernel vs torch fp32; every row is
+    computed the same way whatever the batch (bit-identical alone or among 320 rows)."""
+    for M, K, N in ((320, 768, 80), (1, 1024, 80), (37, 768, 100), (5, 64, 128)):
+        x, w, b = _rand(M, K, seed=31), _rand(N, K, seed=32, scale=K ** -0.5), _rand(N, seed=33)
+        ref = x @ w.t() + b
+        wd = sib.ops.pack_linear_weight(w.cuda())
+        y = torch.empty(M, N, device="cuda")
+        sib.ops.linear_skinny(x.cuda(), wd, b.cuda(), y)
+        assert max_abs(ref, y.cpu()) < 2e-5
+        y1 = torch.empty(1, N, device="cuda")
+        sib.ops.linear_skinny(x[M // 2: M // 2 + 1].cuda().contiguous(), wd, b.cuda(), y1)
+        assert torch.equal(y1[0], y[M // 2])
+    with pytest.raises(sib.SibError):
+        sib.ops.linear_skinny(torch.zeros(2, 8, device="cuda"), torch.zeros(8 * 200, device="cuda"), None, torch.zeros(2, 200, device="cuda"))
