@@ -20,6 +20,9 @@ SHAPES = {
     "ffn1g": (1, 6368, 768, 3072, 1, 1, 1, False, False, "gelu"),
     "ffn2": (1, 6368, 3072, 768, 1, 1, 1, False, False),
     "oproj": (1, 6368, 768, 768, 1, 1, 1, False, False),
+    "tiny1": (1, 256, 768, 256, 1, 1, 1, False, False),          # one pair tile: the fixed cost of a launch
+    "tiny74": (1, 18944, 768, 256, 1, 1, 1, False, False),       # exactly one round of 74 pair tiles
+    "tiny148": (1, 37888, 768, 256, 1, 1, 1, False, False),      # two rounds
     "hubconv1": (32, 12799, 512, 512, 3, 1, 2, False, False),
     "s1k11": (32, 2752, 256, 256, 11, 1, 1, True, True),
     "s2k3c1": (32, 22016, 128, 128, 3, 1, 1, False, False),
