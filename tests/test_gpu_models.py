@@ -447,3 +447,36 @@ def test_stream_pipeline_matches_direct_calls(sib):
             assert torch.equal(out.int16, pcm) and torch.equal(out.labels, lab)   # checked before the buffers are recycled
             n += 1
         assert n == len(batches)
+
+
+def test_blind_inpainting_with_continuous_f0(sib):
+    """BlindInpainter(f0=...) - the reference passes the raw f0 track (inpainting.py:231) and CodeGenerator quantises it
+    (model.py:148-152): same result as handing over the oracle's bins, including the 1280-sample trim of the f0 series."""
+    from oracle import f0vq_ref, glue_ref
+    from oracle.params import HifiCfg, HubertCfg, make_generator_params, make_hubert_params
+    ocfg, gcfg = HubertCfg.tiny(False), HifiCfg.tiny(True)
+    hp, gp, fsd = make_hubert_params(ocfg, 3), make_generator_params(gcfg, 4, "unit"), f0vq_ref.make_params(seed=9)
+    g = torch.Generator().manual_seed(53)
+    B, N, mask = 2, 32000, 6400
+    wave = 0.1 * torch.randn(B, N, generator=g)
+    mu = torch.randn(gcfg.num_embeddings, ocfg.hidden_size, generator=g) * 0.5
+    T = ocfg.feat_lengths(N)
+    f0 = torch.randn(B, 1, 4 * T, generator=g)                 # hop 80: four f0 frames per code frame
+    emb = torch.randn(B, gcfg.embedding_dim, generator=g)
+    hub = sib.HubertModel(_hub_cfg(sib, ocfg)).to("cuda")
+    hub.load_state_dict(hp)
+    gen = sib.CodeGenerator(sib.AttrDict(dict(gcfg.as_attrdict(), f0_quantizer=f0vq_ref.F0_QUANTIZER))).to("cuda")
+    gen.load_state_dict(gp)
+    gen.load_f0_quantizer(fsd)
+    pipe = sib.BlindInpainter(hub, gen, mu, layer=-1, normalize=False)
+    res = pipe(wave, mask, emb=emb, f0=f0, informed=True)
+    n_code = glue_ref.ida_matched_frames(N, T, 4 * T)
+    zp = f0vq_ref.f0_to_bins(fsd, f0[..., : 4 * n_code])        # inpainting.py:243-256: f0 trimmed with the codes
+    assert zp.shape == (B, n_code // 4)
+    ref = pipe(wave, mask, zp, emb, informed=True)
+    assert torch.equal(res.code_inpainting, ref.code_inpainting)
+    assert torch.equal(res.audio_inp, ref.audio_inp) and torch.equal(res.audio_gen, ref.audio_gen)
+    with pytest.raises(sib.SibError):
+        pipe(wave, mask, zp, emb, f0=f0)                         # both given
+    with pytest.raises(sib.SibError):
+        pipe(wave, mask, emb=emb)                                # neither given
