@@ -195,8 +195,18 @@ class InformedInpainter:
         compute = torch.cuda.current_stream(dev)
         # separate upload and download streams: in one in-order copy stream the upload of batch i+1 would queue behind the
         # download of batch i, which waits for compute i - no overlap at all
-        copy, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        slots, hosts, pending = [None] * depth, [None] * (depth + 1), deque()
+        # device slots, pinned result buffers and the two copy streams are kept on the pipeline object: a serving loop calls
+        # stream() again and again, and cudaHostAlloc / cudaMalloc inside it would cost milliseconds per call.  One stream()
+        # generator per pipeline object at a time.
+        cache = self.__dict__.setdefault("_stream_cache", {})
+        if depth not in cache:
+            cache[depth] = ([None] * depth, [None] * (depth + 1), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        slots, hosts, copy, down = cache[depth]
+        pending = deque()
+        for sl in slots:
+            if sl is not None:          # whatever ran on the compute stream since the last call is ordered before the uploads
+                sl.free = torch.cuda.Event()
+                sl.free.record(compute)
 
         def finish(item):
             fin, res, h_pcm, h_lab = item
