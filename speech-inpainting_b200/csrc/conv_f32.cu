@@ -243,9 +243,12 @@ __global__ void __launch_bounds__(CO1_TILE) conv1d_cout1_bf16_rows_kernel(const 
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * CO1_TILE;
+  // a CTA produces CO1_TILE - (K - 1) outputs from exactly CO1_TILE input rows: one row per thread, no second loop trip
+  // in which six threads of warp 0 would redo a whole row's work while 250 wait at the barrier
+  const int tile_out = CO1_TILE - (K - 1);
+  const int t0 = blockIdx.x * tile_out;
   const __nv_bfloat16* xb = x + (int64_t)b * T * C;
-  const int rows = CO1_TILE + K - 1;
+  const int rows = CO1_TILE;
   for (int r = threadIdx.x; r < rows; r += blockDim.x) {
     const int ti = t0 - pad + r;
     float p[CO1_MAXK];
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(CO1_TILE) conv1d_cout1_bf16_rows_kernel(const 
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;
-  if (t >= T) return;
+  if ((int)threadIdx.x >= tile_out || t >= T) return;
   float acc = bias ? bias[0] : 0.f;
 #pragma unroll
   for (int j = 0; j < CO1_MAXK; ++j)
@@ -330,7 +333,7 @@ extern "C" int sib_conv1d_cout1(const void* x, int x_dtype, const float* w, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x_dtype == SIB_BF16 && c % 8 == 0 && k <= CO1_MAXK) {
     const size_t smem2 = ((size_t)k * c + (size_t)k * (CO1_TILE + CO1_MAXK)) * sizeof(float);
-    conv1d_cout1_bf16_rows_kernel<<<dim3(sib::ceil_div(t, CO1_TILE), batch), CO1_TILE, smem2, s>>>(
+    conv1d_cout1_bf16_rows_kernel<<<dim3(sib::ceil_div(t, CO1_TILE - (k - 1)), batch), CO1_TILE, smem2, s>>>(
         (const __nv_bfloat16*)x, w, bias, y, t, c, k, pad, pre_slope, post_act);
   } else if (x_dtype == SIB_BF16)
     conv1d_cout1_kernel<<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, w, bias, y, t, c, k, pad, pre_slope, post_act);
