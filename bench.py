@@ -290,7 +290,7 @@ def main():
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                            "sample": sample},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
+                          "gpu_launches": 0}), flush=True)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
@@ -298,6 +298,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (and any NCCL_DEBUG output) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     sib, pipe, state = build_models(args.precision, dev)
     # rank r owns utterances [r*B, (r+1)*B) of the global batch (weak scaling; no data-path collective)
@@ -443,7 +445,7 @@ def main():
                     "d2h_bytes_per_step": out_h.numel() * 2 * world},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "algorithmic_tflop_per_step": fl_utt * args.batch * world / 1e12,
-        }))
+        }), flush=True)   # flushed before the teardown collectives: a rank dying there must not take the line with it
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
