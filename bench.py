@@ -250,7 +250,30 @@ def ncu_traffic(kernel_key):
     return None, None
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries below us write to fd 1 on their own (NCCL prints its version
+    banner there from C), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -284,13 +307,13 @@ def main():
         v, sec = time_cpu_reference(state, args.steps, args.warmup, args.cpu_sample_utts)
         sample = (f"{args.cpu_sample_utts}x{SECONDS} s utterances per step of the same workload "
                   f"(1/{args.batch // args.cpu_sample_utts} of the batch), {args.steps} steps after {args.warmup} warm-up")
-        print(json.dumps({"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        _emit(({"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                            "sample": sample},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}), flush=True)
+                          "gpu_launches": 0}))
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
@@ -298,8 +321,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (and any NCCL_DEBUG output) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     sib, pipe, state = build_models(args.precision, dev)
     # rank r owns utterances [r*B, (r+1)*B) of the global batch (weak scaling; no data-path collective)
@@ -433,7 +454,7 @@ def main():
             cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{args.cpu_sample_utts}x{SECONDS} s utterances of the same workload, 3 steps after 1 warm-up, "
                              f"{sec:.2f} s per step; oracle port of the reference's PyTorch CPU path"}
-        print(json.dumps({
+        _emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic", "config": config,
@@ -445,7 +466,7 @@ def main():
                     "d2h_bytes_per_step": out_h.numel() * 2 * world},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "algorithmic_tflop_per_step": fl_utt * args.batch * world / 1e12,
-        }), flush=True)   # flushed before the teardown collectives: a rank dying there must not take the line with it
+        }))   # written straight to the descriptor before the teardown collectives: a rank dying there cannot take it along
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
