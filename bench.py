@@ -449,7 +449,7 @@ def main():
                                       "algorithmic_bytes_per_launch": ru["bytes"] / ru["launches"],
                                       "tflops": ru["flops"] / (ru["ms"] / 1e3) / 1e12,
                                       "kernel_share_of_step": ru["ms"] / total_ms}]
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU baseline is an N = 1 figure: other ranks would be spinning beside it
             v, sec = time_cpu_reference(state, 3, 1, args.cpu_sample_utts)
             cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{args.cpu_sample_utts}x{SECONDS} s utterances of the same workload, 3 steps after 1 warm-up, "
