@@ -25,6 +25,7 @@ SHAPES = {
     "tiny148": (1, 37888, 768, 256, 1, 1, 1, False, False),      # two rounds
     "hubconv1": (32, 12799, 512, 512, 3, 1, 2, False, False),
     "s1k11": (32, 2752, 256, 256, 11, 1, 1, True, True),
+    "s2k1": (32, 22016, 128, 128, 1, 1, 1, False, False),          # data-movement floor of the stage-2 tiles (8 MMAs per tile)
     "s2k3c1": (32, 22016, 128, 128, 3, 1, 1, False, False),
     "s2k3c2": (32, 22016, 128, 128, 3, 1, 1, True, True),
     "s2k11c2": (32, 22016, 128, 128, 11, 5, 1, True, True),
