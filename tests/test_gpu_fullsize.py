@@ -156,3 +156,47 @@ def test_config3_blind_inpainting_bf16(sib):
         l1 = _mel_l1(out["fp32"][1][same], out["bf16"][1][same])
         print(f"[cfg3] mel-L1 of the bf16 CodeGenerator on identical units: {l1:.4f}")
         assert l1 < MEL_L1_BOUND
+
+
+def test_config_sweep_throughput_through_the_streaming_api(sib, capsys):
+    """BASELINE configs 2, 4 and 5 at their FULL batch sizes through `InformedInpainter.stream` (host batches in, int16 out,
+    micro-batches of 32 utterances): config 5 is 1024 x 10 s = 10 240 audio-seconds per job.  Checks that every
+    micro-batch comes back complete, in order and equal to a direct call, and prints the whole-job throughput."""
+    import time
+    cases = [("cfg2 base  32 x 4 s, 200 ms mask", "base", 32, 4, [10], 100),
+             ("cfg4 large 128 x 6 s, masks 1..20 frames, K = 500", "large", 128, 6, [1, 2, 3, 4, 5, 10, 15, 20], 500),
+             ("cfg5 base  1024 x 10 s, 200 ms mask", "base", 1024, 10, [10], 100)]
+    lines = []
+    for name, size, B, seconds, lens, K in cases:
+        pipe = _iea(sib, size, "bf16", K=K)
+        MB = 32
+        wave, mel, pos, ln = _workload(MB, seconds, lens)
+        host = {"wave16": wave.pin_memory(), "mel": mel.pin_memory(), "mask_pos": pos, "mask_len": ln}
+        direct = pipe(host["wave16"], host["mel"], pos, ln, return_int16=True)
+        want_pcm, want_lab = direct.int16.cpu(), direct.labels.cpu()
+        n_mb = B // MB
+
+        def batches(n):
+            for _ in range(n):
+                yield host
+
+        for _ in pipe.stream(batches(2)):
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 0
+        for out in pipe.stream(batches(n_mb)):
+            if n in (0, n_mb - 1):     # first and last micro-batch: bit-identical to the direct call
+                assert torch.equal(out.int16, want_pcm) and torch.equal(out.labels, want_lab)
+            n += 1
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert n == n_mb and out.int16.shape[-1] == (seconds * 22050 // 441) * 441 // 256 * 256
+        lines.append(f"[config sweep] {name:52s} {B * seconds / dt:9.0f} audio-s/s  ({dt * 1e3 / n_mb:6.2f} ms per 32-utterance micro-batch, "
+                     f"{n_mb} micro-batches, {dt * 1e3:.0f} ms per job)")
+        del pipe
+        torch.cuda.empty_cache()
+    with capsys.disabled():
+        print()
+        for l in lines:
+            print(l)
