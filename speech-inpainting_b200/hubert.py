@@ -327,28 +327,27 @@ class HubertModel(_StateHolder):
         cfg = self.config
         Bc, T, H = h.shape
         M = Bc * T
-        if True:
-            b = f"encoder.layers.{l}."
-            ob, f2b = self._w(b + "attention.out_proj.bias"), self._w(b + "feed_forward.output_dense.bias")
-            f1b = self._w(b + "feed_forward.intermediate_dense.bias")
-            ln1 = (self._w(b + "layer_norm.weight"), self._w(b + "layer_norm.bias"))
-            ln2 = (self._w(b + "final_layer_norm.weight"), self._w(b + "final_layer_norm.bias"))
-            if cfg.do_stable_layer_norm:  # HF:525-548
-                ops.layernorm(h, ln1[0], ln1[1], nrm, eps)
-                ops.linear(nrm.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
-                ops.attention(qkv, key_len, att, cfg.num_attention_heads)
-                ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, h.view(M, H), residual=h.view(M, H))
-                ops.layernorm(h, ln2[0], ln2[1], nrm, eps)
-                ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
-                ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, h.view(M, H), residual=h.view(M, H))
-            else:  # HF:388-405
-                ops.linear(h.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
-                ops.attention(qkv, key_len, att, cfg.num_attention_heads)
-                ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, tmp.view(M, H))
-                ops.layernorm(tmp, ln1[0], ln1[1], nrm, eps, residual=h)
-                ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
-                ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, tmp.view(M, H))
-                ops.layernorm(tmp, ln2[0], ln2[1], h, eps, residual=nrm)
+        b = f"encoder.layers.{l}."
+        ob, f2b = self._w(b + "attention.out_proj.bias"), self._w(b + "feed_forward.output_dense.bias")
+        f1b = self._w(b + "feed_forward.intermediate_dense.bias")
+        ln1 = (self._w(b + "layer_norm.weight"), self._w(b + "layer_norm.bias"))
+        ln2 = (self._w(b + "final_layer_norm.weight"), self._w(b + "final_layer_norm.bias"))
+        if cfg.do_stable_layer_norm:  # HF:525-548
+            ops.layernorm(h, ln1[0], ln1[1], nrm, eps)
+            ops.linear(nrm.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
+            ops.attention(qkv, key_len, att, cfg.num_attention_heads)
+            ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, h.view(M, H), residual=h.view(M, H))
+            ops.layernorm(h, ln2[0], ln2[1], nrm, eps)
+            ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
+            ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, h.view(M, H), residual=h.view(M, H))
+        else:  # HF:388-405
+            ops.linear(h.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))
+            ops.attention(qkv, key_len, att, cfg.num_attention_heads)
+            ops.linear(att.view(M, H), P[f"l{l}.o.w"], ob, tmp.view(M, H))
+            ops.layernorm(tmp, ln1[0], ln1[1], nrm, eps, residual=h)
+            ops.linear(nrm.view(M, H), P[f"l{l}.ff1.w"], f1b, ff.view(M, -1), post_act=ACT_GELU)
+            ops.linear(ff.view(M, -1), P[f"l{l}.ff2.w"], f2b, tmp.view(M, H))
+            ops.layernorm(tmp, ln2[0], ln2[1], h, eps, residual=nrm)
 
     def _key_len(self, attention_mask, N):
         """HF:690-700: valid frames per utterance from the sample-level attention mask."""
