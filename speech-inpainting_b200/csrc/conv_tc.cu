@@ -94,8 +94,8 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
   const float erfc_abs = poly * t * e;                 // erfc(|x| / sqrt 2)
-  const float cdf = x >= 0.f ? fmaf(-0.5f, erfc_abs, 1.0f) : 0.5f * erfc_abs;
-  return x * cdf;
+  // x * Phi(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2) on both sides of zero: three instructions, no select
+  return fmaf(-0.5f, fabsf(x) * erfc_abs, fmaxf(x, 0.f));
 }
 
 template <int POST_ACT>

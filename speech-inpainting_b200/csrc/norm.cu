@@ -286,7 +286,7 @@ __device__ __forceinline__ float gelu_erf_as(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
   const float erfc_abs = poly * t * e;
-  return x * (x >= 0.f ? fmaf(-0.5f, erfc_abs, 1.0f) : 0.5f * erfc_abs);
+  return fmaf(-0.5f, fabsf(x) * erfc_abs, fmaxf(x, 0.f));   // x Phi(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2): no select
 }
 __device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) {
