@@ -276,15 +276,15 @@ __global__ void __launch_bounds__(256) conv0_gn_stats_kernel(const float* __rest
 // frames at a time so that 25 broadcast shared-memory loads feed 80 FMAs; outputs leave as packed pairs (coalesced
 // 4 / 8 bytes x 256 threads per frame).  bf16 output uses the 2-MUFU erf (|err| < 1.5e-7), fp32 output erff.
 __device__ __forceinline__ float gelu_erf_as(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
+  // z = |x| / sqrt 2 never materialises: 0.3275911 z = 0.23164190 |x| and z^2 log2(e) = 0.72134752 x^2
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // argument in [1, inf)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2316419f, fabsf(x), 1.0f)));   // argument in [1, inf)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));
   const float erfc_abs = poly * t * e;
   return fmaf(-0.5f, fabsf(x) * erfc_abs, fmaxf(x, 0.f));   // x Phi(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2): no select
 }
