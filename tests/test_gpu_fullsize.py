@@ -146,6 +146,20 @@ def test_config3_blind_inpainting_bf16(sib):
         if precision == "bf16":
             part = pipe(wave[2:5], mask, zp[2:5], emb[2:5], informed=False)
             assert torch.equal(part.code_inpainting, out["bf16"][0][2:5]) and torch.equal(part.audio_inp, out["bf16"][1][2:5])
+            # the full configuration (64 x 4 s): throughput of the whole script path - two HuBERT passes (clean and masked
+            # signal, inpainting.py:195-198) and two generate() calls (:258-259) per utterance
+            import time
+            reps = 64 // B
+            w64, z64, e64 = wave.repeat(reps, 1), zp.repeat(reps, 1), emb.repeat(reps, 1)
+            pipe(w64, mask, z64, e64, informed=False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                full = pipe(w64, mask, z64, e64, informed=False)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            assert torch.equal(full.audio_inp[:B], out["bf16"][1])
+            print(f"\n[cfg3 I_da 64x4s] {64 * 4 / dt:8.0f} inpainted audio-s/s ({dt * 1e3:.1f} ms per batch: 2 HuBERT passes + 2 CodeGenerator passes)")
     assert torch.equal(out["bf16"][2], out["fp32"][2])                      # (y + 1e-6) * mask: fp32 in both arms, exact
     assert out["bf16"][0].shape[1] == 196 and out["bf16"][1].shape[-1] == 196 * 320   # inpainting.py:244-256 trim
     agree = float((out["bf16"][0] == out["fp32"][0]).float().mean())
