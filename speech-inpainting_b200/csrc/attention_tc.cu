@@ -39,9 +39,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Persistent: gridDim.x CTAs (two per SM) walk the (query tile, head, utterance) work items with stride gridDim.x.  Barriers,
+// the TMEM allocation and the tensor-map prefetch are paid once per CTA, and the producer warp runs ahead across items: the
+// next item's Q is fetched as soon as the last S MMAs of the current one have retired (q_empty), its first K / V block as
+// soon as a ring stage is free - both under the current item's softmax.  All barrier parities follow running counters.
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out,
-                    const int32_t* __restrict__ key_len, int T, int heads) {
+                    const int32_t* __restrict__ key_len, int T, int heads, int tiles_q, int total_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint64_t* q_full = bars + 0;
@@ -52,11 +56,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
   uint64_t* p_empty = bars + 7;
   uint64_t* o_full = bars + 8;
   uint64_t* o_empty = bars + 9;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* q_empty = bars + 10;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role dispatch
-  const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
   const int H = heads * HD;
+  // item -> (query tile fastest, head, utterance): neighbouring CTAs share K / V of one (head, utterance) in L2
+  auto decode = [&](int item, int& q0, int& h, int& b) {
+    const int qt = item % tiles_q;
+    const int rest = item / tiles_q;
+    q0 = qt * QT;
+    h = rest % heads;
+    b = rest / heads;
+  };
+  auto blocks_of = [&](int b) {
+    const int kl = key_len ? max(1, min(key_len[b], T)) : T;
+    return kl;
+  };
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) asm volatile("trap;");  // the swizzled tiles need 1024-byte alignment
@@ -71,6 +87,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     mbar_init(o_empty, 128);
+    mbar_init(q_empty, 1);
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -85,23 +102,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
   const uint32_t tmem_base = *tmem_ptr;
   sib::pdl_wait();                 // PDL: the prologue above overlapped the previous kernel's tail
   sib::pdl_launch_dependents();
-  const int kl = key_len ? max(1, min(key_len[b], T)) : T;
-  const int nblk = (kl + KB - 1) / KB;
 
   if (warp == 4) {
     // ===================== TMA producer (whole warp in the loop, one elected lane issues) =====================
     const uint32_t issuer = elect_one_sync();
-    if (issuer) {
-      mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(smem + SM_Q, &map_qkv, q_full, h * HD, q0, b);
-    }
-    for (int j = 0; j < nblk; ++j) {
-      const int s = j & 1;
-      mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+    uint32_t g = 0, it = 0;                     // running K/V block counter, running item counter
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      int q0, h, b;
+      decode(item, q0, h, b);
+      const int nblk = (blocks_of(b) + KB - 1) / KB;
+      mbar_wait(q_empty, (it & 1) ^ 1);         // the S MMAs of the previous item have read Q
       if (issuer) {
-        mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        tma_load_3d(smem + SM_K + s * TILE_BYTES, &map_qkv, &kv_full[s], H + h * HD, j * KB, b);
-        tma_load_3d(smem + SM_V + s * TILE_BYTES, &map_qkv, &kv_full[s], 2 * H + h * HD, j * KB, b);
+        mbar_expect_tx(q_full, TILE_BYTES);
+        tma_load_3d(smem + SM_Q, &map_qkv, q_full, h * HD, q0, b);
+      }
+      for (int j = 0; j < nblk; ++j, ++g) {
+        const int s = (int)(g & 1);
+        mbar_wait(&kv_empty[s], ((g >> 1) & 1) ^ 1);
+        if (issuer) {
+          mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+          tma_load_3d(smem + SM_K + s * TILE_BYTES, &map_qkv, &kv_full[s], H + h * HD, j * KB, b);
+          tma_load_3d(smem + SM_V + s * TILE_BYTES, &map_qkv, &kv_full[s], 2 * H + h * HD, j * KB, b);
+        }
       }
     }
   } else if (warp == 5) {
@@ -113,11 +135,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
       const uint64_t qdesc = make_smem_desc(smem_u32(smem + SM_Q), DESC_HI);
       const uint64_t pdesc = make_smem_desc(smem_u32(smem + SM_P), DESC_HI);
       constexpr uint32_t IDESC_O = make_idesc_bf16(QT, HD, /*b_mn_major=*/1);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      int q0, h, b;
+      decode(item, q0, h, b);
+      const int kl = blocks_of(b);
+      const int nblk = (kl + KB - 1) / KB;
+      mbar_wait(q_full, it & 1);
+      for (int j = 0; j < nblk; ++j, ++g) {
+        const int s = (int)(g & 1);
         const int nk16 = (min(KB, kl - j * KB) + 15) & ~15;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        mbar_wait(&kv_full[s], (g >> 1) & 1);
         tc_fence_after();
         // S = Q K^T.  (S of block j-1 has been consumed: the P V MMAs of j-1 were issued after p_full(j-1).)
         const uint64_t kdesc = make_smem_desc(smem_u32(smem + SM_K + s * TILE_BYTES), DESC_HI);
@@ -126,10 +154,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
 #pragma unroll
           for (int ks = 0; ks < HD / 16; ++ks) umma_bf16(tmem_u, qdesc + 2 * ks, kdesc + 2 * ks, idesc_s, ks > 0);
           umma_commit(s_full);
+          if (j == nblk - 1) umma_commit(q_empty);   // last use of Q by this item: the producer may fetch the next one
         }
         // O_blk = P V
-        mbar_wait(p_full, j & 1);
-        mbar_wait(o_empty, (j & 1) ^ 1);
+        mbar_wait(p_full, g & 1);
+        mbar_wait(o_empty, (g & 1) ^ 1);
         tc_fence_after();
         const uint64_t vdesc = make_smem_desc(smem_u32(smem + SM_V + s * TILE_BYTES), DESC_HI);
         if (issuer) {
@@ -144,6 +173,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
           umma_commit(p_empty);
         }
       }
+      }
     }
   } else {
     // ===================== softmax + output: thread r = query row r = TMEM lane r =====================
@@ -153,14 +183,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
     const uint32_t prow = smem_u32(smem + SM_P + r * 128);
     const uint32_t swz = (uint32_t)(r & 7);
     const float c = 0.125f * 1.4426950408889634f;  // d^-1/2 * log2(e)
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int q0, h, b;
+    decode(item, q0, h, b);
+    const int kl = blocks_of(b);
+    const int nblk = (kl + KB - 1) / KB;
     float o_acc[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < nblk; ++j) {
+    for (int j = 0; j < nblk; ++j, ++g) {
       const int nk = min(KB, kl - j * KB);
       const int nk16 = (nk + 15) & ~15;
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, g & 1);
       tc_fence_after();
       float mx = -INFINITY;
       for (int c0 = 0; c0 < nk16; c0 += 16) {
@@ -172,7 +208,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2((m_run - m_new) * c);   // exp2(-inf) = 0 on the first block
       const float mc = m_new * c;
-      mbar_wait(p_empty, (j & 1) ^ 1);                      // the P V MMAs of block j-1 have read P
+      mbar_wait(p_empty, (g & 1) ^ 1);                      // the P V MMAs of the previous block have read P
       float sum = 0.f;
       for (int c0 = 0; c0 < nk16; c0 += 16) {
         uint32_t v[16];
@@ -196,7 +232,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
       tc_fence_before();
       fence_async_smem();   // generic-proxy stores of P -> visible to the tensor core's async-proxy reads
       mbar_arrive(p_full);
-      mbar_wait(o_full, j & 1);
+      mbar_wait(o_full, g & 1);
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < HD; c0 += 16) {
@@ -218,6 +254,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
         for (int i = 0; i < 8; ++i) f[i] = o_acc[8 * u + i] * inv;
         dst[u] = pack8(f);
       }
+    }
     }
     tc_fence_before();
   }
@@ -250,9 +287,16 @@ int sib_attention_bf16_tc(const void* qkv, const int32_t* key_len, void* out, in
     }
     attr_set[dev] = true;
   }
-  dim3 grid(sib::ceil_div(t, QT), heads, batch);
+  const int tiles_q = sib::ceil_div(t, QT);
+  const int64_t items = (int64_t)tiles_q * heads * batch;
+  if (items >= (1ll << 31)) {
+    sib::set_error("sib_attention: too many work items");
+    return SIB_ERR_INVALID;
+  }
+  const int slots = 2 * sib_tc::sm_count_of_current_device();        // two persistent CTAs per SM
+  dim3 grid((unsigned)(items < slots ? items : slots));
   const cudaError_t le = sib::launch_pdl(attention_tc_kernel, grid, dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, map,
-                                         (__nv_bfloat16*)out, key_len, t, heads);
+                                         (__nv_bfloat16*)out, key_len, t, heads, tiles_q, (int)items);
   if (le != cudaSuccess) {
     sib::set_error("sib_attention: launch failed: %s", cudaGetErrorString(le));
     return SIB_ERR_CUDA;
