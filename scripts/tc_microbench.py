@@ -27,6 +27,9 @@ SHAPES = {
     "s1k11": (32, 2752, 256, 256, 11, 1, 1, True, True),
     "s2k1": (32, 22016, 128, 128, 1, 1, 1, False, False),          # data-movement floor of the stage-2 tiles (8 MMAs per tile)
     "s2k3c1": (32, 22016, 128, 128, 3, 1, 1, False, False),
+    "s2k3c1p": (32, 22016, 128, 128, 3, 1, 1, False, False, "pre"),   # first conv of a unit: leaky-relu applied to the A tile in smem
+    "s2k7c1p": (32, 22016, 128, 128, 7, 1, 1, False, False, "pre"),
+    "s1k3c1p": (32, 2752, 256, 256, 3, 1, 1, False, False, "pre"),
     "s2k3c2": (32, 22016, 128, 128, 3, 1, 1, True, True),
     "s2k11c2": (32, 22016, 128, 128, 11, 5, 1, True, True),
     "s2k3c2n": (32, 22016, 128, 128, 3, 1, 1, True, False),     # second conv of a unit whose consumer activates its own input
@@ -53,6 +56,7 @@ def main():
     for name, spec in SHAPES.items():
         B, T, Cin, Cout, k, dil, stride, res, yact = spec[:9]
         act = ops.ACT_GELU if len(spec) > 9 and spec[9] == "gelu" else ops.ACT_NONE
+        pre = dict(pre_slope=0.1, post_act=ops.ACT_LRELU, post_slope=0.1) if len(spec) > 9 and spec[9] == "pre" else {}
         if a.only and name not in a.only.split(","):
             continue
         t_out = (T - k) // stride + 1 if stride > 1 else T
@@ -69,7 +73,7 @@ def main():
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.conv1d(x, w, bias, y, taps, stride=stride, residual=r, y_act=y2, act2_slope=0.1, post_act=act)
+            ops.conv1d(x, w, bias, y, taps, stride=stride, residual=r, y_act=y2, act2_slope=0.1, **(pre or dict(post_act=act)))
             e1.record()
             torch.cuda.synchronize()
             if it >= 2:
