@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SIB_ABI_VERSION 1
+#define SIB_ABI_VERSION 2
 #define SIB_MAX_TAPS 128
 
 enum sib_status { SIB_OK = 0, SIB_ERR_INVALID = 1, SIB_ERR_CUDA = 2, SIB_ERR_UNSUPPORTED = 3 };
@@ -143,9 +143,10 @@ int sib_l2_argmin_f32(const float* f, const float* mu, int m, int k, int d, int6
  * NARROW output (n <= 128), w [k][n] (= sib_conv1d_f32 layout of a linear layer); one CTA per row. */
 int sib_linear_skinny_f32(const float* x, const float* w, const float* bias, float* y, int m, int k, int n,
                           sib_stream_t stream);
-/* a13: mel[b,:,pos[b]+i] = cc[labels[off[b]+i]] + center, i < len[b]; mel is channels-first [B,D,T] (predict.py:184-187) */
+/* a13: mel[b,:,pos[b]+i] = cc[labels[off[b]+i]] + center, i < len[b]; mel is channels-first [B,D,T] (predict.py:184-187).
+ * cc has k rows; a label outside [0, k) is a device-side assert (printf + trap), as torch indexing does. */
 int sib_paste_centroids_f32(float* mel, int batch, int d, int t, const float* cc, const float* center,
-                            const int64_t* labels, const int32_t* pos, const int32_t* len, const int32_t* off,
+                            const int64_t* labels, const int32_t* pos, const int32_t* len, const int32_t* off, int k,
                             sib_stream_t stream);
 /* a14: extend_mel (inference_modified.py:16-19): linear resize along time by 441/256, align_corners=False.
  * in channels-first [B,D,T]; out channels-first [B,D,Tm] (frame_major=0) or frame-major [B,Tm,D] (1). */
@@ -153,10 +154,16 @@ int sib_extend_mel_f32(const float* in, float* out, int batch, int d, int t, int
                        sib_stream_t stream);
 /* [B,C,T] <-> [B,T,C] */
 int sib_transpose_f32(const float* in, float* out, int batch, int rows, int cols, sib_stream_t stream);
-/* a18 front (I_da/src/model.py:141-172): out[b,t,:] = emb_c[code[b,t]] | emb_p[zp[b,t/rep]] | spk[b]  (frame-major) */
+/* a18 front (I_da/src/model.py:141-172): out[b,t,:] = emb_c[code[b,t]] | emb_p[zp[b,t/rep]] | spk[b]  (frame-major).
+ * emb_c has n_codes rows, emb_p n_bins rows; an index outside its table is a device-side assert, as nn.Embedding does. */
 int sib_embed_concat_f32(const int64_t* code, const int64_t* zp, const float* spk, const float* emb_c,
-                         const float* emb_p, float* out, int batch, int t, int t_p, int e, int e_spk,
-                         sib_stream_t stream);
+                         const float* emb_p, float* out, int batch, int t, int t_p, int e, int e_spk, int n_codes,
+                         int n_bins, sib_stream_t stream);
+/* weight-norm folding (`remove_weight_norm()` I_ea/hifi_gan/models.py:125-132, I_da/src/models.py:227-233: dim 0;
+ * HF pos-conv weight_norm(dim=2) HF:59-78): w = v * (g / ||v||).  v, w [outer][inner] fp32.
+ * norm_dim_last = 0: one norm per row (g [outer]); 1: one norm per LAST-axis index over all rows (g [inner]). */
+int sib_weight_norm_fold_f32(const float* v, const float* g, float* w, int outer, int inner, int norm_dim_last,
+                             sib_stream_t stream);
 /* a19: int16 = (int16)(int32)trunc(y*32768) (dataset.py:241-243, predict.py:125-127) */
 int sib_pack_int16_f32(const float* y, int16_t* out, int64_t n, sib_stream_t stream);
 
@@ -220,7 +227,7 @@ typedef struct sib_resunit_desc {
 int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const void* w1, const float* b1, const void* w2,
                      const float* b2, void* y, void* y_act /* nullable */, sib_stream_t stream);
 int sib_resunit_bf16_supported(int c, int k, int dilation, int accumulate, int has_y_act);
-int sib_conv1d_bf16_pre_act_supported(const sib_conv_desc* d);
+int sib_conv1d_bf16_pre_act_supported(const sib_conv_desc* d, int has_residual, int has_y_act);
 
 /* K-block geometry the kernel uses for c_in/groups: cc channels x tb taps per pipeline stage (cc*tb = 64). */
 int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb);

@@ -155,3 +155,18 @@ def kmeans_predict(feats: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
     (ties -> lowest k)."""
     d = (feats.double()[:, None, :] - centers.double()[None, :, :]).pow(2).sum(-1)
     return torch.argmin(d, dim=1)
+
+
+def kmeans_predict_f32(feats: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
+    """The same assignment in the arithmetic sklearn itself uses for float32 features (`_labels_inertia` ->
+    argmin_k (||mu_k||^2 - 2 f.mu_k), float32): pinned against `sklearn.cluster.KMeans.predict` by
+    oracle/make_golden.py:golden_kmeans.  Differs from `kmeans_predict` only on near-ties."""
+    f, mu = feats.float(), centers.float()
+    return torch.argmin((mu * mu).sum(1)[None, :] - 2.0 * (f @ mu.T), dim=1)
+
+
+def ida_emb_longtensor(emb):
+    """I_da/scripts/inpainting.py:233,239 (and src/dataset.py:437): the speaker d-vector reaches the generator as
+    `torch.LongTensor(emb)` - every component truncated toward zero; CodeGenerator.forward then concatenates it with
+    the float embeddings (type promotion back to float, src/model.py:139,170-172)."""
+    return torch.as_tensor(emb).to(torch.int64)

@@ -150,8 +150,10 @@ def golden_hifigan():
     from oracle.hifigan_ref import generator_forward
 
     res = {}
+    # V1 / V2 (ResBlock1) and V3 (ResBlock2, models.py:52-73): the three generator configs the reference ships
     for name, cfg, B, T, init in [("v1_unit", HifiCfg.v1(), 2, 6, "unit"), ("v1_ref", HifiCfg.v1(), 1, 5, "reference"),
-                                  ("tiny_unit", HifiCfg.tiny(), 2, 9, "unit")]:
+                                  ("tiny_unit", HifiCfg.tiny(), 2, 9, "unit"), ("v2_unit", HifiCfg.v2(), 2, 7, "unit"),
+                                  ("v3_unit", HifiCfg.v3(), 2, 11, "unit"), ("v3_ref", HifiCfg.v3(), 1, 6, "reference")]:
         params = make_generator_params(cfg, seed=1234, init=init)
         h = AttrDict(cfg.as_attrdict())
         gen = Generator(h)
@@ -241,6 +243,35 @@ def golden_glue():
         print("CodeGenerator import failed (parity unpinned for _upsample):", repr(e))
         res["upsample_pinned"] = np.array([0])
     np.savez_compressed(os.path.join(OUT, "glue_golden.npz"), **res)
+
+
+def golden_kmeans():
+    """a17: `kmeans_model.predict(feats)` (I_da/scripts/inpainting.py:204-205) with the REAL sklearn estimator
+    (joblib-loaded `KMeans` in the reference; here one whose fitted attributes are set directly - predict only reads
+    cluster_centers_).  Pins oracle.glue_ref.kmeans_predict (exact argmin in float64) and kmeans_predict_f32."""
+    import sklearn
+    from sklearn.cluster import KMeans
+    from oracle import glue_ref
+    res = {"sklearn_version": np.array(sklearn.__version__)}
+    for K, H, M in ((100, 768, 400), (500, 768, 600), (500, 1024, 300)):
+        g = torch.Generator().manual_seed(K + H)
+        mu = torch.randn(K, H, generator=g) * 0.5
+        # features near the centroids (as real HuBERT features are) plus plain noise rows: unambiguous and hard cases
+        idx = torch.randint(0, K, (M,), generator=g)
+        f = torch.cat([mu[idx[: M // 2]] + 0.3 * torch.randn(M // 2, H, generator=g), torch.randn(M - M // 2, H, generator=g) * 0.5])
+        km = KMeans(n_clusters=K, n_init=1)
+        km.cluster_centers_ = mu.numpy().astype(np.float32)
+        km._n_threads = 1
+        km.n_features_in_ = H
+        km._n_features_out = K
+        want = km.predict(f.numpy())
+        mine = glue_ref.kmeans_predict(f, mu).numpy()
+        mine32 = glue_ref.kmeans_predict_f32(f, mu).numpy()
+        agree, agree32 = float((want == mine).mean()), float((want == mine32).mean())
+        print(f"kmeans K={K} H={H}: sklearn {sklearn.__version__} predict vs oracle exact-argmin {agree:.4f}, vs f32 form {agree32:.4f}")
+        assert agree == 1.0, "oracle kmeans_predict differs from sklearn KMeans.predict"
+        res[f"labels_{K}_{H}"] = want.astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, "kmeans_golden.npz"), **res)
 
 
 def golden_mel():
@@ -352,6 +383,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     import_reference()
     golden_mask()
+    golden_kmeans()
     golden_glue()
     golden_mel()
     golden_hifigan()

@@ -88,6 +88,17 @@ class HifiCfg:
         return HifiCfg()
 
     @staticmethod
+    def v2() -> "HifiCfg":
+        """I_ea/hifi_gan/config_v2.json:11-15 (ResBlock1, 128 initial channels: stages of 64 / 32 / 16 / 8)."""
+        return HifiCfg(upsample_initial_channel=128)
+
+    @staticmethod
+    def v3() -> "HifiCfg":
+        """I_ea/hifi_gan/config_v3.json:2,11-15 (ResBlock2: two convs per block, models.py:52-73)."""
+        return HifiCfg(upsample_rates=(8, 8, 4), upsample_kernel_sizes=(16, 16, 8), upsample_initial_channel=256,
+                       resblock_kernel_sizes=(3, 5, 7), resblock_dilation_sizes=((1, 2), (2, 6), (3, 12)), resblock="2")
+
+    @staticmethod
     def ida() -> "HifiCfg":
         return HifiCfg(upsample_rates=(5, 4, 4, 2, 2), upsample_kernel_sizes=(11, 8, 8, 4, 4),
                        model_in_dim=384, num_embeddings=500)
@@ -210,8 +221,11 @@ def make_generator_params(cfg: HifiCfg, seed: int = 1234, init: str = "unit") ->
             n = i * len(cfg.resblock_kernel_sizes) + j
             for m in range(len(dil)):
                 # residual branches are kept small so the stack stays O(1)
-                put(f"resblocks.{n}.convs1.{m}", (ch, ch, rk), ch * rk)
-                put(f"resblocks.{n}.convs2.{m}", (ch, ch, rk), ch * rk * 4)
+                if cfg.resblock == "1":
+                    put(f"resblocks.{n}.convs1.{m}", (ch, ch, rk), ch * rk)
+                    put(f"resblocks.{n}.convs2.{m}", (ch, ch, rk), ch * rk * 4)
+                else:   # ResBlock2: one conv per dilation (models.py:55-61)
+                    put(f"resblocks.{n}.convs.{m}", (ch, ch, rk), ch * rk * 4)
     put("conv_post", (1, ch, 7), ch * 7)
     if cfg.num_embeddings:
         p["emb_c.weight"] = _randn(g, cfg.num_embeddings, cfg.embedding_dim)

@@ -66,10 +66,11 @@ _SIGS = {
     "sib_cos_argmax_f32": ([_P, _P, _I, _I, _I, _P, _P], _I),
     "sib_l2_argmin_f32": ([_P, _P, _I, _I, _I, _P, _P], _I),
     "sib_linear_skinny_f32": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
-    "sib_paste_centroids_f32": ([_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], _I),
+    "sib_paste_centroids_f32": ([_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P], _I),
     "sib_extend_mel_f32": ([_P, _P, _I, _I, _I, _I, _I, _P], _I),
     "sib_transpose_f32": ([_P, _P, _I, _I, _I, _P], _I),
-    "sib_embed_concat_f32": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
+    "sib_embed_concat_f32": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "sib_weight_norm_fold_f32": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "sib_pack_int16_f32": ([_P, _P, _L, _P], _I),
     "sib_mel_spectrogram_f32": ([_P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P], _I),
     "sib_mel_workspace_bytes": ([_I], C.c_size_t),
@@ -82,7 +83,7 @@ _SIGS = {
     "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16": ([C.POINTER(ResUnitDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16_supported": ([_I, _I, _I, _I, _I], _I),
-    "sib_conv1d_bf16_pre_act_supported": ([C.POINTER(ConvDesc)], _I),
+    "sib_conv1d_bf16_pre_act_supported": ([C.POINTER(ConvDesc), _I, _I], _I),
     "sib_conv1d_bf16_kblock": ([_I, C.POINTER(C.c_int), C.POINTER(C.c_int)], _I),
     "sib_layernorm": ([_P, _I, _P, _I, _P, _P, _P, _I, _L, _I, _F, _I, _P], _I),
     "sib_attention": ([_P, _I, _P, _P, _I, _I, _I, _I, _P], _I),
@@ -109,7 +110,7 @@ def lib():
             fn = getattr(l, name)  # AttributeError if the .so is stale
             fn.argtypes = args
             fn.restype = res
-        if l.sib_abi_version() != 1:
+        if l.sib_abi_version() != 2:
             raise SibError("libsib_b200.so ABI version mismatch; rebuild")
         _lib = l
     return _lib

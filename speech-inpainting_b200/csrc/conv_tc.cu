@@ -874,8 +874,11 @@ extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void
 }
 
 // 1 if sib_conv1d_bf16 would run this descriptor with its leaky-relu pre-activation (halo mode selected), else 0
-extern "C" int sib_conv1d_bf16_pre_act_supported(const sib_conv_desc* d) {
+// for a launch with / without a residual input and a second (activated) output: both enlarge the epilogue staging ring,
+// which can push a layer out of the halo mode - the dry run must see the same shared-memory budget as the launch
+extern "C" int sib_conv1d_bf16_pre_act_supported(const sib_conv_desc* d, int has_residual, int has_y_act) {
   if (!d || d->pre_act != SIB_ACT_LRELU) return 0;
   void* fake = reinterpret_cast<void*>(uintptr_t(4096));   // alignment checks only: nothing is dereferenced in a dry run
-  return conv1d_bf16_impl(d, fake, fake, nullptr, nullptr, fake, nullptr, nullptr, true) == SIB_OK ? 1 : 0;
+  return conv1d_bf16_impl(d, fake, fake, nullptr, has_residual ? fake : nullptr, fake, has_y_act ? fake : nullptr, nullptr,
+                          true) == SIB_OK ? 1 : 0;
 }

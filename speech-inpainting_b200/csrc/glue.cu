@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) assign_kernel(const float* __restrict__ v
 __global__ void paste_centroids_kernel(float* __restrict__ mel, int Dm, int T, const float* __restrict__ cc,
                                        const float* __restrict__ center, const int64_t* __restrict__ labels,
                                        const int32_t* __restrict__ pos, const int32_t* __restrict__ len,
-                                       const int32_t* __restrict__ off) {
+                                       const int32_t* __restrict__ off, int K) {
   const int b = blockIdx.y;
   const int L = len[b], p0 = pos[b];
   float* mb = mel + (int64_t)b * Dm * T;
@@ -85,6 +85,10 @@ __global__ void paste_centroids_kernel(float* __restrict__ mel, int Dm, int T, c
     const int c = i / L, f = i - c * L;
     if (p0 + f < 0 || p0 + f >= T) continue;
     const int64_t lab = labels[off[b] + f];
+    if (lab < 0 || lab >= K) {   // as nn.Embedding / tensor indexing: an out-of-range index is a device-side assert
+      printf("sib_paste_centroids_f32: label %lld outside the %d-entry codebook\n", (long long)lab, K);
+      __trap();
+    }
     mb[(int64_t)c * T + p0 + f] = cc[lab * Dm + c] + center[c];
   }
 }
@@ -136,12 +140,18 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 __global__ void embed_concat_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ zp,
                                     const float* __restrict__ spk, const float* __restrict__ emb_c,
                                     const float* __restrict__ emb_p, float* __restrict__ out, int T, int Tp, int E,
-                                    int Es) {
+                                    int Es, int n_codes, int n_bins) {
   const int b = blockIdx.y, t = blockIdx.x;
   const int W = 2 * E + Es;
   const int rep = T / Tp;  // _upsample repeats each pitch step T // Tp times (model.py:104)
   const int64_t ci = code[(int64_t)b * T + t];
   const int64_t pi = zp[(int64_t)b * Tp + min(t / rep, Tp - 1)];
+  if (ci < 0 || ci >= n_codes || pi < 0 || pi >= n_bins) {   // nn.Embedding raises a device assert in the same case
+    if (threadIdx.x == 0)
+      printf("sib_embed_concat_f32: code %lld / pitch bin %lld outside the %d / %d-row embedding tables\n", (long long)ci,
+             (long long)pi, n_codes, n_bins);
+    __trap();
+  }
   float* o = out + ((int64_t)b * T + t) * W;
   for (int i = threadIdx.x; i < W; i += blockDim.x) {
     float v;
@@ -202,11 +212,11 @@ extern "C" int sib_l2_argmin_f32(const float* f, const float* mu, int m, int k, 
 
 extern "C" int sib_paste_centroids_f32(float* mel, int batch, int d, int t, const float* cc, const float* center,
                                        const int64_t* labels, const int32_t* pos, const int32_t* len,
-                                       const int32_t* off, sib_stream_t stream) {
-  SIB_REQUIRE(mel && cc && center && labels && pos && len && off && batch > 0 && batch <= 65535 && d > 0 && t > 0,
+                                       const int32_t* off, int k, sib_stream_t stream) {
+  SIB_REQUIRE(mel && cc && center && labels && pos && len && off && batch > 0 && batch <= 65535 && d > 0 && t > 0 && k > 0,
               "sib_paste_centroids_f32: bad argument");
   paste_centroids_kernel<<<dim3(8, batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(mel, d, t, cc, center, labels,
-                                                                                        pos, len, off);
+                                                                                        pos, len, off, k);
   SIB_CHECK_LAUNCH("sib_paste_centroids_f32");
   return SIB_OK;
 }
@@ -239,13 +249,14 @@ extern "C" int sib_transpose_f32(const float* in, float* out, int batch, int row
 
 extern "C" int sib_embed_concat_f32(const int64_t* code, const int64_t* zp, const float* spk, const float* emb_c,
                                     const float* emb_p, float* out, int batch, int t, int t_p, int e, int e_spk,
-                                    sib_stream_t stream) {
-  SIB_REQUIRE(code && zp && spk && emb_c && emb_p && out && batch > 0 && batch <= 65535 && t > 0 && t_p > 0 && e > 0,
+                                    int n_codes, int n_bins, sib_stream_t stream) {
+  SIB_REQUIRE(code && zp && spk && emb_c && emb_p && out && batch > 0 && batch <= 65535 && t > 0 && t_p > 0 && e > 0 &&
+                  n_codes > 0 && n_bins > 0,
               "sib_embed_concat_f32: bad argument");
   SIB_REQUIRE(t >= t_p && (t - t_p * (t / t_p)) / (t / t_p) == 0,
               "sib_embed_concat_f32: misaligned condition lengths t=%d t_p=%d (model.py:110-114)", t, t_p);
   embed_concat_kernel<<<dim3(t, batch), 128, 0, static_cast<cudaStream_t>(stream)>>>(code, zp, spk, emb_c, emb_p, out,
-                                                                                     t, t_p, e, e_spk);
+                                                                                     t, t_p, e, e_spk, n_codes, n_bins);
   SIB_CHECK_LAUNCH("sib_embed_concat_f32");
   return SIB_OK;
 }
@@ -317,5 +328,62 @@ extern "C" int sib_linear_skinny_f32(const float* x, const float* w, const float
   SIB_REQUIRE(smem <= 48 * 1024, "sib_linear_skinny_f32: k=%d too large", k);
   linear_skinny_kernel<<<m, SK_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, k, n);
   SIB_CHECK_LAUNCH("sib_linear_skinny_f32");
+  return SIB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// torch weight_norm folded on the device: w = v * (g / ||v||), the norm taken over every dimension but `dim`
+// (remove_weight_norm(), I_ea/hifi_gan/models.py:125-132 -> dim 0, g [C0,1,1]; HF pos-conv HF:59-78 -> dim 2, g [1,1,k]).
+// One launch per tensor at load / pack time instead of the pow / sum / sqrt / div / mul chain of eager ops.
+namespace {
+// dim 0: v [rows][inner], one CTA per row
+__global__ void __launch_bounds__(256) weight_norm_rows_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                               float* __restrict__ w, int inner) {
+  __shared__ float part[8];
+  const int r = blockIdx.x;
+  const float* vr = v + (int64_t)r * inner;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < inner; i += 256) s = fmaf(vr[i], vr[i], s);
+  s = sib::warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += part[i];
+  const float scale = g[r] / sqrtf(tot);
+  for (int i = threadIdx.x; i < inner; i += 256) w[(int64_t)r * inner + i] = vr[i] * scale;
+}
+// last dim: v [outer][k]; CTA = 32 consecutive k (lanes, coalesced) x 8 warps striding the outer index
+__global__ void __launch_bounds__(256) weight_norm_last_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                               float* __restrict__ w, int outer, int k) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (j < k)
+    for (int o = wi; o < outer; o += 8) {
+      const float x = v[(int64_t)o * k + j];
+      s = fmaf(x, x, s);
+    }
+  part[wi][lane] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += part[i][lane];
+  if (j < k) {
+    const float scale = g[j] / sqrtf(tot);
+    for (int o = wi; o < outer; o += 8) w[(int64_t)o * k + j] = v[(int64_t)o * k + j] * scale;
+  }
+}
+}  // namespace
+
+extern "C" int sib_weight_norm_fold_f32(const float* v, const float* g, float* w, int outer, int inner, int norm_dim_last,
+                                        sib_stream_t stream) {
+  SIB_REQUIRE(v && g && w && outer > 0 && inner > 0, "sib_weight_norm_fold_f32: bad argument");
+  if (norm_dim_last)
+    weight_norm_last_kernel<<<sib::ceil_div(inner, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(v, g, w, outer, inner);
+  else
+    weight_norm_rows_kernel<<<outer, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, g, w, inner);
+  SIB_CHECK_LAUNCH("sib_weight_norm_fold_f32");
   return SIB_OK;
 }

@@ -17,11 +17,11 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .hubert import _StateHolder
+from .module import SibModule
 from .ops import SibError
 
 
-class F0Quantizer(_StateHolder):
+class F0Quantizer(SibModule):
     def __init__(self, f0_quantizer: dict):
         super().__init__()
         enc = dict(f0_quantizer["f0_encoder_params"])
@@ -44,6 +44,22 @@ class F0Quantizer(_StateHolder):
         if self.emb_width != self.out_width:
             raise SibError("F0Quantizer: encoder output width must equal the codebook width")
         self.hop = self.stride_t ** self.down_t
+        for name, shape in self._conv_shapes().items():
+            self._add_param(name + ".weight", torch.empty(shape).normal_(0.0, 0.02))
+            self._add_param(name + ".bias", torch.zeros(shape[0]))
+        self._add_param("vq.level_blocks.0.k", torch.randn(self.l_bins, self.emb_width))
+
+    def _conv_shapes(self):
+        """Conv1d weight shapes of the Jukebox encoder (jukebox.py:89-110, resnet.py:36-52)."""
+        shapes = {}
+        for i in range(self.down_t):
+            n = f"encoder.level_blocks.0.model.{i}"
+            shapes[n + ".0"] = (self.width, self.in_width if i == 0 else self.width, 2 * self.stride_t)
+            for d in range(self.depth):
+                shapes[f"{n}.1.model.{d}.model.1"] = (self.state, self.width, 3)
+                shapes[f"{n}.1.model.{d}.model.3"] = (self.width, self.state, 1)
+        shapes[f"encoder.level_blocks.0.model.{self.down_t}"] = (self.out_width, self.width, 3)
+        return shapes
 
     def _dilation(self, d):
         return self.growth ** (d if self.cycle is None else d % int(self.cycle))
@@ -60,9 +76,8 @@ class F0Quantizer(_StateHolder):
     def _expected_keys(self):
         return [n + s for n in self._conv_names() for s in (".weight", ".bias")] + ["vq.level_blocks.0.k"]
 
-    def load_state_dict(self, sd, strict: bool = True):
-        sd = {k: v for k, v in sd.items() if not k.startswith("decoder.")}
-        return super().load_state_dict(sd, strict)
+    def _adapt_state_dict(self, sd):
+        return {k: v for k, v in sd.items() if not k.startswith("decoder.")}   # training-only half of the VQ-VAE
 
     def _pack(self):
         if self._packed is None:
@@ -75,7 +90,12 @@ class F0Quantizer(_StateHolder):
         self._require_cuda()
         if f0.dim() != 3 or f0.shape[1] != self.in_width:
             raise SibError(f"F0Quantizer: f0 must be [B, {self.in_width}, L], got {tuple(f0.shape)}")
-        P, sd, dev = self._pack(), self._sd, self._device
+        dev = self._device
+        with torch.cuda.device(dev):
+            return self._encode_features(f0, dev)
+
+    def _encode_features(self, f0, dev):
+        P, sd = self._pack(), self._sd
         x = f0.to(dev, torch.float32)
         x = x.transpose(1, 2).contiguous() if self.in_width > 1 else x.reshape(x.shape[0], x.shape[2], 1).contiguous()
         B, L, _ = x.shape
@@ -106,8 +126,9 @@ class F0Quantizer(_StateHolder):
         """f0 [B, 1, L] -> pitch bins z_p int64 [B, L / hop] (model.py:148-152)."""
         h = self.encode_features(f0)
         B, T, W = h.shape
-        z = torch.empty(B * T, device=h.device, dtype=torch.int64)
-        ops.l2_argmin(h.view(B * T, W), self._sd["vq.level_blocks.0.k"], z)
+        with torch.cuda.device(h.device):
+            z = torch.empty(B * T, device=h.device, dtype=torch.int64)
+            ops.l2_argmin(h.view(B * T, W), self._sd["vq.level_blocks.0.k"], z)
         return z.view(B, T)
 
-    __call__ = encode
+    forward = encode

@@ -17,7 +17,7 @@ from types import SimpleNamespace
 import torch
 
 from . import ops
-from .hubert import _StateHolder
+from .module import SibModule
 from .ops import ACT_NONE, ACT_TANH, Plan, SibError
 
 LRELU_SLOPE = 0.1  # models.py:9
@@ -42,7 +42,7 @@ def _hget(h, name, default=None):
     return getattr(h, name, default)
 
 
-class Generator(_StateHolder):
+class Generator(SibModule):
     def __init__(self, h, precision: str = "fp32"):
         super().__init__()
         self.h = h
@@ -59,12 +59,18 @@ class Generator(_StateHolder):
         self.num_upsamples = len(self.upsample_rates)
         self.total_upsample = math.prod(self.upsample_rates)
         self._weight_norm_removed = False
-        self._plans = {}
         self.use_cuda_graph = False
         self.use_fused_resunits = True   # bf16 arm: fused ResBlock1 units on the narrow stages (A/B switch)
         # bf16 arm: unfused convs apply the leaky-relu that precedes them to their A tile in shared memory, so producers
         # stop writing an activated copy of every tensor (A/B switch, SIB_SMEM_PREACT=0)
         self.use_smem_preact = os.environ.get("SIB_SMEM_PREACT", "1") != "0"
+        # parameters under the reference's checkpoint names, WITH weight-norm (weight_g / weight_v) as `Generator.__init__`
+        # creates them (models.py:82-105): 234 tensors for V1
+        for name, shape in self._conv_shapes().items():
+            v = torch.empty(shape).normal_(0.0, 0.01)                       # init_weights, utils.py:24-32
+            self._add_param(name + ".weight_v", v)
+            self._add_param(name + ".weight_g", v.pow(2).sum(dim=(1, 2), keepdim=True).sqrt())
+            self._add_param(name + ".bias", torch.zeros(shape[1] if name.startswith("ups.") else shape[0]))
 
     # ---- state
     def _conv_names(self):
@@ -79,6 +85,23 @@ class Generator(_StateHolder):
                     names += [f"resblocks.{n}.convs.{m}" for m in range(len(self.rb_dilations[j]))]
         return names + ["conv_post"]
 
+    def _conv_shapes(self):
+        """torch weight shape of every conv: Conv1d [Cout, Cin, k], ConvTranspose1d [Cin, Cout, k] (models.py:82-105)."""
+        shapes = {"conv_pre": (self.c0, self.in_dim, 7)}
+        ch = self.c0
+        for i, k in enumerate(self.upsample_kernel_sizes):
+            cin, ch = self.c0 // (2 ** i), self.c0 // (2 ** (i + 1))
+            shapes[f"ups.{i}"] = (cin, ch, k)
+            for j, rk in enumerate(self.rb_kernels):
+                n = i * self.num_kernels + j
+                for m in range(len(self.rb_dilations[j])):
+                    if self.resblock == "1":
+                        shapes[f"resblocks.{n}.convs1.{m}"] = shapes[f"resblocks.{n}.convs2.{m}"] = (ch, ch, rk)
+                    else:
+                        shapes[f"resblocks.{n}.convs.{m}"] = (ch, ch, rk)
+        shapes["conv_post"] = (1, ch, 7)
+        return shapes
+
     def _extra_keys(self):
         return []
 
@@ -88,28 +111,41 @@ class Generator(_StateHolder):
             keys += [n + ".bias", n + ".weight_g", n + ".weight_v"]
         return keys + self._extra_keys()
 
-    def load_state_dict(self, sd, strict: bool = True):
-        folded = {k for k in sd if k.endswith(".weight") and not k.startswith("emb_")}
-        if folded:  # checkpoint saved after remove_weight_norm()
-            exp = {n + s for n in self._conv_names() for s in (".bias", ".weight")} | set(self._extra_keys())
-            if strict and set(sd.keys()) != exp:
-                raise RuntimeError(f"Error(s) in loading state_dict: missing {sorted(exp - set(sd))[:8]} "
-                                   f"unexpected {sorted(set(sd) - exp)[:8]}")
-            self._sd = {k: v.detach().to(self._device, torch.float32).contiguous() for k, v in sd.items()}
-            self._packed = None
-            return SimpleNamespace(missing_keys=[], unexpected_keys=[])
-        return super().load_state_dict(sd, strict)
+    def _adapt_state_dict(self, sd):
+        folded = any(k.endswith(".weight") and not k.startswith(("emb_", "fo_vqvae.")) for k in sd)
+        if folded and not self._weight_norm_removed:   # checkpoint saved after remove_weight_norm(): same structure here
+            self._drop_weight_norm(fold=False)
+        return sd
 
-    def remove_weight_norm(self):
-        """models.py:125-132.  Folding happens at pack time; this only records the call."""
+    def _drop_weight_norm(self, fold: bool):
+        """Replace (weight_g, weight_v) by `weight`, as torch's remove_weight_norm does (156 tensors left for V1)."""
+        sd = self._sd
+        for n in self._conv_names():
+            if not self._has_param(n + ".weight_v"):
+                continue
+            v, g = sd[n + ".weight_v"], sd[n + ".weight_g"]
+            w = ops.weight_norm_fold(v, g.reshape(-1), dim=0) if fold else torch.empty_like(v)
+            # torch registers `weight` first, then bias stays: key order is irrelevant to load_state_dict
+            self._del_param(n + ".weight_g")
+            self._del_param(n + ".weight_v")
+            self._add_param(n + ".weight", w)
         self._weight_norm_removed = True
 
+    def remove_weight_norm(self):
+        """models.py:125-132: fold weight = v * (g / ||v||) (one `sib_weight_norm_fold_f32` launch per conv) and replace
+        the weight-norm pair by the folded tensor, so that `state_dict()` afterwards is the reference's 156-key one."""
+        if self._weight_norm_removed:
+            return
+        self._require_cuda()
+        with torch.cuda.device(self._device):
+            self._drop_weight_norm(fold=True)
+
     def _weight(self, name):
-        """weight = g * v / ||v|| with the norm over all dims but 0 (torch weight_norm dim=0)."""
-        if name + ".weight" in self._sd:
-            return self._sd[name + ".weight"]
-        g, v = self._sd[name + ".weight_g"], self._sd[name + ".weight_v"]
-        return g * v / v.pow(2).sum(dim=(1, 2), keepdim=True).sqrt()
+        """Folded conv weight: `weight` after remove_weight_norm(), else v * (g / ||v||) folded on the device."""
+        sd = self._sd
+        if name + ".weight" in sd:
+            return sd[name + ".weight"]
+        return ops.weight_norm_fold(sd[name + ".weight_v"], sd[name + ".weight_g"].reshape(-1), dim=0)
 
     def _pack(self):
         if self._packed is not None:
@@ -131,7 +167,7 @@ class Generator(_StateHolder):
         elif self.precision != "fp32":
             raise SibError(f"unknown precision {self.precision!r} (fp32 | bf16)")
         self._packed = P
-        self._plans = {}
+        self._plans.clear()
         return P
 
     # ---- plan (bf16 / tcgen05 arm)
@@ -174,8 +210,10 @@ class Generator(_StateHolder):
             pre = self.use_smem_preact
             c_prev = [self.c0] + chans[:-1]
             t_prev = [Tm] + lens[:-1]
+            # (queried for the larger launch - with the activated second output - so that the answer holds either way)
             ups_pa = [pre and i > 0 and ops.conv_pre_act_supported(B, t_prev[i], c_prev[i], u * chans[i], P[f"ups.{i}.taps"],
-                                                                   LRELU_SLOPE) for i, u in enumerate(self.upsample_rates)]
+                                                                   LRELU_SLOPE, has_y_act=True)
+                      for i, u in enumerate(self.upsample_rates)]
             cur, cur_act = None, cur_act     # conv_pre wrote lrelu(y) only (nobody needs its raw output)
             for i, u in enumerate(self.upsample_rates):
                 C_, L_ = chans[i], lens[i]
@@ -194,8 +232,11 @@ class Generator(_StateHolder):
                         need_act = (j == self.num_kernels - 1 and next_needs_act) if last_m else (not srow[m + 1])
                         row[m] = (self.resblock == "1" and self.use_fused_resunits and
                                   ops.resunit_supported(C_, rk, dils[m], last_m and j > 0, need_act))
+                        # ResBlock1's first conv has neither residual nor second output; a ResBlock2 conv has both
+                        rb2 = self.resblock != "1"
                         srow[m] = row[m] or (pre and ops.conv_pre_act_supported(
-                            B, L_, C_, C_, ops.conv_taps(rk, dils[m], get_padding(rk, dils[m])), LRELU_SLOPE))
+                            B, L_, C_, C_, ops.conv_taps(rk, dils[m], get_padding(rk, dils[m])), LRELU_SLOPE,
+                            has_residual=rb2, has_y_act=rb2))
                     fused.append(row)
                     self_act.append(srow)
                 need_up_act = not all(sa[0] for sa in self_act)
@@ -331,23 +372,22 @@ class Generator(_StateHolder):
         if Cin != self.in_dim:
             raise RuntimeError(f"expected input with {self.in_dim} channels, got {Cin}")  # torch conv1d raises RuntimeError too
         key = (B, Tm, frame_major_in)
-        self._pack()
-        io = self._plans.get(key)
-        if io is None:
-            io = self._plans[key] = self._build_plan(B, Tm, frame_major_in)
-        (io.x if frame_major_in else io.x_cf).copy_(x.to(self._device, torch.float32), non_blocking=True)
-        io.plan.run()
+        with torch.cuda.device(self._device):   # the C side launches on the current device: make it this module's
+            self._pack()
+            io = self._cached_plan(key, lambda: self._build_plan(B, Tm, frame_major_in))
+            (io.x if frame_major_in else io.x_cf).copy_(x.to(self._device, torch.float32), non_blocking=True)
+            io.plan.run()
         return io
 
     def forward(self, x):
-        """x [B, in_dim, Tm] (channels-first, as the reference) -> [B, 1, Tm*prod(rates)]."""
+        """x [B, in_dim, Tm] (channels-first, as the reference) -> a fresh [B, 1, Tm*prod(rates)] tensor."""
         return self._run(x).y.clone()
 
-    def forward_frame_major(self, x):
-        """x [B, Tm, in_dim] frame-major (what extend_mel / embed_concat kernels emit) -> same output."""
-        return self._run(x, frame_major_in=True).y.clone()
-
-    __call__ = forward
+    def forward_frame_major(self, x, clone: bool = True):
+        """x [B, Tm, in_dim] frame-major (what extend_mel / embed_concat kernels emit) -> same output.  clone=False
+        returns the plan's own output buffer (valid until the next call with this shape)."""
+        y = self._run(x, frame_major_in=True).y
+        return y.clone() if clone else y
 
 
 class CodeGenerator(Generator):
@@ -364,7 +404,13 @@ class CodeGenerator(Generator):
         self.embedding_dim = int(_hget(h, "embedding_dim"))
         fq = _hget(h, "f0_quantizer") or {}
         self.f0_bins = int(fq.get("f0_vq_params", {}).get("l_bins", 20)) if isinstance(fq, dict) else 20
+        self.n_speakers = int(_hget(h, "num_speakers", 200) or 200)
+        E = self.embedding_dim
+        self._add_param("emb_c.weight", torch.randn(self.num_embeddings, E))      # nn.Embedding default init N(0, 1)
+        self._add_param("emb_p.weight", torch.randn(self.f0_bins, E))
+        self._add_param("emb_s.weight", torch.randn(self.n_speakers, E))          # unused on the d-vector path (model.py:139)
         self.fo_vqvae = None
+        self._f0_loaded = False
         if isinstance(fq, dict) and "f0_encoder_params" in fq:
             from .f0vq import F0Quantizer
             self.fo_vqvae = F0Quantizer(fq)
@@ -372,30 +418,35 @@ class CodeGenerator(Generator):
     def _extra_keys(self):
         return ["emb_c.weight", "emb_p.weight", "emb_s.weight"]
 
-    def load_state_dict(self, sd, strict: bool = True):
-        fo = {k[len("fo_vqvae."):]: v for k, v in sd.items() if k.startswith("fo_vqvae.")}
-        if fo and self.fo_vqvae is not None:
-            self.fo_vqvae.load_state_dict(fo, strict)
-        sd = {k: v for k, v in sd.items() if not k.startswith("fo_vqvae.")}
-        return super().load_state_dict(sd, strict)
+    def _adapt_state_dict(self, sd):
+        sd = super()._adapt_state_dict(sd)
+        if "emb_s.weight" in sd and tuple(sd["emb_s.weight"].shape) != tuple(self._sd["emb_s.weight"].shape):
+            self._add_param("emb_s.weight", torch.empty_like(sd["emb_s.weight"], device=self._device))
+        fo = [k for k in sd if k.startswith("fo_vqvae.")]
+        if self.fo_vqvae is None:
+            for k in fo:            # a checkpoint with the frozen f0 VQ-VAE loaded into a generator configured without it
+                sd.pop(k)
+        else:
+            for k in [k for k in fo if k.startswith("fo_vqvae.decoder.")]:   # training-only half of the VQ-VAE
+                sd.pop(k)
+            if fo:
+                self._f0_loaded = True
+            else:                   # generator-only checkpoint: keep whatever the quantiser holds
+                sd.update({"fo_vqvae." + k: v for k, v in self.fo_vqvae.state_dict().items()})
+        return sd
 
     def load_f0_quantizer(self, sd, strict: bool = True):
         """`torch.load(h.f0_quantizer_path)["generator"]` (model.py:66-69)."""
         if self.fo_vqvae is None:
             raise SibError("this CodeGenerator was configured without an f0_quantizer")
+        self._f0_loaded = True
         return self.fo_vqvae.load_state_dict(sd, strict)
-
-    def to(self, device=None, *a, **k):
-        super().to(device, *a, **k)
-        if self.fo_vqvae is not None:
-            self.fo_vqvae.to(device, *a, **k)
-        return self
 
     def forward(self, **kwargs):
         self._require_cuda()
         code = kwargs["code"]
         if "f0_code" not in kwargs:
-            if kwargs.get("f0") is None or self.fo_vqvae is None or not self.fo_vqvae._sd:
+            if kwargs.get("f0") is None or self.fo_vqvae is None or not self._f0_loaded:
                 raise SibError("CodeGenerator needs f0= together with loaded fo_vqvae weights (load_state_dict with "
                                "fo_vqvae.* keys or load_f0_quantizer), or precomputed bins through f0_code=")
             kwargs = dict(kwargs, f0_code=self.fo_vqvae.encode(kwargs["f0"]))   # model.py:148-152
@@ -409,8 +460,7 @@ class CodeGenerator(Generator):
         Tmax = max(T, zp.shape[1])
         if Tmax != T:
             raise SibError("pitch series longer than the code series is not produced by the reference pipeline")
-        x = torch.empty(B, T, 2 * E + emb.shape[1], device=dev, dtype=torch.float32)
-        ops.embed_concat(code, zp, emb, self._sd["emb_c.weight"], self._sd["emb_p.weight"], x)
+        with torch.cuda.device(dev):
+            x = torch.empty(B, T, 2 * E + emb.shape[1], device=dev, dtype=torch.float32)
+            ops.embed_concat(code, zp, emb, self._sd["emb_c.weight"], self._sd["emb_p.weight"], x)
         return self.forward_frame_major(x)
-
-    __call__ = forward

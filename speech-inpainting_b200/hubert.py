@@ -17,6 +17,7 @@ from types import SimpleNamespace
 import torch
 
 from . import ops
+from .module import SibModule, _Node
 from .ops import ACT_GELU, ACT_NONE, Plan, SibError
 
 
@@ -100,58 +101,65 @@ def expected_hubert_keys(cfg: HubertConfig, prefix: str = "", new_wn_names: bool
     return [prefix + k for k in keys]
 
 
-class _StateHolder:
-    """Minimal nn.Module-like surface: load_state_dict / state_dict / parameters / to / eval."""
-
-    def __init__(self):
-        self._sd = {}
-        self._device = torch.device("cpu")
-        self._packed = None
-        self.training = False
-
-    def load_state_dict(self, sd, strict: bool = True):
-        exp = set(self._expected_keys())
-        got = set(sd.keys())
-        alt = {k.replace("parametrizations.weight.original0", "weight_g").replace(
-            "parametrizations.weight.original1", "weight_v") for k in exp}
-        if strict and got != exp and got != alt:
-            missing, extra = sorted((exp - got) & (alt - got)), sorted(got - exp - alt)
-            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:8]} unexpected {extra[:8]}")
-        self._sd = {k: v.detach().to(self._device, torch.float32).contiguous() for k, v in sd.items()}
-        self._packed = None
-        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
-
-    def state_dict(self):
-        return dict(self._sd)
-
-    def parameters(self):
-        return iter(self._sd.values())
-
-    def to(self, device=None, *a, **k):
-        if device is not None and not isinstance(device, torch.dtype):
-            self._device = torch.device(device)
-            self._sd = {k_: v.to(self._device) for k_, v in self._sd.items()}
-            self._packed = None
-        return self
-
-    def cuda(self, device=None):
-        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
-
-    def eval(self):
-        self.training = False
-        return self
-
-    def train(self, mode: bool = True):
-        if mode:
-            raise SibError("this is an inference-only path (SURVEY 2: training is out of scope)")
-        return self
-
-    def _require_cuda(self):
-        if self._device.type != "cuda":
-            raise SibError("module must be moved to a CUDA device before forward (no CPU fallback)")
+def hubert_param_shapes(cfg: HubertConfig, prefix: str = ""):
+    """Shape of every tensor in an HF `HubertModel.state_dict()` for this config (HF:106-231, 45-92, 262-405)."""
+    H, F = cfg.hidden_size, cfg.intermediate_size
+    K, G = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+    shapes, cin = {}, 1
+    for i, (c, k) in enumerate(zip(cfg.conv_dim, cfg.conv_kernel)):
+        b = f"feature_extractor.conv_layers.{i}."
+        shapes[b + "conv.weight"] = (c, cin, k)
+        if cfg.conv_bias:
+            shapes[b + "conv.bias"] = (c,)
+        if cfg.feat_extract_norm == "layer" or i == 0:
+            shapes[b + "layer_norm.weight"] = shapes[b + "layer_norm.bias"] = (c,)
+        cin = c
+    shapes["feature_projection.layer_norm.weight"] = shapes["feature_projection.layer_norm.bias"] = (cin,)
+    shapes["feature_projection.projection.weight"], shapes["feature_projection.projection.bias"] = (H, cin), (H,)
+    shapes["encoder.pos_conv_embed.conv.bias"] = (H,)
+    shapes["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = (1, 1, K)
+    shapes["encoder.pos_conv_embed.conv.parametrizations.weight.original1"] = (H, H // G, K)
+    shapes["encoder.layer_norm.weight"] = shapes["encoder.layer_norm.bias"] = (H,)
+    for l in range(cfg.num_hidden_layers):
+        b = f"encoder.layers.{l}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            shapes[b + f"attention.{n}.weight"], shapes[b + f"attention.{n}.bias"] = (H, H), (H,)
+        for n in ("layer_norm", "final_layer_norm"):
+            shapes[b + n + ".weight"] = shapes[b + n + ".bias"] = (H,)
+        shapes[b + "feed_forward.intermediate_dense.weight"], shapes[b + "feed_forward.intermediate_dense.bias"] = (F, H), (F,)
+        shapes[b + "feed_forward.output_dense.weight"], shapes[b + "feed_forward.output_dense.bias"] = (H, F), (H,)
+    shapes["masked_spec_embed"] = (H,)
+    return {prefix + k: v for k, v in shapes.items()}
 
 
-class HubertModel(_StateHolder):
+def _init_param(name: str, shape, gen=None) -> torch.Tensor:
+    """Placeholder initialisation until a checkpoint is loaded (the reference scripts always load one): norm scales 1,
+    biases 0, weights N(0, 0.02) - HF:640-673 in spirit; weight-norm gains are set by the caller."""
+    leaf = name.rsplit(".", 1)[-1]
+    if leaf == "bias":
+        return torch.zeros(shape)
+    if leaf == "weight" and len(shape) == 1:
+        return torch.ones(shape)
+    return torch.empty(shape).normal_(0.0, 0.02, generator=gen)
+
+
+_OLD_WN = (("parametrizations.weight.original0", "weight_g"), ("parametrizations.weight.original1", "weight_v"))
+
+
+def _to_new_wn_names(sd: dict) -> dict:
+    """Old-style weight-norm names of the pos-conv (`weight_g` / `weight_v`, torch < 2.1 checkpoints) -> the
+    parametrization names the module registers (SURVEY 8b accepts both)."""
+    out = {}
+    for k, v in sd.items():
+        if "pos_conv_embed.conv." in k:
+            for new, old in _OLD_WN:
+                if k.endswith("conv." + old):
+                    k = k[: -len(old)] + new
+        out[k] = v
+    return out
+
+
+class HubertModel(SibModule):
     """HF `HubertModel` surface over the sm_100a kernels (eval mode, SpecAugment off)."""
 
     def __init__(self, config=None, precision: str = "fp32", key_prefix: str = ""):
@@ -159,8 +167,13 @@ class HubertModel(_StateHolder):
         self.config = HubertConfig.from_any(config) if config is not None else HubertConfig()
         self.precision = precision
         self._prefix = key_prefix
-        self._plans = {}
         self.use_cuda_graph = False
+        for name, shape in hubert_param_shapes(self.config).items():
+            self._add_param(name, _init_param(name, shape))
+        with torch.no_grad():   # weight-norm gain of the pos-conv starts at ||v|| (HF:59-78)
+            b = "encoder.pos_conv_embed.conv.parametrizations.weight."
+            self._sd[b + "original0"].copy_(self._sd[b + "original1"].pow(2).sum(dim=(0, 1), keepdim=True).sqrt())
+        self._sd_cache = None
         # independent half-batch chains through the transformer stack (ops.Plan.chain).  Measured on B200 at 32 x 4 s: two chains
         # 11.15-11.33 ms per step against 10.97-11.04 for one (the persistent GEMMs own every SM, so the second chain only
         # adds smaller, less efficient tiles) - kept as an A/B switch, off by default
@@ -170,19 +183,16 @@ class HubertModel(_StateHolder):
     def _expected_keys(self):
         return expected_hubert_keys(self.config, "")
 
+    def _adapt_state_dict(self, sd):
+        return _to_new_wn_names(sd)
+
     def _w(self, name):
         return self._sd[name]
 
     def _pos_conv_weight(self):
-        """weight_norm(dim=2) folded: w = g * v / ||v||_(0,1)  (HF:59-78)."""
-        b = "encoder.pos_conv_embed.conv."
-        if b + "weight" in self._sd:
-            return self._sd[b + "weight"]
-        if b + "weight_g" in self._sd:
-            g, v = self._sd[b + "weight_g"], self._sd[b + "weight_v"]
-        else:
-            g, v = self._sd[b + "parametrizations.weight.original0"], self._sd[b + "parametrizations.weight.original1"]
-        return g * v / v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()
+        """weight_norm(dim=2) folded on the device: w = v * (g / ||v||_(0,1))  (HF:59-78)."""
+        b = "encoder.pos_conv_embed.conv.parametrizations.weight."
+        return ops.weight_norm_fold(self._sd[b + "original1"], self._sd[b + "original0"].reshape(-1), dim=2)
 
     def _pack(self):
         """One-time weight packing into kernel layouts (fold weight-norm, transpose, fuse QKV)."""
@@ -217,7 +227,7 @@ class HubertModel(_StateHolder):
         elif self.precision != "fp32":
             raise SibError(f"unknown precision {self.precision!r} (fp32 | bf16)")
         self._packed = P
-        self._plans = {}
+        self._plans.clear()
         return P
 
     # ---- plan
@@ -365,22 +375,19 @@ class HubertModel(_StateHolder):
         L = self.config.num_hidden_layers if n_layers is None else n_layers
         padded = attention_mask is not None and not bool(attention_mask.to(torch.bool).all())
         key = (B, N, padded, L)
-        self._pack()
-        io = self._plans.get(key)
-        if io is None:
-            io = self._plans[key] = self._build_plan(B, N, padded, L)
-        io.wave.copy_(input_values.to(self._device, torch.float32), non_blocking=True)
-        if padded:
-            io.key_len.copy_(self._key_len(attention_mask.to(self._device), N))
-        io.plan.run()
+        with torch.cuda.device(self._device):   # the C side launches on the current device: make it this module's
+            self._pack()
+            io = self._cached_plan(key, lambda: self._build_plan(B, N, padded, L))
+            io.wave.copy_(input_values.to(self._device, torch.float32), non_blocking=True)
+            if padded:
+                io.key_len.copy_(self._key_len(attention_mask.to(self._device), N))
+            io.plan.run()
         return io
 
     # ---- reference surface
     def forward(self, input_values, attention_mask=None, **_unused):
         io = self._run(input_values, attention_mask)
-        return SimpleNamespace(last_hidden_state=io.out.clone())
-
-    __call__ = forward
+        return SimpleNamespace(last_hidden_state=io.out.clone())   # fresh tensor, as the reference returns
 
     def extract_features(self, source, padding_mask=None, mask=False, output_layer=None):
         """fairseq HuBERT surface used by I_da (hubert_feature_reader.py:60-65); output_layer is 1-based,
@@ -393,10 +400,10 @@ class HubertModel(_StateHolder):
         return io.out.clone(), padding_mask
 
 
-class CustomModel(_StateHolder):
+class CustomModel(SibModule):
     """I_ea/model.py:22-89 `CustomModel`: HubertModel + final_layers = LayerNorm(H) -> Linear(H, codebook_dim).
     Constructed from a config instead of `from_pretrained` (no network on the path); state-dict keys are
-    `base_model.*` and `final_layers.{0,1}.*`."""
+    `base_model.*` and `final_layers.{0,1}.*` (211 tensors for HuBERT-base)."""
 
     def __init__(self, codebook_dim=80, type="large", load_pretrained=False, train_encoder=False, loss_function="",
                  config=None, precision: str = "fp32"):
@@ -406,24 +413,24 @@ class CustomModel(_StateHolder):
         self.base_model = HubertModel(config, precision=precision)
         self.last_hidden_dim = self.base_model.config.hidden_size
         self.codebook_dim = 100 if loss_function == "softmax" else codebook_dim
+        H = self.last_hidden_dim
+        self._add_param("final_layers.0.weight", torch.ones(H))
+        self._add_param("final_layers.0.bias", torch.zeros(H))
+        self._add_param("final_layers.1.weight", torch.empty(self.codebook_dim, H).normal_(0.0, 0.02))
+        self._add_param("final_layers.1.bias", torch.zeros(self.codebook_dim))
         self._head = None
 
     def _expected_keys(self):
         return (expected_hubert_keys(self.base_model.config, "base_model.") +
                 ["final_layers.0.weight", "final_layers.0.bias", "final_layers.1.weight", "final_layers.1.bias"])
 
-    def load_state_dict(self, sd, strict: bool = True):
-        r = super().load_state_dict(sd, strict)
-        self.base_model._device = self._device
-        self.base_model.load_state_dict({k[len("base_model."):]: v for k, v in self._sd.items() if k.startswith("base_model.")}, strict)
-        self._head = None
-        return r
+    def _adapt_state_dict(self, sd):
+        return _to_new_wn_names(sd)
 
-    def to(self, device=None, *a, **k):
-        super().to(device, *a, **k)
-        self.base_model.to(device)
-        self._head = None
-        return self
+    def _head_weight(self):
+        if self._head is None:
+            self._head = ops.pack_linear_weight(self._sd["final_layers.1.weight"])
+        return self._head
 
     def forward_frames(self, input_values, attention_mask, pos_t, len_t, off_t, n_rows: int):
         """final_layers applied ONLY to the frames [pos_b, pos_b + len_b) of every utterance: what predict.py:164-168
@@ -432,30 +439,28 @@ class CustomModel(_StateHolder):
         io = self.base_model._run(input_values, attention_mask)
         h = io.out
         B, T, H = h.shape
-        if self._head is None:
-            self._head = ops.pack_linear_weight(self._sd["final_layers.1.weight"])
-        rows = torch.empty(max(n_rows, 1), H, device=h.device, dtype=torch.float32)[:n_rows]
-        out = torch.empty(max(n_rows, 1), self.codebook_dim, device=h.device, dtype=torch.float32)[:n_rows]
-        if n_rows > 0:
-            ops.gather_frames(h, pos_t, len_t, off_t, rows)
-            nrm = torch.empty_like(rows)
-            ops.layernorm(rows, self._sd["final_layers.0.weight"], self._sd["final_layers.0.bias"], nrm, 1e-5)
-            if self.codebook_dim <= 128 and H <= 8192:   # a few hundred rows x 80 outputs: one CTA per row
-                ops.linear_skinny(nrm, self._head, self._sd["final_layers.1.bias"], out)
-            else:
-                ops.linear(nrm, self._head, self._sd["final_layers.1.bias"], out)
+        sd = self._sd
+        with torch.cuda.device(h.device):
+            rows = torch.empty(max(n_rows, 1), H, device=h.device, dtype=torch.float32)[:n_rows]
+            out = torch.empty(max(n_rows, 1), self.codebook_dim, device=h.device, dtype=torch.float32)[:n_rows]
+            if n_rows > 0:
+                ops.gather_frames(h, pos_t, len_t, off_t, rows)
+                nrm = torch.empty_like(rows)
+                ops.layernorm(rows, sd["final_layers.0.weight"], sd["final_layers.0.bias"], nrm, 1e-5)
+                if self.codebook_dim <= 128 and H <= 8192:   # a few hundred rows x 80 outputs: one CTA per row
+                    ops.linear_skinny(nrm, self._head_weight(), sd["final_layers.1.bias"], out)
+                else:
+                    ops.linear(nrm, self._head_weight(), sd["final_layers.1.bias"], out)
         return out, T
 
     def forward(self, input_values, attention_mask=None):
         io = self.base_model._run(input_values, attention_mask)
         h = io.out
         B, T, H = h.shape
-        if self._head is None:
-            self._head = ops.pack_linear_weight(self._sd["final_layers.1.weight"])
-        nrm = torch.empty_like(h)
-        ops.layernorm(h, self._sd["final_layers.0.weight"], self._sd["final_layers.0.bias"], nrm, 1e-5)
-        out = torch.empty(B, T, self.codebook_dim, device=h.device, dtype=torch.float32)
-        ops.linear(nrm.view(B * T, H), self._head, self._sd["final_layers.1.bias"], out.view(B * T, -1))
+        sd = self._sd
+        with torch.cuda.device(h.device):
+            nrm = torch.empty_like(h)
+            ops.layernorm(h, sd["final_layers.0.weight"], sd["final_layers.0.bias"], nrm, 1e-5)
+            out = torch.empty(B, T, self.codebook_dim, device=h.device, dtype=torch.float32)
+            ops.linear(nrm.view(B * T, H), self._head_weight(), sd["final_layers.1.bias"], out.view(B * T, -1))
         return out
-
-    __call__ = forward

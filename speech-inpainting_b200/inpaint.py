@@ -124,8 +124,12 @@ class InformedInpainter:
         self.cc = (all_t - self.center[None, :]).contiguous()  # all_embeds_t_c
         self.device = dev
 
-    def __call__(self, wave16, mel, mask_pos, mask_len, apply_mask: bool = True, normalize: bool = True,
-                 attention_mask=None, return_int16: bool = False, wave22=None, zero22=None):
+    def __call__(self, *args, **kwargs):
+        with torch.cuda.device(self.device):   # every launch below goes to the CURRENT device: make it the pipeline's
+            return self._call(*args, **kwargs)
+
+    def _call(self, wave16, mel, mask_pos, mask_len, apply_mask: bool = True, normalize: bool = True,
+              attention_mask=None, return_int16: bool = False, wave22=None, zero22=None, keep_wave: bool = True):
         """wave16 [B,N] float32 (host or device), mel [B,80,T'] (hop-441 log-mel of the masked 22 kHz wave),
         mask_pos/mask_len: per-utterance frame index / length (ints or sequences).
         Instead of a precomputed `mel` (pass None) the 22.05 kHz rendition `wave22` [B,S] and its zero ranges `zero22`
@@ -166,7 +170,10 @@ class InformedInpainter:
         # predict.py:163-168: outputs = model(inputs)[b, pos:pos+L]; the head (LayerNorm + Linear) is row-wise, so it is
         # evaluated on the gathered frames only (bit-identical rows, sum(L) of them instead of B*T)
         values, _ = self.model.forward_frames(x, attention_mask, pos_t, len_t, off_t, M)
-        mel_dev = mel.to(dev, torch.float32, non_blocking=True).clone() if mel.is_cuda else mel.to(dev, torch.float32, non_blocking=True).contiguous()
+        # a private, DENSE [B, 80, T'] copy on the device (the paste below writes into it; a permuted view would keep its
+        # strides through .clone())
+        mel_dev = mel.to(dev, torch.float32, non_blocking=True)
+        mel_dev = mel_dev.clone(memory_format=torch.contiguous_format) if mel_dev.data_ptr() == mel.data_ptr() else mel_dev.contiguous()
         labels = torch.empty(max(M, 1), dtype=torch.int64, device=dev)[:M]
         if M > 0:
             ops.cos_argmax(values, self.cc, labels)                        # loss_fn.py:44-46
@@ -174,7 +181,9 @@ class InformedInpainter:
         Tp = mel_dev.shape[2]
         feats = torch.empty(B, ops.extend_mel_len(Tp), mel_dev.shape[1], device=dev, dtype=torch.float32)
         ops.extend_mel(mel_dev, feats, frame_major=True)                   # predict.py:189
-        y = self.generator.forward_frame_major(feats)                      # predict.py:203
+        # predict.py:203.  keep_wave=False (the streaming loop, which only ships the int16 rendition) skips the private
+        # copy of the float waveform: res.wave is then the plan's own buffer, valid until the next call
+        y = self.generator.forward_frame_major(feats, clone=keep_wave)
         res = SimpleNamespace(wave=y, labels=labels, mel=mel_dev, offsets=off, values=values)
         if return_int16:                                                   # predict.py:204-206
             res.int16 = torch.empty(y.shape, dtype=torch.int16, device=dev)
@@ -183,6 +192,10 @@ class InformedInpainter:
 
 
     def stream(self, batches, depth: int = 2):
+        with torch.cuda.device(self.device):
+            yield from self._stream(batches, depth)
+
+    def _stream(self, batches, depth: int = 2):
         """Pipelined serving loop over an iterable of HOST batches (pinned memory recommended) - the micro-batch executor
         BASELINE config 5 needs (1024 x 10 s does not fit one pass): while batch i computes on the current stream, a copy
         stream uploads batch i+1 into one of `depth` device slots and a third one downloads the int16 result of batch i-1.
@@ -231,7 +244,7 @@ class InformedInpainter:
                 ready = torch.cuda.Event()
                 ready.record(copy)
             compute.wait_event(ready)
-            res = self(sl.wave, sl.mel, b["mask_pos"], b["mask_len"], return_int16=True)
+            res = self._call(sl.wave, sl.mel, b["mask_pos"], b["mask_len"], return_int16=True, keep_wave=False)
             done = torch.cuda.Event()
             done.record(compute)
             sl.free = done
@@ -256,8 +269,13 @@ class BlindInpainter:
     """I_da inpainting for a batch of equal-length utterances (scripts/inpainting.py:181-259)."""
 
     def __init__(self, hubert, code_generator, kmeans_centers: torch.Tensor, layer: int = -1, normalize: bool = False,
-                 code_hop_size: int = 320, sampling_rate: int = 16000):
+                 code_hop_size: int = 320, sampling_rate: int = 16000, emb_as_long: bool = True):
+        """emb_as_long: the reference hands the speaker d-vector to the generator as `torch.LongTensor(emb)`
+        (scripts/inpainting.py:233,239; the training set does the same, src/dataset.py:437), i.e. TRUNCATED TOWARD ZERO
+        to integers before it is concatenated - the shipped checkpoints were trained on those values.  True (default)
+        reproduces that; False feeds the raw float d-vector (a deliberate divergence from the reference)."""
         self.hubert, self.gen = hubert, code_generator
+        self.emb_as_long = emb_as_long
         self.device = hubert._device
         self.mu = kmeans_centers.to(self.device, torch.float32).contiguous()  # [K, H]
         self.layer, self.normalize = layer, normalize
@@ -282,8 +300,12 @@ class BlindInpainter:
         ops.l2_argmin(feats.reshape(B * T, H), self.mu, labels)  # kmeans_model.predict (inpainting.py:204-205)
         return labels.view(B, T)
 
-    def __call__(self, wave, mask_size: int, f0_code=None, emb=None, informed: bool = True, return_int16: bool = False,
-                 f0=None):
+    def __call__(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return self._call(*args, **kwargs)
+
+    def _call(self, wave, mask_size: int, f0_code=None, emb=None, informed: bool = True, return_int16: bool = False,
+              f0=None):
         """`f0` = the continuous f0 track [B, 1, frames at hop 80] the reference passes (inpainting.py:231, quantised
         inside CodeGenerator by the frozen f0 VQ-VAE); `f0_code` = already quantised bins [B, frames / 16] instead."""
         dev = self.device
@@ -291,6 +313,8 @@ class BlindInpainter:
             raise SibError("BlindInpainter needs emb and exactly one of f0= (continuous track) / f0_code= (pitch bins)")
         y = wave.to(dev, torch.float32).contiguous()
         B, N = y.shape
+        if self.emb_as_long:                                                 # inpainting.py:233 `torch.LongTensor(emb)`
+            emb = emb.to(torch.int64)
         frame_start = int(self.sr * 3 / 2)                                  # inpainting.py:187
         y_inp = y.clone()
         ops.zero_ranges(y_inp, _i32([frame_start] * B, dev), _i32([frame_start + mask_size] * B, dev), add_eps=1e-6)  # :188-191

@@ -27,6 +27,11 @@ def _chk(t, dtype=None, name="tensor"):
         return None
     if not t.is_cuda:
         raise SibError(f"{name} must be a CUDA tensor (no CPU fallback on this path)")
+    if t.device.index != torch.cuda.current_device():
+        # the C side launches on the CURRENT device (stream, SM count, attribute cache): a tensor of another device would
+        # be an illegal address or silent peer traffic.  Modules / pipelines enter `torch.cuda.device(their device)`.
+        raise SibError(f"{name} lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}; "
+                       "wrap the call in `with torch.cuda.device(...)`")
     if dtype is not None and t.dtype != dtype:
         raise SibError(f"{name} must be {dtype}, got {t.dtype}")
     return t
@@ -62,6 +67,7 @@ class Plan:
         self._chain = 0
         self._side = {}   # chain id -> torch.cuda.Stream
         self._n_chains = 1
+        self.device = torch.cuda.current_device() if torch.cuda.is_available() else None
 
     @contextlib.contextmanager
     def record(self):
@@ -123,6 +129,8 @@ class Plan:
                     main.wait_event(ev)
 
     def run(self):
+        if self.device is not None and self.device != torch.cuda.current_device():
+            raise SibError(f"plan recorded on cuda:{self.device} replayed with cuda:{torch.cuda.current_device()} current")
         if self.graph is not None:
             self.graph.replay()
             return
@@ -214,6 +222,24 @@ def to_kmajor_bf16(w_packed: torch.Tensor) -> torch.Tensor:
     return w.to(torch.bfloat16).contiguous()
 
 
+def weight_norm_fold(v: torch.Tensor, g: torch.Tensor, dim: int = 0) -> torch.Tensor:
+    """torch weight_norm folded on the device: v * (g / ||v||), norm over every dim but `dim` (0, or the last one)."""
+    _chk(v, torch.float32, "weight_v"); _chk(g, torch.float32, "weight_g")
+    v, g = v.contiguous(), g.contiguous()
+    w = torch.empty_like(v)
+    if dim == 0:
+        outer, inner, last = v.shape[0], v.numel() // v.shape[0], 0
+    elif dim in (v.dim() - 1, -1):
+        inner = v.shape[-1]
+        outer, last = v.numel() // inner, 1
+    else:
+        raise SibError(f"weight_norm_fold: dim={dim} unsupported (0 or last)")
+    if g.numel() != (inner if last else outer):
+        raise SibError(f"weight_norm_fold: weight_g has {g.numel()} entries for a {tuple(v.shape)} weight_v (dim {dim})")
+    _emit("sib_weight_norm_fold_f32", (_p(v), _p(g), _p(w), outer, inner, last), keep=(v, g, w))
+    return w
+
+
 def conv_taps(k: int, dilation: int, padding: int):
     return [j * dilation - padding for j in range(k)]
 
@@ -288,10 +314,11 @@ def conv1d(x, w, bias, y, taps, *, stride=1, groups=1, residual=None, y_act=None
         raise SibError(f"unsupported dtype {x.dtype}")
 
 
-def conv_pre_act_supported(batch, t, c_in, c_out, taps, pre_slope=0.1) -> bool:
-    """Whether the tcgen05 conv can apply leaky-relu to its A tile in shared memory for this (stride-1) layer."""
+def conv_pre_act_supported(batch, t, c_in, c_out, taps, pre_slope=0.1, has_residual=False, has_y_act=False) -> bool:
+    """Whether the tcgen05 conv can apply leaky-relu to its A tile in shared memory for this (stride-1) layer when it is
+    launched with / without a residual input and an activated second output (both cost epilogue staging memory)."""
     d = make_desc(batch, t, t, c_in, c_out, taps, pre_slope=pre_slope)
-    return bool(_lib.lib().sib_conv1d_bf16_pre_act_supported(C.byref(d)))
+    return bool(_lib.lib().sib_conv1d_bf16_pre_act_supported(C.byref(d), int(has_residual), int(has_y_act)))
 
 
 def resunit_supported(c: int, k: int, dilation: int, accumulate: bool = False, has_y_act: bool = False) -> bool:
@@ -429,9 +456,11 @@ def l2_argmin(f, mu, labels):
 
 def paste_centroids(mel, cc, center, labels, pos, length, off):
     B, Dm, T = mel.shape
-    _chk(mel, torch.float32, "mel"); _chk(labels, torch.int64, "labels")
-    _emit("sib_paste_centroids_f32", (_p(mel), B, Dm, T, _p(cc), _p(center), _p(labels), _p(pos), _p(length), _p(off)),
-          keep=(mel, cc, center, labels, pos, length, off))
+    _chk(mel, torch.float32, "mel"); _chk(labels, torch.int64, "labels"); _chk(cc, torch.float32, "cc")
+    if not (mel.is_contiguous() and cc.is_contiguous()) or cc.shape[1] != Dm:
+        raise SibError("paste_centroids: mel must be a dense [B, D, T] tensor and cc a dense [K, D] codebook")
+    _emit("sib_paste_centroids_f32", (_p(mel), B, Dm, T, _p(cc), _p(center), _p(labels), _p(pos), _p(length), _p(off),
+                                      cc.shape[0]), keep=(mel, cc, center, labels, pos, length, off))
 
 
 def extend_mel_len(t: int) -> int:
@@ -444,6 +473,8 @@ def extend_mel(mel, out, frame_major: bool):
     B, Dm, T = mel.shape
     tm = out.shape[1] if frame_major else out.shape[2]
     _chk(mel, torch.float32, "mel"); _chk(out, None, "out")
+    if not (mel.is_contiguous() and out.is_contiguous()):
+        raise SibError("extend_mel: mel [B, D, T] and out must be dense tensors")
     _emit("sib_extend_mel", (_p(mel), _p(out), _dt(out), B, Dm, T, tm, int(frame_major)), keep=(mel, out))
 
 
@@ -457,8 +488,12 @@ def transpose(x, out):
 def embed_concat(code, zp, spk, emb_c, emb_p, out):
     B, T = code.shape
     _chk(code, torch.int64, "code"); _chk(zp, torch.int64, "zp"); _chk(spk, torch.float32, "spk")
+    _chk(emb_c, torch.float32, "emb_c"); _chk(emb_p, torch.float32, "emb_p")
+    if not all(t.is_contiguous() for t in (code, zp, spk, emb_c, emb_p, out)):
+        raise SibError("embed_concat: operands must be dense")
     _emit("sib_embed_concat_f32", (_p(code), _p(zp), _p(spk), _p(emb_c), _p(emb_p), _p(out), B, T, zp.shape[1],
-                                   emb_c.shape[1], spk.shape[1]), keep=(code, zp, spk, emb_c, emb_p, out))
+                                   emb_c.shape[1], spk.shape[1], emb_c.shape[0], emb_p.shape[0]),
+          keep=(code, zp, spk, emb_c, emb_p, out))
 
 
 def pack_int16(y, out):

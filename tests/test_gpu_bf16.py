@@ -22,11 +22,12 @@ def sib():
     return m
 
 
-@pytest.mark.parametrize("kind,B,T", [("tiny", 2, 40), ("v1", 2, 43), ("ida", 1, 12)])
+@pytest.mark.parametrize("kind,B,T", [("tiny", 2, 40), ("v1", 2, 43), ("ida", 1, 12), ("v3", 2, 37)])
 def test_generator_bf16(sib, kind, B, T):
+    """v3 = config_v3.json: ResBlock2 (models.py:52-73) through the tcgen05 convs with residual + in-kernel leaky-relu."""
     from oracle import hifigan_ref, mel_ref
     from oracle.params import HifiCfg, make_generator_params
-    cfg = {"v1": HifiCfg.v1(), "tiny": HifiCfg.tiny(), "ida": HifiCfg.ida(), "ida_tiny": HifiCfg.tiny(True)}[kind]
+    cfg = {"v1": HifiCfg.v1(), "v3": HifiCfg.v3(), "tiny": HifiCfg.tiny(), "ida": HifiCfg.ida(), "ida_tiny": HifiCfg.tiny(True)}[kind]
     params = {k: v for k, v in make_generator_params(cfg, 1234, "unit").items() if not k.startswith("emb_")}
     gen = sib.Generator(sib.AttrDict(cfg.as_attrdict()), precision="bf16").to("cuda")
     gen.load_state_dict(params)
@@ -43,11 +44,12 @@ def test_generator_bf16(sib, kind, B, T):
         assert l1 < MEL_L1_BOUND
 
 
-@pytest.mark.parametrize("name,B,N", [("tiny_group", 2, 8000), ("tiny_layer", 2, 8000), ("base", 2, 32000)])
+@pytest.mark.parametrize("name,B,N", [("tiny_group", 2, 8000), ("tiny_layer", 2, 8000), ("base", 2, 32000), ("large", 2, 24000)])
 def test_hubert_bf16(sib, name, B, N):
     from oracle import hubert_ref
     from oracle.params import HubertCfg, make_hubert_params
-    ocfg = {"tiny_group": HubertCfg.tiny(False), "tiny_layer": HubertCfg.tiny(True), "base": HubertCfg.base()}[name]
+    ocfg = {"tiny_group": HubertCfg.tiny(False), "tiny_layer": HubertCfg.tiny(True), "base": HubertCfg.base(),
+            "large": HubertCfg.large()}[name]
     params = make_hubert_params(ocfg, 1234)
     model = sib.HubertModel(sib.HubertConfig.from_any(ocfg), precision="bf16").to("cuda")
     model.load_state_dict(params)
@@ -88,7 +90,7 @@ def test_informed_inpainting_bf16_config1(sib):
     l1 = mel_ref.mel_l1(ref_wave[:, 0], res.wave[:, 0].cpu())
     s = snr_db(ref_wave, res.wave.cpu())
     print(f"\n[bf16 I_ea cfg1] label agreement {agree:.3f}, waveform SNR {s:.1f} dB, mel-L1 {l1:.4f}")
-    assert agree >= 0.9
+    assert agree >= 0.98
     assert l1 < MEL_L1_BOUND
 
 

@@ -101,31 +101,35 @@ def test_custom_model_state_dict_surface(sib):
 
 
 GEN_CASES = [("v1_unit", "v1", 2, 6, "unit"), ("v1_ref", "v1", 1, 5, "reference"), ("tiny_unit", "tiny", 2, 9, "unit"),
-             ("ida_unit", "ida", 1, 4, "unit"), ("ida_tiny", "ida_tiny", 2, 8, "unit")]
+             ("ida_unit", "ida", 1, 4, "unit"), ("ida_tiny", "ida_tiny", 2, 8, "unit"),
+             # config_v2.json (ResBlock1, 128 channels) and config_v3.json (ResBlock2, models.py:52-73)
+             ("v2_unit", "v2", 2, 7, "unit"), ("v3_unit", "v3", 2, 11, "unit"), ("v3_ref", "v3", 1, 6, "reference")]
 
 
 def _gen_cfg(kind):
     from oracle.params import HifiCfg
-    return {"v1": HifiCfg.v1(), "tiny": HifiCfg.tiny(), "ida": HifiCfg.ida(), "ida_tiny": HifiCfg.tiny(True)}[kind]
+    return {"v1": HifiCfg.v1(), "v2": HifiCfg.v2(), "v3": HifiCfg.v3(), "tiny": HifiCfg.tiny(), "ida": HifiCfg.ida(),
+            "ida_tiny": HifiCfg.tiny(True)}[kind]
 
 
 @pytest.mark.parametrize("name,kind,B,T,init", GEN_CASES)
 def test_generator_vs_reference_golden(sib, golden_dir, name, kind, B, T, init):
-    from oracle.params import make_generator_params
+    from oracle.params import fold_weight_norm, make_generator_params
     gold = torch.from_numpy(np.load(f"{golden_dir}/hifigan_golden.npz")[name + "_out"])
     cfg = _gen_cfg(kind)
     params = {k: v for k, v in make_generator_params(cfg, 1234, init).items() if not k.startswith("emb_")}
     gen = sib.Generator(sib.AttrDict(cfg.as_attrdict())).to("cuda")
     gen.load_state_dict(params)       # with weight_g / weight_v, as the reference checkpoints
     gen.eval()
-    gen.remove_weight_norm()
+    assert set(gen.state_dict()) == set(params)
+    gen.remove_weight_norm()          # folds on the device and leaves the reference's post-removal key set
+    assert set(gen.state_dict()) == set(fold_weight_norm(params)) and len(gen.state_dict()) == 2 * len(params) // 3
     x = torch.randn(B, cfg.model_in_dim, T, generator=torch.Generator().manual_seed(7))
     y = gen(x.cuda()).cpu()
     assert y.shape == gold.shape == (B, 1, T * cfg.total_upsample)
     assert snr_db(gold, y) > 60, snr_db(gold, y)
     assert max_abs(gold, y) < 1e-4 * max(1.0, float(gold.abs().max()))
     # folded ("remove_weight_norm"-ed) checkpoints load too and give the same answer
-    from oracle.params import fold_weight_norm
     gen2 = sib.Generator(sib.AttrDict(cfg.as_attrdict())).to("cuda")
     gen2.load_state_dict(fold_weight_norm(params))
     assert max_abs(y, gen2(x.cuda()).cpu()) < 1e-5
@@ -312,8 +316,12 @@ def test_blind_inpainting_tiny(sib):
         code_inp = glue_ref.ida_splice_codes(code, code_inp, fs, mask)
         assert np.array_equal(code[:n_code], res.code[b].cpu().numpy())
         assert np.array_equal(code_inp[:n_code], res.code_inpainting[b].cpu().numpy())
-        ref = hifigan_ref.code_generator_forward(gp, gcfg, torch.from_numpy(code_inp[:n_code])[None], zp[b:b + 1, : n_code // 4], emb[b:b + 1])
+        # inpainting.py:233: the d-vector reaches the generator as torch.LongTensor(emb) (truncated toward zero)
+        emb_l = glue_ref.ida_emb_longtensor(emb[b:b + 1])
+        ref = hifigan_ref.code_generator_forward(gp, gcfg, torch.from_numpy(code_inp[:n_code])[None], zp[b:b + 1, : n_code // 4], emb_l)
         assert snr_db(ref, res.audio_inp[b:b + 1].cpu()) > 60
+    raw = sib.BlindInpainter(hub, gen, mu, layer=-1, normalize=False, emb_as_long=False)(wave, mask, zp, emb, informed=True)
+    assert not torch.equal(raw.audio_inp, res.audio_inp)        # the raw float d-vector is a different (non-reference) input
 
 
 def test_mask_golden_on_device(sib, golden_dir):
@@ -480,3 +488,124 @@ def test_blind_inpainting_with_continuous_f0(sib):
         pipe(wave, mask, zp, emb, f0=f0)                         # both given
     with pytest.raises(sib.SibError):
         pipe(wave, mask, emb=emb)                                # neither given
+
+
+def test_modules_are_real_nn_modules_used_as_the_reference_scripts_do(sib, tmp_path):
+    """the shims are `nn.Module`s built, moved, loaded and saved exactly as I_ea/predict.py:117-122,145-150 do:
+    Generator(h).to(device); load_state_dict(ckpt['generator']); eval(); remove_weight_norm();
+    CustomModel(codebook_dim=80, type=..., load_pretrained=False); model.to(device); load_state_dict(torch.load(ckpt)); eval()."""
+    from torch import nn
+    from oracle import hifigan_ref, hubert_ref
+    from oracle.params import HifiCfg, HubertCfg, fold_weight_norm, make_generator_params, make_head_params, make_hubert_params
+    device = torch.device("cuda")
+    gcfg = HifiCfg.v1()
+    gp = make_generator_params(gcfg, 1234, "unit")
+    torch.save({"generator": gp}, tmp_path / "g_ckpt")                    # checkpoint layout of hifi_gan/train.py
+    h = sib.AttrDict(gcfg.as_attrdict())
+    generator = sib.Generator(h).to(device)
+    assert isinstance(generator, nn.Module) and len(generator.state_dict()) == 234 == len(list(generator.named_parameters()))
+    state_dict_g = torch.load(tmp_path / "g_ckpt", map_location=device)
+    generator.load_state_dict(state_dict_g["generator"])
+    generator.eval()
+    generator.remove_weight_norm()
+    assert len(generator.state_dict()) == 156 and not generator.training
+    x = torch.randn(1, 80, 12, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        y = generator(x.to(device))
+    ref = hifigan_ref.generator_forward(gp, gcfg, x)
+    assert snr_db(ref, y.cpu()) > 60
+    for k, v in fold_weight_norm(gp).items():                              # the folded tensors are the reference's
+        assert max_abs(v, generator.state_dict()[k].cpu()) < 1e-6 * max(1.0, float(v.abs().max())), k
+    # whole-module pickling (torch.save(model)) and a hook
+    torch.save(generator, tmp_path / "g_module")
+    g2 = torch.load(tmp_path / "g_module", weights_only=False)
+    seen = []
+    g2.register_forward_hook(lambda m, i, o: seen.append(tuple(o.shape)))
+    assert torch.equal(g2(x.to(device)), y) and seen == [(1, 1, 12 * 256)]
+    # CustomModel: tiny config stands in for from_pretrained (no network); keys and semantics are the reference's
+    ocfg = HubertCfg.tiny(False)
+    sd = make_hubert_params(ocfg, 5, prefix="base_model.")
+    sd.update(make_head_params(ocfg.hidden_size, 80))
+    torch.save(sd, tmp_path / "m_ckpt")
+    model = sib.CustomModel(codebook_dim=80, type="base", load_pretrained=False, config=_hub_cfg(sib, ocfg))
+    model.to(device)
+    model.load_state_dict(torch.load(tmp_path / "m_ckpt", map_location="cuda"))
+    model.eval()
+    assert isinstance(model, nn.Module) and isinstance(model.base_model, nn.Module)
+    assert set(model.state_dict()) == set(sd) and all(not p.requires_grad for p in model.parameters())
+    for p_ in model.base_model.encoder.parameters():                       # I_ea/model.py:53-55 touches these
+        assert p_.is_cuda
+    assert any(isinstance(m, nn.Module) for m in model.modules()) and model.base_model.config.hidden_size == 128
+    xw = 0.1 * torch.randn(2, 4000, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        out = model(xw.to(device), None)
+    assert max_abs(hubert_ref.custom_model_forward(sd, ocfg, xw), out.cpu()) < 2e-4
+    # .half() / .float() round trip keeps the module usable (weights are re-packed from the parameters)
+    model.half().float()
+    out2 = model(xw.to(device), None)
+    assert snr_db(out.cpu(), out2.cpu()) > 50
+    model.load_state_dict(torch.load(tmp_path / "m_ckpt", map_location="cuda"))
+    assert torch.equal(model(xw.to(device), None), out)
+
+
+def test_plan_cache_is_bounded_over_many_distinct_lengths(sib):
+    """one multi-GB plan per distinct input length must not accumulate - an LRU bounds the resident plans, and
+    device memory stays flat over 60 distinct lengths."""
+    from oracle.params import HifiCfg, HubertCfg, make_generator_params, make_hubert_params
+    ocfg, gcfg = HubertCfg.tiny(False), HifiCfg.tiny()
+    hub = sib.HubertModel(_hub_cfg(sib, ocfg)).to("cuda")
+    hub.load_state_dict(make_hubert_params(ocfg, 1))
+    gen = sib.Generator(sib.AttrDict(gcfg.as_attrdict())).to("cuda")
+    gen.load_state_dict(make_generator_params(gcfg, 1, "unit"))
+    first = {}
+    peak = []
+    for i in range(60):
+        n, tm = 4000 + 160 * i, 20 + i
+        y = hub(torch.zeros(2, n, device="cuda") + 0.01 * i).last_hidden_state
+        w = gen(torch.full((2, 80, tm), 0.01 * i, device="cuda"))
+        if i == 0:
+            first = (y.clone(), w.clone())
+        torch.cuda.synchronize()
+        peak.append(torch.cuda.memory_allocated())
+    assert len(hub._plans) <= hub._plans.max_plans and len(gen._plans) <= gen._plans.max_plans
+    assert hub._plans.evictions >= 60 - hub._plans.max_plans
+    assert max(peak[20:]) <= 1.5 * max(peak[:12]) + (8 << 20), (peak[:12], peak[-5:])
+    # an evicted shape is simply re-planned and reproduces its first answer bit for bit
+    y0 = hub(torch.zeros(2, 4000, device="cuda")).last_hidden_state
+    assert torch.equal(y0, first[0]) and torch.equal(gen(torch.zeros(2, 80, 20, device="cuda")), first[1])
+
+
+def test_wrong_current_device_is_refused_loudly(sib):
+    """the C side launches on the CURRENT device; modules enter their own device, raw ops refuse a mismatch."""
+    if torch.cuda.device_count() < 2:
+        x = torch.zeros(4, 8, device="cuda")
+        sib.ops.cast_to_bf16(x, torch.empty(4, 8, device="cuda", dtype=torch.bfloat16))   # same device: fine
+        pytest.skip("needs two GPUs for the cross-device half")
+    from oracle.params import HifiCfg, make_generator_params
+    gcfg = HifiCfg.tiny()
+    gp = make_generator_params(gcfg, 1, "unit")
+    g0 = sib.Generator(sib.AttrDict(gcfg.as_attrdict())).to("cuda:0"); g0.load_state_dict(gp)
+    g1 = sib.Generator(sib.AttrDict(gcfg.as_attrdict())).to("cuda:1"); g1.load_state_dict(gp)
+    x = torch.randn(1, 80, 16)
+    assert torch.cuda.current_device() == 0
+    y0, y1 = g0(x.to("cuda:0")), g1(x.to("cuda:1"))       # g1 runs on cuda:1 although cuda:0 is current
+    assert y1.device.index == 1 and torch.equal(y0.cpu(), y1.cpu())
+    with pytest.raises(sib.SibError, match="current device"):
+        sib.ops.znorm(torch.zeros(1, 64, device="cuda:1"), torch.zeros(1, 64, device="cuda:1"))
+
+
+def test_out_of_range_codes_trap_on_the_device(sib):
+    """a k-means unit / pitch bin / codebook label outside its table is a device-side assert (as
+    nn.Embedding), not a silent out-of-bounds read.  Run in a child process: the trap poisons the CUDA context."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "import speech_inpainting_b200 as sib\n"
+        "code = torch.tensor([[1, 2, 99]], device='cuda'); zp = torch.zeros(1, 3, dtype=torch.int64, device='cuda')\n"
+        "out = torch.empty(1, 3, 40, device='cuda')\n"
+        "sib.ops.embed_concat(code, zp, torch.zeros(1, 8, device='cuda'), torch.zeros(50, 16, device='cuda'),"
+        " torch.zeros(20, 16, device='cuda'), out)\n"
+        "torch.cuda.synchronize()\n" % root)
+    r = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and ("outside the 50" in r.stdout + r.stderr or "CUDA error" in r.stderr), r.stderr[-500:]

@@ -98,7 +98,7 @@ def test_c_abi_library_exports_every_declared_symbol(sib):
     assert set(sib.exported_symbols()) <= declared, sorted(set(sib.exported_symbols()) - declared)
     lib = ctypes.CDLL(lib_path)          # loads without a GPU
     lib.sib_abi_version.restype = ctypes.c_int
-    assert lib.sib_abi_version() == 1
+    assert lib.sib_abi_version() == 2
 
 
 def test_conv_desc_layout_matches_header(sib, tmp_path):

@@ -88,18 +88,48 @@ def test_hubert_oracle_live_pin_against_transformers():
 
 @pytest.mark.parametrize("name,kind,B,T,init", [("v1_unit", "v1", 2, 6, "unit"), ("v1_ref", "v1", 1, 5, "reference"),
                                                 ("tiny_unit", "tiny", 2, 9, "unit"), ("ida_unit", "ida", 1, 4, "unit"),
-                                                ("ida_tiny", "ida_tiny", 2, 8, "unit")])
+                                                ("ida_tiny", "ida_tiny", 2, 8, "unit"), ("v2_unit", "v2", 2, 7, "unit"),
+                                                ("v3_unit", "v3", 2, 11, "unit"), ("v3_ref", "v3", 1, 6, "reference")])
 def test_generator_oracle_vs_reference_golden(golden_dir, name, kind, B, T, init):
+    """V1 / V2 (ResBlock1), V3 (ResBlock2, models.py:52-73) and the I_da generator against the reference's own modules."""
     from oracle import hifigan_ref
     from oracle.params import HifiCfg, make_generator_params
     gold = torch.from_numpy(np.load(f"{golden_dir}/hifigan_golden.npz")[name + "_out"])
-    cfg = {"v1": HifiCfg.v1(), "tiny": HifiCfg.tiny(), "ida": HifiCfg.ida(), "ida_tiny": HifiCfg.tiny(True)}[kind]
+    cfg = {"v1": HifiCfg.v1(), "v2": HifiCfg.v2(), "v3": HifiCfg.v3(), "tiny": HifiCfg.tiny(), "ida": HifiCfg.ida(),
+           "ida_tiny": HifiCfg.tiny(True)}[kind]
     params = make_generator_params(cfg, 1234, init)
     x = torch.randn(B, cfg.model_in_dim, T, generator=torch.Generator().manual_seed(7))
     with torch.no_grad():
         y = hifigan_ref.generator_forward(params, cfg, x)
     assert y.shape == gold.shape == (B, 1, T * cfg.total_upsample)
     assert max_abs(gold, y) < 1e-5 * max(1.0, float(gold.abs().max()))
+
+
+def test_kmeans_oracle_vs_sklearn_golden(golden_dir):
+    """a17: `kmeans_predict` against labels produced by the real `sklearn.cluster.KMeans.predict`
+    (oracle/make_golden.py:golden_kmeans), and live against the installed sklearn when it is importable."""
+    from oracle import glue_ref
+    gold = np.load(f"{golden_dir}/kmeans_golden.npz")
+    for K, H, M in ((100, 768, 400), (500, 768, 600), (500, 1024, 300)):
+        g = torch.Generator().manual_seed(K + H)
+        mu = torch.randn(K, H, generator=g) * 0.5
+        idx = torch.randint(0, K, (M,), generator=g)
+        f = torch.cat([mu[idx[: M // 2]] + 0.3 * torch.randn(M // 2, H, generator=g), torch.randn(M - M // 2, H, generator=g) * 0.5])
+        want = gold[f"labels_{K}_{H}"]
+        assert np.array_equal(glue_ref.kmeans_predict(f, mu).numpy(), want)
+        assert np.array_equal(glue_ref.kmeans_predict_f32(f, mu).numpy(), want)
+        assert np.array_equal(want[: M // 2], idx[: M // 2].numpy())          # the near-centroid rows are unambiguous
+    cluster = pytest.importorskip("sklearn.cluster")
+    km = cluster.KMeans(n_clusters=K, n_init=1)
+    km.cluster_centers_, km._n_threads, km.n_features_in_, km._n_features_out = mu.numpy().astype(np.float32), 1, H, K
+    assert np.array_equal(km.predict(f.numpy()), want)
+
+
+def test_ida_emb_longtensor_quirk():
+    """I_da/scripts/inpainting.py:233: the d-vector goes through torch.LongTensor -> truncation toward zero."""
+    from oracle import glue_ref
+    emb = np.array([0.9, -0.9, 1.5, -2.7, 0.0, 3.0], dtype=np.float32)
+    assert glue_ref.ida_emb_longtensor(emb).tolist() == torch.LongTensor(emb).tolist() == [0, 0, 1, -2, 0, 3]
 
 
 def test_glue_oracle_vs_reference_golden(golden_dir):
