@@ -2,7 +2,8 @@
 """Turn the ncu launch-list CSV of `bench.py` (timed region selected with --nvtx --nvtx-include "sib_timed/") into the
 committed summaries under profiles/: one row per launch, and per-kernel-family totals (time share, DRAM bytes, tensor-pipe
 activity) that bench.py reads for `roofline.traffic`.
-Usage: python scripts/summarize_ncu_launches.py gpurun_out/launches_vNN.csv vNN [steps]"""
+Usage: python scripts/summarize_ncu_launches.py gpurun_out/launches_vNN.csv vNN [steps] [round] [git_head] [workload]
+The git head of the tree the capture was taken on is stamped into the summary (bench.py quotes it in roofline.traffic_note)."""
 import collections
 import csv
 import json
@@ -27,6 +28,9 @@ def family(name):
 def main():
     src, tag = sys.argv[1], sys.argv[2]
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    rnd = sys.argv[4] if len(sys.argv) > 4 else "r02"
+    head = sys.argv[5] if len(sys.argv) > 5 else "unknown"
+    wkl = sys.argv[6] if len(sys.argv) > 6 else "cfg2"
     hdr, recs = None, collections.OrderedDict()
     for r in csv.reader(open(src)):
         if r and r[0] == "ID":
@@ -64,9 +68,10 @@ def main():
                     "dram_write_bytes_per_step": a["wr"] / steps, "tensor_pipe_active_pct_time_weighted": round(tp, 1)})
     json.dump({"source": "ncu --nvtx --nvtx-include sib_timed/ --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
                          "dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none "
-                         f"python bench.py --steps {steps} --warmup 3 --no-cpu-baseline (B200, r01 {tag})",
-               "steps": steps, "kernels": out}, open(f"profiles/r01_ncu_step_{tag}_summary.json", "w"), indent=1)
-    with open(f"profiles/r01_ncu_launches_{tag}.csv", "w") as f:
+                         f"python bench.py --workload {wkl} --steps {steps} --warmup 3 --no-cpu-baseline (B200, {rnd} {tag})",
+               "git_head": head, "workload": wkl, "steps": steps, "kernels": out},
+              open(f"profiles/{rnd}_ncu_step_{tag}_summary.json", "w"), indent=1)
+    with open(f"profiles/{rnd}_ncu_launches_{tag}.csv", "w") as f:
         w = csv.writer(f)
         w.writerow(["id", "kernel", "grid", "block", "gpu__time_duration.sum[us]", "dram__bytes_read.sum", "dram__bytes_write.sum",
                     "sm__pipe_tensor_cycles_active.pct"])
