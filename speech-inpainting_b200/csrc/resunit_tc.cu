@@ -43,6 +43,7 @@ struct RuArgs {
   int c_cta;                                             // weight rows (output channels) this CTA holds per tap: C, or C/2 in pair mode
   float slope_in, slope_mid, out_scale, act2_slope;
   int accumulate, has_y2;
+  int early_w;                                           // resident weights fetched before the PDL dependency wait
   uint32_t desc_hi, idesc;
   uint32_t tmem_cols;
 };
@@ -138,7 +139,8 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (PAIR) mbar_arrive_cluster(bar, 0);
     else mbar_arrive(bar);
   };
-  sib::pdl_wait();                 // PDL: the prologue above overlapped the previous kernel's tail
+  // PDL: the prologue above overlapped the previous kernel's tail.  Only the x producer and epilogue 2 touch activations
+  // in global memory and wait for the previous grid; the resident weights are fetched before that wait.
   sib::pdl_launch_dependents();
 
   // work list: tile i of this CTA = first + i * step.  Pair mode: cluster c takes tile pairs c, c + #clusters, ...; CTA r of
@@ -174,6 +176,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one raw x tile per output tile =====================
     const uint32_t issuer = elect_one_sync();
+    if (!p.early_w) sib::pdl_wait();
     if (issuer) {
       // pair: each CTA loads its half of the output channels; both halves complete on the even CTA's barrier
       if (!PAIR || cta_rank == 0) mbar_expect_tx(w_full, (uint32_t)((PAIR ? 4 : 2) * p.w_tx_bytes));
@@ -187,6 +190,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         }
       }
     }
+    sib::pdl_wait();
     int s = 0;
     uint32_t ph = 0;
     TileCursor tc = cursor0();
@@ -247,21 +251,38 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   } else if (warp == 2 || warp == 3 || warp >= 12) {
     // ===================== activation: leaky-relu in place on the freshly landed x tile =====================
     // (six warps: with two, this stage paced the whole kernel on the short k = 3 tiles - the MMA warp sat on act_done)
+    // bf16x2 arithmetic as in sib_conv1d_bf16: slope * x = x * hi + x * lo with hi + lo = slope to ~2^-17 (no slope bias
+    // from rounding 0.1 to bf16), then max(x, slope * x): 12 instead of 28 ALU instructions per 16-byte chunk
     const int tid = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
     const int n16 = (p.xr * p.row_bytes) >> 4;
-    const float slope = p.slope_in;
+    const __nv_bfloat16 s_hi = __float2bfloat16_rn(p.slope_in);
+    const __nv_bfloat16 s_lo = __float2bfloat16_rn(p.slope_in - __bfloat162float(s_hi));
+    const __nv_bfloat162 hi2 = __halves2bfloat162(s_hi, s_hi), lo2 = __halves2bfloat162(s_lo, s_lo);
     int s = 0;
     uint32_t ph = 0;
     for (int i = 0; i < n_my; ++i) {
       mbar_wait(&x_full[s], ph);
       const uint32_t tile = smem_u32(sm_x + s * p.x_stage_bytes);
-#pragma unroll 4
-      for (int e = tid; e < n16; e += ACT_WARPS * 32) {
-        float f[8];
-        unpack8(lds128(tile + (uint32_t)e * 16u), f);
+      int e = tid;
+      for (; e + 3 * ACT_WARPS * 32 < n16; e += 4 * ACT_WARPS * 32) {      // four chunks in flight per thread
+        uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], f[u] * slope);      // leaky-relu, 0 < slope < 1
-        sts128(tile + (uint32_t)e * 16u, pack8(f));
+        for (int j = 0; j < 4; ++j) v[j] = lds128(tile + (uint32_t)(e + j * ACT_WARPS * 32) * 16u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v[j]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) h[u] = __hmax2(h[u], __hfma2(h[u], lo2, __hmul2(h[u], hi2)));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts128(tile + (uint32_t)(e + j * ACT_WARPS * 32) * 16u, v[j]);
+      }
+      for (; e < n16; e += ACT_WARPS * 32) {
+        uint4 v = lds128(tile + (uint32_t)e * 16u);
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = __hmax2(h[u], __hfma2(h[u], lo2, __hmul2(h[u], hi2)));
+        sts128(tile + (uint32_t)e * 16u, v);
       }
       fence_async_smem();
       __syncwarp();
@@ -331,6 +352,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t pre_bytes = (uint32_t)(1 + (p.accumulate ? 1 : 0)) * (uint32_t)box_bytes;
     const int rows_q = q < 3 ? 32 : p.tail_rows;               // rows of this quarter that belong to the tile (R = 96 + tail)
     uint64_t* my_res = res_bar + q * 3;
+    sib::pdl_wait();                                           // residual / running-sum reads and the stores below
     auto prefetch = [&](const TileCursor& c, int slot) {       // lane 0 only
       const int t0 = c.t0(), b = c.bb();
       mbar_expect_tx(&my_res[slot], pre_bytes);
@@ -363,31 +385,37 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       res_phase_bits ^= 1u << slot;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((p.na1 + a) * p.C);
+      // 16 columns per call: both residual (and running-sum) chunks are fetched up front - the shared-memory accesses are
+      // volatile asm and keep their program order, so loads issued inside the per-chunk loop would serialise every chunk's
+      // LDS latency behind the previous chunk's stores (ncu: this warp group was 93 % busy and paced the k = 3 units)
       auto emit16 = [&](const uint32_t (&v)[16], int c0) {
+        const uint32_t off0 = (((uint32_t)c0 >> 3) ^ swz) << 4, off1 = ((((uint32_t)c0 >> 3) + 1) ^ swz) << 4;
+        const uint4 x0 = lds128(box_a + off0), x1 = lds128(box_a + off1);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col = c0 + 8 * h;
-          const uint32_t off = (((uint32_t)col >> 3) ^ swz) << 4;
           const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + col));
           const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col + 4));
           float f[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           float xr[8];
-          unpack8(lds128(box_a + off), xr);
+          unpack8(h ? x1 : x0, xr);
 #pragma unroll
           for (int u = 0; u < 8; ++u) f[u] += __uint_as_float(v[8 * h + u]) + xr[u];
-          if (p.accumulate) {
+          if (p.accumulate) {                                    // (2 of the 9 units of a stage: loaded in place)
             float o[8];
-            unpack8(lds128(box_b + off), o);
+            unpack8(lds128(box_b + (h ? off1 : off0)), o);
 #pragma unroll
             for (int u = 0; u < 8; ++u) f[u] += o[u];
           }
+          if (p.out_scale != 1.f) {                              // only the last unit of a stage carries the MRF 1/3
 #pragma unroll
-          for (int u = 0; u < 8; ++u) f[u] *= p.out_scale;
-          sts128(box_a + off, pack8(f));
+            for (int u = 0; u < 8; ++u) f[u] *= p.out_scale;
+          }
+          sts128(box_a + (h ? off1 : off0), pack8(f));
           if (p.has_y2) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) f[u] = f[u] > 0.f ? f[u] : f[u] * p.act2_slope;
-            sts128(box_b + off, pack8(f));
+            for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], f[u] * p.act2_slope);   // leaky-relu, 0 < slope <= 1
+            sts128(box_b + (h ? off1 : off0), pack8(f));
           }
         }
       };
@@ -546,6 +574,8 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
               "sib_resunit_bf16: leaky-relu slopes must be in (0, 1] (max(x, slope x) form)");
   a.b1 = b1; a.b2 = b2;
   a.T = d->t; a.batch = d->batch;
+  static const bool early_w = !(getenv("SIB_PDL_EARLY_W") && atoi(getenv("SIB_PDL_EARLY_W")) == 0);
+  a.early_w = early_w ? 1 : 0;
   a.slope_in = d->slope_in; a.slope_mid = d->slope_mid; a.out_scale = d->out_scale; a.act2_slope = d->act2_slope;
   a.tiles_m = sib::ceil_div(d->t, a.R);
   const int64_t total = (int64_t)a.tiles_m * d->batch;

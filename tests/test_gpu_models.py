@@ -558,21 +558,34 @@ def test_plan_cache_is_bounded_over_many_distinct_lengths(sib):
     gen = sib.Generator(sib.AttrDict(gcfg.as_attrdict())).to("cuda")
     gen.load_state_dict(make_generator_params(gcfg, 1, "unit"))
     first = {}
-    peak = []
-    for i in range(60):
-        n, tm = 4000 + 160 * i, 20 + i
-        y = hub(torch.zeros(2, n, device="cuda") + 0.01 * i).last_hidden_state
-        w = gen(torch.full((2, 80, tm), 0.01 * i, device="cuda"))
-        if i == 0:
-            first = (y.clone(), w.clone())
+    shapes = [(4000 + 160 * i, 20 + i) for i in range(60)]
+
+    def run(hub_, gen_, todo):
+        out = None
+        for n, tm in todo:
+            y = hub_(torch.zeros(2, n, device="cuda") + 1e-4 * n).last_hidden_state
+            w = gen_(torch.full((2, 80, tm), 1e-4 * n, device="cuda"))
+            out = out or (y.clone(), w.clone())
         torch.cuda.synchronize()
-        peak.append(torch.cuda.memory_allocated())
+        return out
+
+    base = torch.cuda.memory_allocated()
+    first = run(hub, gen, shapes)
+    after_60 = torch.cuda.memory_allocated() - base
     assert len(hub._plans) <= hub._plans.max_plans and len(gen._plans) <= gen._plans.max_plans
     assert hub._plans.evictions >= 60 - hub._plans.max_plans
-    assert max(peak[20:]) <= 1.5 * max(peak[:12]) + (8 << 20), (peak[:12], peak[-5:])
+    # what the resident plans alone need: fresh modules that only ever saw the last `max_plans` shapes
+    hub2 = sib.HubertModel(_hub_cfg(sib, ocfg)).to("cuda")
+    hub2.load_state_dict(make_hubert_params(ocfg, 1))
+    gen2 = sib.Generator(sib.AttrDict(gcfg.as_attrdict())).to("cuda")
+    gen2.load_state_dict(make_generator_params(gcfg, 1, "unit"))
+    base2 = torch.cuda.memory_allocated()
+    run(hub2, gen2, shapes[-hub._plans.max_plans:])
+    resident = torch.cuda.memory_allocated() - base2
+    assert after_60 <= 1.25 * resident + (4 << 20), (after_60, resident)       # 60 shapes hold what 6 shapes hold
     # an evicted shape is simply re-planned and reproduces its first answer bit for bit
-    y0 = hub(torch.zeros(2, 4000, device="cuda")).last_hidden_state
-    assert torch.equal(y0, first[0]) and torch.equal(gen(torch.zeros(2, 80, 20, device="cuda")), first[1])
+    y0 = hub(torch.zeros(2, 4000, device="cuda") + 1e-4 * 4000).last_hidden_state
+    assert torch.equal(y0, first[0]) and torch.equal(gen(torch.full((2, 80, 20), 1e-4 * 4000, device="cuda")), first[1])
 
 
 def test_wrong_current_device_is_refused_loudly(sib):
