@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsib_b200.so")
+# SIB_LIB_VARIANT=<tag> loads libsib_b200_<tag>.so instead: same-box A/B of two kernel builds (e.g. a baseline build of an
+# older tree kept beside the current one); unset in normal use
+LIB_PATH = os.path.join(HERE, "libsib_b200" + ("_" + os.environ["SIB_LIB_VARIANT"] if os.environ.get("SIB_LIB_VARIANT") else "") + ".so")
 
 SIB_MAX_TAPS = 128
 ACT_NONE, ACT_GELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3

@@ -67,7 +67,6 @@ struct TcArgs {
   int a_sub_bytes, b_sub_bytes;  // bytes of one (tap) sub-tile of A / B inside a stage
   uint32_t desc_hi;              // SBO / version / swizzle bits of the smem matrix descriptor (bits 32..63)
   uint32_t idesc;
-  int early_w;                   // weights' first TMA loads go out BEFORE the PDL dependency wait (A/B: SIB_PDL_EARLY_W=0)
   int pre_act;                   // halo mode: leaky-relu(pre_slope) applied in place to every landed A tile (warp 3)
   float pre_slope;
   int tap_row[SIB_MAX_TAPS];     // row coordinate delta per tap
@@ -122,10 +121,13 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 // loads its own 128 A rows and its own half (bn/2 rows) of every weight slab, the even CTA issues M = 256 MMAs that
 // read both shared memories and write both TMEMs.  Per CTA the B bytes (TMA writes, L2 traffic, MMA operand reads)
 // halve, and with half the columns per CTA twice as many weight sets stay resident.
-// NARROW = true: the two-CTAs-per-SM build (<= 85 registers) for the bn <= 32 layers; every other single-CTA launch runs one
-// CTA per SM anyway (shared memory), so it gets the full register file instead of that cap.
-template <int POST_ACT, bool PAIR, bool NARROW = false>
-__global__ void __launch_bounds__(PAIR ? NUM_THREADS_PAIR : NUM_THREADS, (PAIR || !NARROW) ? 1 : 2)
+// HOIST = true: the epilogue build for layers with a residual input added before the activation (every second conv of a
+// HiFi-GAN unit): the residual chunks of a 16-column group are fetched before any arithmetic.  It is a SEPARATE
+// instantiation on purpose - the short HuBERT GEMMs are sensitive to the epilogue's instruction schedule, code size and
+// register allocation (any edit to the shared lambda cost them 4-19 % in same-box A/Bs), so the plain layers keep the
+// original code untouched.  HOIST kernels always run one CTA per SM (no 85-register cap).
+template <int POST_ACT, bool PAIR, bool HOIST = false>
+__global__ void __launch_bounds__(PAIR ? NUM_THREADS_PAIR : NUM_THREADS, (PAIR || HOIST) ? 1 : 2)
 conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y2,
                       const __grid_constant__ CUtensorMap map_r, const __grid_constant__ TcArgs p) {
@@ -191,10 +193,8 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent loop over (pair) tiles
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  // PDL: everything above overlapped the previous kernel's tail.  Only the roles that touch ACTIVATIONS in global memory
-  // (A producer, epilogue) wait for the previous grid below; the weights never depend on it, so their first TMA loads
-  // go out before the wait: a CTA that got its SM while the predecessor's last tiles are still running elsewhere fills
-  // its weight ring (2/3 of a plain GEMM's operand bytes) during that tail instead of after it.
+  // PDL: everything above overlapped the previous kernel's tail; from here on global memory is touched
+  sib::pdl_wait();
   sib::pdl_launch_dependents();
 
   // tile -> (n fastest, m, batch*group): CTAs that run concurrently share the same A rows in L2
@@ -217,29 +217,6 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t issuer = elect_one_sync();
     int stage = 0;
     uint32_t phase = 0;
-    // mode 0: weight halves of the first ring fill (first tile only) before the dependency wait
-    int npre = 0;
-    if (p.mode == 0 && p.early_w && tile0 < p.total_tiles) {
-      int t0, n0, b, g;
-      decode(tile0, t0, n0, b, g);
-      const int iters = p.n_chunks * p.n_tapblocks;
-      npre = iters < p.stages ? iters : p.stages;
-      int cc = 0, tb = 0;
-      for (int it = 0; it < npre; ++it) {
-        uint8_t* b_dst = smem + it * p.stage_bytes + A_STAGE_BYTES;
-        const int nsub = min(p.tb, p.n_taps - tb * p.tb);
-        if (issuer) {
-          if (!PAIR || cta_rank == 0)
-            mbar_expect_tx(&a_full[it], (uint32_t)((PAIR ? 2 : 1) * nsub) * (uint32_t)(p.a_sub_bytes + p.b_sub_bytes));
-          for (int sidx = 0; sidx < nsub; ++sidx)
-            tma_ld<PAIR>(b_dst + sidx * p.b_sub_bytes, &map_b, &a_full[it], 0, n0 + (int)cta_rank * p.bn_cta,
-                         (g * p.n_chunks + cc) * p.n_taps + tb * p.tb + sidx);
-        }
-        if (++tb == p.n_tapblocks) { tb = 0; ++cc; }
-      }
-    }
-    sib::pdl_wait();
-    int g_it = 0;   // iterations issued so far (mode 0): the first npre already carry their expect_tx and weight loads
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
       int t0, n0, b, g;
       decode(tile, t0, n0, b, g);
@@ -267,18 +244,15 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           uint8_t* a_dst = smem + stage * p.stage_bytes;
           uint8_t* b_dst = a_dst + A_STAGE_BYTES;
           const int nsub = min(p.tb, p.n_taps - tb * p.tb);
-          const bool b_done = g_it < npre;     // weight half (and expect_tx) of this stage went out before the wait
-          ++g_it;
           if (issuer) {
-            if (!b_done && (!PAIR || cta_rank == 0))
+            if (!PAIR || cta_rank == 0)
               mbar_expect_tx(&a_full[stage], (uint32_t)((PAIR ? 2 : 1) * nsub) * (uint32_t)(p.a_sub_bytes + p.b_sub_bytes));
             for (int sidx = 0; sidx < nsub; ++sidx) {
               const int j = tb * p.tb + sidx;
               tma_ld<PAIR>(a_dst + sidx * p.a_sub_bytes, &map_a, &a_full[stage], g * p.cin_g + cc * p.cc + p.tap_ch[j],
                            t0 + p.tap_row[j], b);
-              if (!b_done)
-                tma_ld<PAIR>(b_dst + sidx * p.b_sub_bytes, &map_b, &a_full[stage], 0, n0 + (int)cta_rank * p.bn_cta,
-                             (g * p.n_chunks + cc) * p.n_taps + j);
+              tma_ld<PAIR>(b_dst + sidx * p.b_sub_bytes, &map_b, &a_full[stage], 0, n0 + (int)cta_rank * p.bn_cta,
+                           (g * p.n_chunks + cc) * p.n_taps + j);
             }
           }
           if (++tb == p.n_tapblocks) { tb = 0; ++cc; }
@@ -289,7 +263,6 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   } else if (warp == 2) {
     // ===================== B producer (mode 1) =====================
     const uint32_t issuer = elect_one_sync();
-    if (!p.early_w) sib::pdl_wait();
     if (p.mode == 1) {
       if (p.b_resident) {
         // every tile of this launch uses the same weights: load them once (groups == 1, tiles_n == 1)
@@ -435,7 +408,6 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int q = warp & 3;
     const int half = (warp - EPI_WARP0) >> 2;
     const int NB = p.nb;
-    sib::pdl_wait();                                 // residual / accumulate reads and every store below touch activations
     const int row_bytes = p.cw * 2;                  // 128 / 64 / 32: also the TMA swizzle width of the boxes
     const int chunks_per_row = row_bytes >> 4;       // 16-byte chunks per box row
     const int swz_shift = row_bytes == 128 ? 0 : (row_bytes == 64 ? 1 : 2);
@@ -488,17 +460,11 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int cb = blk * p.cw;                   // first tile column of this block
         // the two warps of a pair take the two column halves of the block; with cw == 64 that is 32 columns per
         // warp: both 16-column TMEM loads are issued before the single wait
-        // 16 columns per call.  The shared-memory accesses are volatile asm and keep their program order: the residual /
-        // running-sum chunks of BOTH 8-column halves are fetched before any arithmetic and all stores come last, so one
-        // LDS latency is exposed per call instead of one per half behind the previous half's stores.
-        auto process16 = [&](const uint32_t (&v)[16], const int c0) {
-          const uint32_t rowoff = (uint32_t)(lane * row_bytes);
-          const uint32_t off0 = rowoff + ((((uint32_t)c0 >> 3) ^ swz) << 4), off1 = rowoff + (((((uint32_t)c0 >> 3) + 1) ^ swz) << 4);
-          uint4 rr[2];
-          if (p.has_res) { rr[0] = lds128(sr + off0); rr[1] = lds128(sr + off1); }
+        auto process16_plain = [&](const uint32_t (&v)[16], const int c0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int col = c0 + 8 * h;              // column inside the box
+            const uint32_t off = (uint32_t)(lane * row_bytes) + ((((uint32_t)col >> 3) ^ swz) << 4);
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]);
@@ -510,15 +476,15 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
             float r[8];
             if (p.has_res) {
-              unpack8(rr[h], r);
+              unpack8(lds128(sr + off), r);
               if (!p.res_after_act) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += r[i];
               }
             }
-            if (p.accumulate) {                      // (2 of the 9 units of a stage: loaded in place)
+            if (p.accumulate) {
               float o[8];
-              unpack8(lds128(sy + (h ? off1 : off0)), o);
+              unpack8(lds128(sy + off), o);
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += o[i];
             }
@@ -528,13 +494,56 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += r[i];
             }
-            sts128(sy + (h ? off1 : off0), pack8(f));
+            sts128(sy + off, pack8(f));
             if (p.has_y2) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * p.act2_slope;
-              sts128(sr + (h ? off1 : off0), pack8(f));
+              sts128(sr + off, pack8(f));
             }
           }
+        };
+        // HOIST: the shared-memory accesses are volatile asm and keep their program order, so with the residual load inside the
+        // per-half loop every half exposes its LDS latency behind the previous half's stores; here both chunks of the 16
+        // columns are fetched first and all stores follow the arithmetic of their half.
+        auto process16_hoist = [&](const uint32_t (&v)[16], const int c0) {
+          const uint32_t rowoff = (uint32_t)(lane * row_bytes);
+          const uint32_t off0 = rowoff + ((((uint32_t)c0 >> 3) ^ swz) << 4), off1 = rowoff + (((((uint32_t)c0 >> 3) + 1) ^ swz) << 4);
+          uint4 rr[2];
+          rr[0] = lds128(sr + off0);
+          rr[1] = lds128(sr + off1);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = c0 + 8 * h;              // column inside the box
+            const uint32_t off = h ? off1 : off0;
+            float f[8], r[8];
+            unpack8(rr[h], r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]) + r[i];
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (p.accumulate) {                      // (2 of the 9 units of a stage: loaded in place)
+              float o[8];
+              unpack8(lds128(sy + off), o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += o[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = act_t<POST_ACT>(f[i] * p.out_scale, p.post_slope);
+            sts128(sy + off, pack8(f));
+            if (p.has_y2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * p.act2_slope;
+              sts128(sr + off, pack8(f));
+            }
+          }
+        };
+        auto process16 = [&](const uint32_t (&v)[16], const int c0) {
+          if constexpr (HOIST) process16_hoist(v, c0);
+          else process16_plain(v, c0);
         };
         if (p.cw == 64) {
           uint32_t va[16], vb[16];
@@ -793,8 +802,6 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
   }
   a.pre_act = d->pre_act == SIB_ACT_LRELU ? 1 : 0;
   a.pre_slope = d->pre_slope;
-  static const bool early_w = !(getenv("SIB_PDL_EARLY_W") && atoi(getenv("SIB_PDL_EARLY_W")) == 0);
-  a.early_w = early_w ? 1 : 0;
   if (a.pre_act && a.mode != 1) {
     sib::set_error("sib_conv1d_bf16: pre-activation needs the halo mode (stride 1, > 1 evenly spaced taps, tile fits); "
                    "have the producer write the activated tensor (y_act) for this layer");
@@ -873,8 +880,9 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
                            (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, false>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH, false>,
                            (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, true>,
                            (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH, true>,
-                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, false, true>,
-                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, false, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH, false, true>};
+                           // residual-before-activation layers (HiFi-GAN conv2 of a unit, ResBlock2 convs): no activation or leaky-relu
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, false, true>,
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, true, true>};
     for (const void* fn : fns) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) {
@@ -889,23 +897,30 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
   const int grid = (a.total_tiles < slots ? a.total_tiles : slots) * (pair ? 2 : 1);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   cudaError_t le = cudaSuccess;
-#define SIB_TC_LAUNCH(ACT)                                                                                              \
-  le = pair ? sib::launch_pdl_cluster(conv1d_bf16_tc_kernel<ACT, true>, dim3(grid), dim3(NUM_THREADS_PAIR), (size_t)smem_bytes, cs, \
-                                      2u, map_a, map_b, map_y, map_y2, map_r, a)                                        \
-      : ctas_per_sm == 2                                                                                                \
-          ? sib::launch_pdl(conv1d_bf16_tc_kernel<ACT, false, true>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
-                            map_a, map_b, map_y, map_y2, map_r, a)                                                      \
-          : sib::launch_pdl(conv1d_bf16_tc_kernel<ACT, false, false>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
-                            map_a, map_b, map_y, map_y2, map_r, a)
-  switch (d->post_act) {
-    case SIB_ACT_NONE: SIB_TC_LAUNCH(SIB_ACT_NONE); break;
-    case SIB_ACT_GELU: SIB_TC_LAUNCH(SIB_ACT_GELU); break;
-    case SIB_ACT_LRELU: SIB_TC_LAUNCH(SIB_ACT_LRELU); break;
-    case SIB_ACT_TANH: SIB_TC_LAUNCH(SIB_ACT_TANH); break;
-    default:
-      SIB_REQUIRE(false, "sib_conv1d_bf16: unknown post_act %d", d->post_act);
+#define SIB_TC_LAUNCH_H(ACT, HOIST)                                                                                     \
+  le = pair ? sib::launch_pdl_cluster(conv1d_bf16_tc_kernel<ACT, true, HOIST>, dim3(grid), dim3(NUM_THREADS_PAIR),      \
+                                      (size_t)smem_bytes, cs, 2u, map_a, map_b, map_y, map_y2, map_r, a)                \
+            : sib::launch_pdl(conv1d_bf16_tc_kernel<ACT, false, HOIST>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
+                              map_a, map_b, map_y, map_y2, map_r, a)
+#define SIB_TC_LAUNCH(ACT) SIB_TC_LAUNCH_H(ACT, false)
+  static const bool hoist_on = !(getenv("SIB_TC_HOIST") && atoi(getenv("SIB_TC_HOIST")) == 0);   // A/B switch
+  const bool hoist = hoist_on && a.has_res && !a.res_after_act && ctas_per_sm == 1 &&
+                     (d->post_act == SIB_ACT_NONE || d->post_act == SIB_ACT_LRELU);
+  if (hoist) {
+    if (d->post_act == SIB_ACT_NONE) SIB_TC_LAUNCH_H(SIB_ACT_NONE, true);
+    else SIB_TC_LAUNCH_H(SIB_ACT_LRELU, true);
+  } else {
+    switch (d->post_act) {
+      case SIB_ACT_NONE: SIB_TC_LAUNCH(SIB_ACT_NONE); break;
+      case SIB_ACT_GELU: SIB_TC_LAUNCH(SIB_ACT_GELU); break;
+      case SIB_ACT_LRELU: SIB_TC_LAUNCH(SIB_ACT_LRELU); break;
+      case SIB_ACT_TANH: SIB_TC_LAUNCH(SIB_ACT_TANH); break;
+      default:
+        SIB_REQUIRE(false, "sib_conv1d_bf16: unknown post_act %d", d->post_act);
+    }
   }
 #undef SIB_TC_LAUNCH
+#undef SIB_TC_LAUNCH_H
   if (le != cudaSuccess) {
     sib::set_error("sib_conv1d_bf16: launch failed: %s", cudaGetErrorString(le));
     return SIB_ERR_CUDA;
