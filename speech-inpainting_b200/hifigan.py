@@ -64,6 +64,10 @@ class Generator(SibModule):
         # bf16 arm: unfused convs apply the leaky-relu that precedes them to their A tile in shared memory, so producers
         # stop writing an activated copy of every tensor (A/B switch, SIB_SMEM_PREACT=0)
         self.use_smem_preact = os.environ.get("SIB_SMEM_PREACT", "1") != "0"
+        # bf16 arm: utterances per chunk when a ResBlock's unit chain is run chunk by chunk (0 = whole batch per launch)
+        self.rb_chunk = int(os.environ.get("SIB_RB_CHUNK", "0"))
+        # bf16 arm: the ResBlocks of a stage as concurrent chains on separate streams (A/B switch SIB_RB_STREAMS=0/1)
+        self.rb_streams = os.environ.get("SIB_RB_STREAMS", "0") != "0"
         # parameters under the reference's checkpoint names, WITH weight-norm (weight_g / weight_v) as `Generator.__init__`
         # creates them (models.py:82-105): 234 tensors for V1
         for name, shape in self._conv_shapes().items():
@@ -188,10 +192,16 @@ class Generator(SibModule):
             L *= u
             lens.append(L)
         big = max(l * c for l, c in zip(lens, chans))
-        pool = [torch.empty(B * big, **b16) for _ in range(11)]
+        # the MRF's ResBlocks of a stage are independent chains of units (models.py:113-118); with `rb_streams` they are
+        # recorded on separate plan chains (own scratch tensors each), so the tail of one chain's kernel overlaps the head
+        # of another's instead of leaving SMs idle at every launch boundary
+        n_ch = self.num_kernels if (self.rb_streams and self.num_kernels > 1) else 1
+        pool = [torch.empty(B * big, **b16) for _ in range(11 + 5 * (n_ch - 1))]
         UP, UPA, PA, PAA, PB, PBA, T1, XS0, XS0A, XS1, XS1A = range(11)
 
-        def view(i, L_, C_):
+        def view(i, L_, C_, ch=0):
+            if ch > 0 and i in (PA, PAA, PB, PBA, T1):          # chain-private scratch
+                i = 11 + 5 * (ch - 1) + (PA, PAA, PB, PBA, T1).index(i)
             return pool[i][: B * L_ * C_].view(B, L_, C_)
 
         plan = Plan()
@@ -247,43 +257,61 @@ class Generator(SibModule):
                 else:
                     ops.conv1d(cur_act, P[f"ups.{i}.w"], P[f"ups.{i}.b"], up.view(B, t_in, u * C_), P[f"ups.{i}.taps"],
                                y_act=up_act.view(B, t_in, u * C_) if need_up_act else None, act2_slope=LRELU_SLOPE)
+                # A ResBlock's chain of units runs per CHUNK of utterances (`rb_chunk`): a chunk's tensors (45 MB for 8
+                # utterances of the 32 x 4 s workload) then stay in the 126 MB L2 from one unit to the next - the conv1 -> conv2
+                # intermediate of the unfused units and the unit -> unit hand-offs never make the HBM round trip.
+                cb = self.rb_chunk if self.rb_chunk and self.rb_chunk > 0 else B
+                chunks = [(b0, min(b0 + cb, B)) for b0 in range(0, B, cb)]
+                if n_ch > 1:
+                    plan.fork()
                 for j, (rk, dils) in enumerate(zip(self.rb_kernels, self.rb_dilations)):
                     n = i * self.num_kernels + j
                     last_j = j == self.num_kernels - 1
-                    xcur, xcur_act = up, (up_act if need_up_act else None)
-                    for m, dl in enumerate(dils):
-                        last_m = m == len(dils) - 1
-                        if last_m:
-                            dst, dst_act = xs, (xs_act if (last_j and next_needs_act) else None)
-                            # the next consumer of xs is lrelu(0.1)->ups[i+1] or lrelu(0.01)->conv_post
-                            slope2 = 0.01 if last_stage else LRELU_SLOPE
-                        else:
-                            dst, dst_act = (view(PA, L_, C_), view(PAA, L_, C_)) if m % 2 == 0 else (view(PB, L_, C_), view(PBA, L_, C_))
-                            slope2 = LRELU_SLOPE
-                            if self_act[j][m + 1]:
-                                dst_act = None      # the consumer activates its own input tile
-                        acc = last_m and j > 0
-                        scale = (1.0 / self.num_kernels) if (last_m and last_j) else 1.0
-                        if fused[j][m]:
-                            ops.resunit(xcur, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
-                                        P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
-                                        dst, rk, dl, y_act=dst_act, accumulate=acc, out_scale=scale,
-                                        slope_in=LRELU_SLOPE, slope_mid=LRELU_SLOPE, act2_slope=slope2)
-                        else:
-                            kw = dict(accumulate=acc, out_scale=scale, residual=xcur, y_act=dst_act, act2_slope=slope2)
-                            # first conv of the unit: raw x + in-kernel leaky-relu, or the producer's activated copy
-                            src, pkw = (xcur, dict(pre_slope=LRELU_SLOPE)) if self_act[j][m] else (xcur_act, {})
-                            if self.resblock == "1":
-                                t1 = view(T1, L_, C_)
-                                ops.conv1d(src, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
-                                           t1, ops.conv_taps(rk, dl, get_padding(rk, dl)), post_act=ops.ACT_LRELU,
-                                           post_slope=LRELU_SLOPE, **pkw)
-                                ops.conv1d(t1, P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
-                                           dst, ops.conv_taps(rk, 1, get_padding(rk, 1)), **kw)
+                    chn = j if n_ch > 1 else 0
+                    for b0, b1 in chunks:
+                      with plan.chain(chn):
+                        sl = lambda t: None if t is None else t[b0:b1]   # noqa: E731
+                        xcur, xcur_act = sl(up), (sl(up_act) if need_up_act else None)
+                        for m, dl in enumerate(dils):
+                            last_m = m == len(dils) - 1
+                            if last_m:
+                                dst, dst_act = sl(xs), (sl(xs_act) if (last_j and next_needs_act) else None)
+                                # the next consumer of xs is lrelu(0.1)->ups[i+1] or lrelu(0.01)->conv_post
+                                slope2 = 0.01 if last_stage else LRELU_SLOPE
                             else:
-                                ops.conv1d(src, P[f"resblocks.{n}.convs.{m}.w"], self._sd[f"resblocks.{n}.convs.{m}.bias"],
-                                           dst, ops.conv_taps(rk, dl, get_padding(rk, dl)), **kw, **pkw)
-                        xcur, xcur_act = dst, dst_act
+                                dst, dst_act = ((sl(view(PA, L_, C_, chn)), sl(view(PAA, L_, C_, chn))) if m % 2 == 0
+                                                else (sl(view(PB, L_, C_, chn)), sl(view(PBA, L_, C_, chn))))
+                                slope2 = LRELU_SLOPE
+                                if self_act[j][m + 1]:
+                                    dst_act = None      # the consumer activates its own input tile
+                            acc = last_m and j > 0
+                            scale = (1.0 / self.num_kernels) if (last_m and last_j) else 1.0
+                            if acc and n_ch > 1:          # the running MRF sum: after the previous ResBlock's last unit
+                                plan.wait(("xs", i, j - 1, b0))
+                            if fused[j][m]:
+                                ops.resunit(xcur, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
+                                            P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
+                                            dst, rk, dl, y_act=dst_act, accumulate=acc, out_scale=scale,
+                                            slope_in=LRELU_SLOPE, slope_mid=LRELU_SLOPE, act2_slope=slope2)
+                            else:
+                                kw = dict(accumulate=acc, out_scale=scale, residual=xcur, y_act=dst_act, act2_slope=slope2)
+                                # first conv of the unit: raw x + in-kernel leaky-relu, or the producer's activated copy
+                                src, pkw = (xcur, dict(pre_slope=LRELU_SLOPE)) if self_act[j][m] else (xcur_act, {})
+                                if self.resblock == "1":
+                                    t1 = sl(view(T1, L_, C_, chn))
+                                    ops.conv1d(src, P[f"resblocks.{n}.convs1.{m}.w"], self._sd[f"resblocks.{n}.convs1.{m}.bias"],
+                                               t1, ops.conv_taps(rk, dl, get_padding(rk, dl)), post_act=ops.ACT_LRELU,
+                                               post_slope=LRELU_SLOPE, **pkw)
+                                    ops.conv1d(t1, P[f"resblocks.{n}.convs2.{m}.w"], self._sd[f"resblocks.{n}.convs2.{m}.bias"],
+                                               dst, ops.conv_taps(rk, 1, get_padding(rk, 1)), **kw)
+                                else:
+                                    ops.conv1d(src, P[f"resblocks.{n}.convs.{m}.w"], self._sd[f"resblocks.{n}.convs.{m}.bias"],
+                                               dst, ops.conv_taps(rk, dl, get_padding(rk, dl)), **kw, **pkw)
+                            if last_m and n_ch > 1 and not last_j:
+                                plan.signal(("xs", i, j, b0))
+                            xcur, xcur_act = dst, dst_act
+                if n_ch > 1:
+                    plan.join()
                 cur, cur_act = xs, (xs_act if next_needs_act else None)
                 t_in = L_
             io.y = torch.empty(B, 1, lens[-1], **f32)

@@ -93,6 +93,14 @@ class Plan:
     def join(self):
         self.marks.setdefault(len(self.steps), []).append("join")
 
+    def signal(self, tag):
+        """Record an event on the CURRENT chain's stream after the steps recorded so far (see `wait`)."""
+        self.marks.setdefault(len(self.steps), []).append(("signal", tag, self._chain))
+
+    def wait(self, tag):
+        """The current chain's stream waits for the event `tag` of another chain before its next step."""
+        self.marks.setdefault(len(self.steps), []).append(("wait", tag, self._chain))
+
     def _launch_all(self, multi_stream: bool):
         main = torch.cuda.current_stream()
         s_main = main.cuda_stream
@@ -106,6 +114,8 @@ class Plan:
             if c not in self._side:
                 self._side[c] = torch.cuda.Stream(main.device)
         handles = {0: s_main, **{c: st.cuda_stream for c, st in self._side.items()}}
+        streams = {0: main, **self._side}
+        tagged = {}
         for i, ((fn, args, name), c) in enumerate(zip(self.steps, self.chains)):
             for m in self.marks.get(i, ()):
                 if m == "fork":
@@ -113,11 +123,17 @@ class Plan:
                     ev.record(main)
                     for st in self._side.values():
                         st.wait_event(ev)
-                else:
+                elif m == "join":
                     for st in self._side.values():
                         ev = torch.cuda.Event()
                         ev.record(st)
                         main.wait_event(ev)
+                elif m[0] == "signal":
+                    ev = torch.cuda.Event()
+                    ev.record(streams[m[2]])
+                    tagged[m[1]] = ev
+                else:   # ("wait", tag, chain)
+                    streams[m[2]].wait_event(tagged[m[1]])
             rc = fn(*args, handles[c])
             if rc:
                 _lib.check(rc, name)
