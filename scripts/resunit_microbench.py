@@ -19,6 +19,8 @@ SHAPES = {
     "s3k3d1": (32, 44032, 64, 3, 1, False, False),
     "s3k7d3": (32, 44032, 64, 7, 3, False, False),
     "s3k11d5": (32, 44032, 64, 11, 5, True, False),
+    "s2k3d1": (32, 22016, 128, 3, 1, False, False),      # stage 2, C = 128: wide CTA-pair variant
+    "s2k3d5": (32, 22016, 128, 3, 5, False, False),
 }
 
 

@@ -25,6 +25,11 @@ using namespace sib_tc;
 
 constexpr int NUM_THREADS = 512;
 constexpr int ACT_WARPS = 6;                        // warps 2-3 and 12-15
+// wide (C = 128) builds: 18 warps - epilogue 1 gets EIGHT warps (4-7: columns 0-63, 12-15: columns 64-127), because with the
+// single intermediate buffer that fits, conv2(i) -> epilogue 1(i+1) -> conv2(i+1) is a serial chain and its length is
+// what paces the kernel; the activation warps are 2-3 only (bf16x2 arithmetic: two warps keep up with the 36 KB tiles)
+constexpr int NUM_THREADS_WIDE = 512;              // (18 warps cap the registers at 113: epilogue 2's prefetch spilled, 0.185 -> 0.276 ms)
+constexpr int ACT_WARPS_WIDE = 2;
 
 struct RuArgs {
   const float* b1;
@@ -44,9 +49,29 @@ struct RuArgs {
   float slope_in, slope_mid, out_scale, act2_slope;
   int accumulate, has_y2;
   int early_w;                                           // resident weights fetched before the PDL dependency wait
+  // C = 128 ("wide", CTA pairs only): a row is TWO 64-channel chunks, every operand tile is two 128-byte-swizzled slabs
+  int nch;                                               // channel chunks per row: 1, or 2 when C = 128
+  int x_chunk_bytes, t1_chunk_bytes;                     // one chunk slab of an x stage / of the intermediate tile
+  const void* xg;                                        // wide: epilogue 2 reads the residual rows straight from global x
+  long long xg_batch_stride;                             //       (elements)
+  int xg_row_stride;
   uint32_t desc_hi, idesc;
   uint32_t tmem_cols;
 };
+
+// 16-byte shared-memory load of data that is constant for the kernel's lifetime (the bias vectors): NOT volatile and no
+// memory clobber, so the compiler may hoist and batch it freely
+__device__ __forceinline__ float4 lds_const_f4(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+// read-only 16-byte global load that does not allocate in L1 (streamed once per tile row)
+__device__ __forceinline__ uint4 ldg_stream(const uint4* ptr) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
 
 template <bool PAIR>
 __device__ __forceinline__ void commit_u(uint64_t* bar) {
@@ -59,8 +84,12 @@ __device__ __forceinline__ void commit_u(uint64_t* bar) {
 // stay resident.  The even CTA issues M = 256 MMAs for both; every hand-off towards the MMA warp (activated x tile,
 // intermediate tile, drained accumulators) is a remote arrive on the even CTA's barrier, every hand-off from it a
 // multicast commit.
-template <bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS, PAIR ? 1 : 2)
+// WIDE (C = 128, pairs only, k <= 3): both weight sets split over the pair are 96 KB per CTA, which leaves room for two x
+// stages, ONE intermediate tile and 16 KB of output staging - so epilogue 2 takes its residual rows straight from global
+// memory (the tile's x rows were fetched by TMA moments ago: L2 hits) and drains the tile in four 32-channel groups
+// through two small staging boxes per warp.  A separate instantiation: the C <= 64 builds keep their code.
+template <bool PAIR, bool WIDE = false>
+__global__ void __launch_bounds__(WIDE ? NUM_THREADS_WIDE : NUM_THREADS, PAIR ? 1 : 2)
 resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                   const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
                   const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yt,
@@ -74,7 +103,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint8_t* sm_w2 = sm_w1 + p.w_bytes;
   uint8_t* sm_sa = sm_w2 + p.w_bytes;                     // [2] staging A: residual in -> y out
   uint8_t* sm_sb = sm_sa + p.slots * p.stage_box_bytes;   // [slots] staging B: accumulate in -> y_act out
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_sb + (p.need_b ? p.slots * p.stage_box_bytes : 0));
+  // wide: both bias vectors live in shared memory (the residual rows that epilogue 2 streams through L1 evict the bias
+  // lines: ncu showed every bias add waiting on an L2 round trip)
+  float* sm_bias = reinterpret_cast<float*>(sm_sb + (p.need_b ? p.slots * p.stage_box_bytes : 0));   // [2][128] when WIDE
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm_bias) + (WIDE ? 1024 : 0));
   uint64_t* x_full = bars;            // [4]
   uint64_t* x_empty = bars + 4;       // [4]
   uint64_t* act_done = bars + 8;      // [4]
@@ -99,12 +131,12 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int s = 0; s < 4; ++s) {
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
-      mbar_init(&act_done[s], (PAIR ? 2 : 1) * ACT_WARPS);
+      mbar_init(&act_done[s], (PAIR ? 2 : 1) * (WIDE ? ACT_WARPS_WIDE : ACT_WARPS));
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&acc1_full[s], 1);
-      mbar_init(&acc1_empty[s], PAIR ? 8 : 4);
-      mbar_init(&t1_full[s], PAIR ? 8 : 4);
+      mbar_init(&acc1_empty[s], WIDE ? 16 : (PAIR ? 8 : 4));     // one arrive per epilogue-1 warp (of both CTAs)
+      mbar_init(&t1_full[s], WIDE ? 16 : (PAIR ? 8 : 4));
       mbar_init(&t1_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -127,6 +159,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+  }
+  if (WIDE && threadIdx.x >= 128 && threadIdx.x < 384) {       // parameters, not activations: no dependency wait needed
+    const int i = (int)threadIdx.x - 128;
+    sm_bias[i] = i < 128 ? p.b1[i] : p.b2[i - 128];
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all();
@@ -197,8 +233,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int i = 0; i < n_my; ++i, tc.next()) {
       mbar_wait(&x_empty[s], ph ^ 1);
       if (issuer) {
-        mbar_expect_tx(&x_full[s], (uint32_t)(p.xr * p.row_bytes));
+        mbar_expect_tx(&x_full[s], (uint32_t)((WIDE ? 2 : 1) * p.xr * p.row_bytes));
         tma_load_3d(sm_x + s * p.x_stage_bytes, &map_x, &x_full[s], 0, tc.t0() - p.p2 - p.p1, tc.bb());
+        if (WIDE)
+          tma_load_3d(sm_x + s * p.x_stage_bytes + p.x_chunk_bytes, &map_x, &x_full[s], 64, tc.t0() - p.p2 - p.p1, tc.bb());
       }
       if (++s == p.nxs) { s = 0; ph ^= 1; }
     }
@@ -221,6 +259,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       tc_fence_after();
       umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)(a1 * p.C), make_desc_lo(x_base + (uint32_t)(xs * p.x_stage_bytes)), w1_lo,
                    a1_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
+      if (WIDE)   // second 64-channel chunk of the reduction: its own x slab and weight slabs [k, 2k)
+        umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)(a1 * p.C),
+                           make_desc_lo(x_base + (uint32_t)(xs * p.x_stage_bytes + p.x_chunk_bytes)), w1_lo + (uint32_t)p.k * w_inc,
+                           a1_inc, w_inc, p.k, p.desc_hi, p.idesc, 1u);
       if (issuer) {
         commit_u<PAIR>(&acc1_full[a1]);
         commit_u<PAIR>(&x_empty[xs]);
@@ -235,6 +277,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       tc_fence_after();
       umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)((p.na1 + a) * p.C), make_desc_lo(t1_base + (uint32_t)(tb * p.t1_bytes)), w2_lo,
                    a2_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
+      if (WIDE)
+        umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)((p.na1 + a) * p.C),
+                           make_desc_lo(t1_base + (uint32_t)(tb * p.t1_bytes + p.t1_chunk_bytes)), w2_lo + (uint32_t)p.k * w_inc,
+                           a2_inc, w_inc, p.k, p.desc_hi, p.idesc, 1u);
       if (issuer) {
         commit_u<PAIR>(&acc2_full[a]);
         commit_u<PAIR>(&t1_empty[tb]);
@@ -248,13 +294,14 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (i + p.la < n_my) conv1();
       conv2(i);
     }
-  } else if (warp == 2 || warp == 3 || warp >= 12) {
+  } else if (warp == 2 || warp == 3 || (!WIDE && warp >= 12)) {
     // ===================== activation: leaky-relu in place on the freshly landed x tile =====================
     // (six warps: with two, this stage paced the whole kernel on the short k = 3 tiles - the MMA warp sat on act_done)
     // bf16x2 arithmetic as in sib_conv1d_bf16: slope * x = x * hi + x * lo with hi + lo = slope to ~2^-17 (no slope bias
     // from rounding 0.1 to bf16), then max(x, slope * x): 12 instead of 28 ALU instructions per 16-byte chunk
+    constexpr int AW = WIDE ? ACT_WARPS_WIDE : ACT_WARPS;
     const int tid = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
-    const int n16 = (p.xr * p.row_bytes) >> 4;
+    const int n16 = ((WIDE ? p.x_chunk_bytes : 0) + p.xr * p.row_bytes) >> 4;   // wide: chunk 0's slab (with its pad) + chunk 1
     const __nv_bfloat16 s_hi = __float2bfloat16_rn(p.slope_in);
     const __nv_bfloat16 s_lo = __float2bfloat16_rn(p.slope_in - __bfloat162float(s_hi));
     const __nv_bfloat162 hi2 = __halves2bfloat162(s_hi, s_hi), lo2 = __halves2bfloat162(s_lo, s_lo);
@@ -264,10 +311,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_wait(&x_full[s], ph);
       const uint32_t tile = smem_u32(sm_x + s * p.x_stage_bytes);
       int e = tid;
-      for (; e + 3 * ACT_WARPS * 32 < n16; e += 4 * ACT_WARPS * 32) {      // four chunks in flight per thread
+      for (; e + 3 * AW * 32 < n16; e += 4 * AW * 32) {      // four chunks in flight per thread
         uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = lds128(tile + (uint32_t)(e + j * ACT_WARPS * 32) * 16u);
+        for (int j = 0; j < 4; ++j) v[j] = lds128(tile + (uint32_t)(e + j * AW * 32) * 16u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v[j]);
@@ -275,9 +322,9 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           for (int u = 0; u < 4; ++u) h[u] = __hmax2(h[u], __hfma2(h[u], lo2, __hmul2(h[u], hi2)));
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sts128(tile + (uint32_t)(e + j * ACT_WARPS * 32) * 16u, v[j]);
+        for (int j = 0; j < 4; ++j) sts128(tile + (uint32_t)(e + j * AW * 32) * 16u, v[j]);
       }
-      for (; e < n16; e += ACT_WARPS * 32) {
+      for (; e < n16; e += AW * 32) {
         uint4 v = lds128(tile + (uint32_t)e * 16u);
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
 #pragma unroll
@@ -289,7 +336,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (lane == 0) arrive_mma(&act_done[s]);
       if (++s == p.nxs) { s = 0; ph ^= 1; }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || (WIDE && warp >= 12 && warp < 16)) {
     // ===================== epilogue 1: conv1 accumulator -> lrelu -> bf16 A tile of conv2 =====================
     const int q = warp & 3;
     const int r = q * 32 + lane;                               // tile row == TMEM lane == t1-local row
@@ -313,24 +360,28 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col = c0 + 8 * h;
-          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b1 + col));
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + col + 4));
+          const float4 ba = WIDE ? lds_const_f4(smem_u32(sm_bias + col)) : __ldg(reinterpret_cast<const float4*>(p.b1 + col));
+          const float4 bb = WIDE ? lds_const_f4(smem_u32(sm_bias + col + 4)) : __ldg(reinterpret_cast<const float4*>(p.b1 + col + 4));
           float f[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             f[u] += __uint_as_float(v[8 * h + u]);
             f[u] = fmaxf(f[u], f[u] * p.slope_mid);          // leaky-relu, 0 < slope < 1
           }
-          sts128(row_ptr + ((((uint32_t)col >> 3) ^ swz) << 4), inside ? pack8(f) : make_uint4(0u, 0u, 0u, 0u));
+          // (wide: columns 64.. live in the second chunk slab of the intermediate tile)
+          const uint32_t cofs = WIDE ? (uint32_t)(col >> 6) * (uint32_t)p.t1_chunk_bytes + (((((uint32_t)col & 63u) >> 3) ^ swz) << 4)
+                                     : ((((uint32_t)col >> 3) ^ swz) << 4);
+          sts128(row_ptr + cofs, inside ? pack8(f) : make_uint4(0u, 0u, 0u, 0u));
         }
       };
-      for (int c0 = 0; c0 < p.C; c0 += 32) {                   // two TMEM loads in flight per wait
+      const int c_lo = WIDE ? (warp >= 12 ? 64 : 0) : 0, c_hi = WIDE ? c_lo + 64 : p.C;   // wide: this warp's column half
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {               // two TMEM loads in flight per wait
         uint32_t va[16], vb[16];
         tmem_ld16_nowait(taddr + (uint32_t)c0, va);
-        if (c0 + 16 < p.C) tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), vb);
+        if (c0 + 16 < c_hi) tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), vb);
         tmem_ld_wait();
         emit16(va, c0);
-        if (c0 + 16 < p.C) emit16(vb, c0 + 16);
+        if (c0 + 16 < c_hi) emit16(vb, c0 + 16);
       }
       tc_fence_before();
       fence_async_smem();
@@ -342,6 +393,82 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (++a == p.na1) { a = 0; aph ^= 1; }
       if (++tb == p.t1_bufs) { tb = 0; tbph ^= 1; }
     }
+  } else if (WIDE && warp >= 8 && warp < 12) {
+    // ===================== epilogue 2, C = 128: four 32-channel groups per tile ==========
+    // residual rows by plain (read-only) loads from global x - one 64-byte slice of this lane's row per group, fetched a
+    // group ahead -, output through two 2 KB staging boxes per warp (32 rows x 32 channels, 64-byte swizzle) and TMA stores
+    const int q = warp & 3;
+    const uint32_t swz = ((uint32_t)lane >> 1) & 3u;           // 64-byte swizzle: chunk ^= (row >> 1) & 3
+    const int rows_q = q < 3 ? 32 : p.tail_rows;
+    sib::pdl_wait();
+    uint8_t* my_box = sm_sa + q * 4096;                        // [2 slots][32 rows][64 B]
+    const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(p.xg);
+    uint32_t slot = 0;
+    TileCursor tc = cursor0();
+    for (int i = 0; i < n_my; ++i, tc.next()) {
+      const int t0 = tc.t0(), b = tc.bb();
+      const bool valid = tc.valid();
+      const int a = i & 1;
+      const int row = t0 + q * 32 + lane;
+      const bool row_ok = row < p.T;
+      const uint4* xrow = reinterpret_cast<const uint4*>(xg + (long long)b * p.xg_batch_stride + (long long)(row_ok ? row : 0) * p.xg_row_stride);
+      // residual slices (64 B of this lane's row per group) run TWO groups ahead of the arithmetic and bypass L1
+      uint4 xq[3][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xq[0][j] = row_ok ? ldg_stream(xrow + j) : make_uint4(0u, 0u, 0u, 0u);
+        xq[1][j] = row_ok ? ldg_stream(xrow + 4 + j) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      mbar_wait(&acc2_full[a], (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((p.na1 + a) * p.C);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t va[16], vb[16];
+        tmem_ld16_nowait(taddr + (uint32_t)(g * 32), va);
+        tmem_ld16_nowait(taddr + (uint32_t)(g * 32 + 16), vb);
+        if (g < 2) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) xq[(g + 2) % 3][j] = row_ok ? ldg_stream(xrow + (g + 2) * 4 + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        // the box about to be written was handed to the TMA two groups ago: its read-out must have finished
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        tmem_ld_wait();
+        if (g == 3) {                                          // accumulator drained: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_mma(&acc2_empty[a]);
+        } else {
+          __syncwarp();
+        }
+        const uint32_t box = smem_u32(my_box + slot * 2048 + lane * 64);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int col = g * 32 + 8 * h;
+          const float4 ba = lds_const_f4(smem_u32(sm_bias + 128 + col));
+          const float4 bb = lds_const_f4(smem_u32(sm_bias + 128 + col + 4));
+          float f[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          float xf[8];
+          unpack8(xq[g % 3][h], xf);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[u] += __uint_as_float(h < 2 ? va[8 * h + u] : vb[8 * (h - 2) + u]) + xf[u];
+          if (p.out_scale != 1.f) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] *= p.out_scale;
+          }
+          sts128(box + ((((uint32_t)h) ^ swz) << 4), pack8(f));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (rows_q > 0 && valid) tma_store_3d(q < 3 ? &map_y : &map_yt, my_box + slot * 2048, g * 32, t0 + q * 32, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        slot ^= 1u;
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tc_fence_before();
   } else if (warp >= 8 && warp < 12) {
     // ===================== epilogue 2: conv2 accumulator + bias + x (+ running sum) -> y (and lrelu(y)) ==========
     const int q = warp & 3;
@@ -470,14 +597,22 @@ int plan_resunit_mode(int c, int k, int dil, int accumulate, int has_y2, int pai
 int plan_resunit(int c, int k, int dil, int accumulate, int has_y2, RuPlan* out) {
   static const int force_pair = getenv("SIB_RU_PAIR") ? atoi(getenv("SIB_RU_PAIR")) : -1;   // 0 never, 1 whenever legal
   if (force_pair == 1 && c >= 32 && plan_resunit_mode(c, k, dil, accumulate, has_y2, 1, out) == SIB_OK) return SIB_OK;
+  static const bool wide_on = !(getenv("SIB_RU_WIDE") && atoi(getenv("SIB_RU_WIDE")) == 0);   // A/B switch for the C = 128 units
+  if (c == 128) return wide_on ? plan_resunit_mode(c, k, dil, accumulate, has_y2, 1, out) : SIB_ERR_UNSUPPORTED;
   if (plan_resunit_mode(c, k, dil, accumulate, has_y2, 0, out) == SIB_OK) return SIB_OK;
   if (force_pair != 0 && c == 64) return plan_resunit_mode(c, k, dil, accumulate, has_y2, 1, out);
   return SIB_ERR_UNSUPPORTED;
 }
 
 int plan_resunit_mode(int c, int k, int dil, int accumulate, int has_y2, int pair, RuPlan* out) {
-  if (!(c == 64 || c == 32 || c == 16)) {
-    sib::set_error("sib_resunit_bf16: c=%d unsupported (16 / 32 / 64; wider stages use sib_conv1d_bf16)", c);
+  const bool wide = c == 128;
+  if (!(c == 128 || c == 64 || c == 32 || c == 16)) {
+    sib::set_error("sib_resunit_bf16: c=%d unsupported (16 / 32 / 64 / 128; wider stages use sib_conv1d_bf16)", c);
+    return SIB_ERR_UNSUPPORTED;
+  }
+  if (wide && (!pair || k > 3 || accumulate || has_y2)) {
+    sib::set_error("sib_resunit_bf16: c=128 runs as CTA pairs with k <= 3 and neither a running sum nor a second output "
+                   "(k=%d accumulate=%d y_act=%d): use sib_conv1d_bf16 for this unit", k, accumulate, has_y2);
     return SIB_ERR_UNSUPPORTED;
   }
   if (k < 1 || (k & 1) == 0 || k > 15 || dil < 1) {
@@ -496,26 +631,31 @@ int plan_resunit_mode(int c, int k, int dil, int accumulate, int has_y2, int pai
     sib::set_error("sib_resunit_bf16: k=%d dilation=%d needs a %d-row halo tile (max 256)", k, dil, a.xr);
     return SIB_ERR_UNSUPPORTED;
   }
-  a.row_bytes = c * 2;
-  a.ksteps = c / 16;
+  a.nch = wide ? 2 : 1;
+  const int cc = c / a.nch;                          // channels per chunk = K-row of an operand slab
+  a.row_bytes = cc * 2;
+  a.ksteps = cc / 16;
   a.c_cta = pair ? c / 2 : c;
-  a.tap_bytes = a.c_cta * a.row_bytes;
+  a.tap_bytes = a.c_cta * a.row_bytes;               // one (tap, chunk) weight slab of this CTA
   out->pair = pair;
-  a.x_stage_bytes = (a.xr * a.row_bytes + 1023) / 1024 * 1024;
-  a.t1_bytes = ((128 + k - 1) * a.row_bytes + 1023) / 1024 * 1024;
-  // weights: as few TMA boxes as possible (<= 32 KB each), no padding taps when one box takes them all
-  a.w_loads = (k * a.tap_bytes + 32767) / 32768;
-  a.w_tg = (k + a.w_loads - 1) / a.w_loads;
-  a.w_tx_bytes = a.w_loads * a.w_tg * a.tap_bytes;   // full boxes: taps past k are TMA zero fill but still counted
+  a.x_chunk_bytes = (a.xr * a.row_bytes + 1023) / 1024 * 1024;
+  a.x_stage_bytes = a.nch * a.x_chunk_bytes;
+  a.t1_chunk_bytes = ((128 + k - 1) * a.row_bytes + 1023) / 1024 * 1024;
+  a.t1_bytes = a.nch * a.t1_chunk_bytes;
+  // weights: as few TMA boxes as possible (<= 32 KB each), no padding slabs when one box takes them all
+  const int slabs = k * a.nch;                       // [chunk][tap] slabs per conv
+  a.w_loads = (slabs * a.tap_bytes + 32767) / 32768;
+  a.w_tg = (slabs + a.w_loads - 1) / a.w_loads;
+  a.w_tx_bytes = a.w_loads * a.w_tg * a.tap_bytes;   // full boxes: slabs past the last are TMA zero fill but still counted
   a.w_bytes = (a.w_tx_bytes + 1023) / 1024 * 1024;
-  a.stage_box_bytes = 128 * a.row_bytes;
+  a.stage_box_bytes = wide ? 16384 : 128 * a.row_bytes;   // wide: 4 warps x 2 slots x (32 rows x 64 B)
   a.need_b = (accumulate || has_y2) ? 1 : 0;
   a.accumulate = accumulate; a.has_y2 = has_y2;
   a.desc_hi = make_desc_hi(a.row_bytes);
   a.idesc = make_idesc_bf16(pair ? 256 : 128, c);
   // ring depths: prefer (4 x-tiles, 2 staging slots) inside the two-CTAs-per-SM budget, then the same inside one SM,
   // then shrink (3, 2 x-tiles; finally a single staging slot) until the resident weights fit
-  const int fixed = 2 * a.w_bytes + 512 + 1024;
+  const int fixed = 2 * a.w_bytes + 512 + 1024 + (wide ? 1024 : 0);   // (+ both bias vectors in shared memory when wide)
   auto need = [&](int nxs, int slots, int t1b) {
     return fixed + t1b * a.t1_bytes + nxs * a.x_stage_bytes + slots * a.stage_box_bytes * (1 + a.need_b);
   };
@@ -523,6 +663,10 @@ int plan_resunit_mode(int c, int k, int dil, int accumulate, int has_y2, int pai
   a.nxs = 0;
   // (three staging slots are supported by the kernel but measured 5-8 % slower than two: not offered)
   const int tries[9][3] = {{4, 2, 3}, {3, 2, 3}, {4, 2, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {3, 1, 1}, {2, 1, 2}, {2, 1, 1}};
+  if (wide) {                                        // the staging boxes are fixed: only the x ring may grow
+    if (need(3, 1, 1) <= one_cta) { a.nxs = 3; a.slots = 1; a.t1_bufs = 1; }
+    else if (need(2, 1, 1) <= one_cta) { a.nxs = 2; a.slots = 1; a.t1_bufs = 1; }
+  } else
   for (int pass = pair ? 1 : 0; pass < 2 && a.nxs == 0; ++pass)
     for (const auto& tr : tries)
       if (need(tr[0], tr[1], tr[2]) <= (pass == 0 ? two_cta : one_cta) && (pass == 1 || tr[1] >= 2)) {
@@ -574,6 +718,7 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
               "sib_resunit_bf16: leaky-relu slopes must be in (0, 1] (max(x, slope x) form)");
   a.b1 = b1; a.b2 = b2;
   a.T = d->t; a.batch = d->batch;
+  a.xg = x; a.xg_batch_stride = d->x_batch_stride; a.xg_row_stride = d->x_row_stride;
   static const bool early_w = !(getenv("SIB_PDL_EARLY_W") && atoi(getenv("SIB_PDL_EARLY_W")) == 0);
   a.early_w = early_w ? 1 : 0;
   a.slope_in = d->slope_in; a.slope_mid = d->slope_mid; a.out_scale = d->out_scale; a.act2_slope = d->act2_slope;
@@ -589,21 +734,26 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
     const cuuint64_t dims[3] = {(cuuint64_t)d->c, (cuuint64_t)d->t, (cuuint64_t)d->batch};
     const cuuint64_t xs[3] = {2, (cuuint64_t)d->x_row_stride * 2, (cuuint64_t)d->x_batch_stride * 2};
     const cuuint64_t ys[3] = {2, (cuuint64_t)d->y_row_stride * 2, (cuuint64_t)d->y_batch_stride * 2};
-    const cuuint32_t box_x[3] = {(cuuint32_t)d->c, (cuuint32_t)a.xr, 1};
-    const cuuint32_t box_q[3] = {(cuuint32_t)d->c, 32, 1};
-    const cuuint32_t box_t[3] = {(cuuint32_t)d->c, (cuuint32_t)a.tail_rows, 1};
+    const cuuint32_t ccx = (cuuint32_t)(d->c / a.nch);          // channels per operand slab
+    const cuuint32_t cy = a.nch == 2 ? 32u : (cuuint32_t)d->c;  // wide: output boxes of 32 channels (64-byte swizzle)
+    const CUtensorMapSwizzle swz_y = a.nch == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : swz;
+    const cuuint32_t box_x[3] = {ccx, (cuuint32_t)a.xr, 1};
+    const cuuint32_t box_r[3] = {ccx, 32, 1};
+    const cuuint32_t box_q[3] = {cy, 32, 1};
+    const cuuint32_t box_t[3] = {cy, (cuuint32_t)a.tail_rows, 1};
     if (int rc = encode_map(&map_x, x, 3, dims, xs, box_x, swz, who, "x")) return rc;
-    if (int rc = encode_map(&map_res, x, 3, dims, xs, box_q, swz, who, "x (residual)")) return rc;
-    if (int rc = encode_map(&map_y, y, 3, dims, ys, box_q, swz, who, "y")) return rc;
-    if (int rc = encode_map(&map_yt, y, 3, dims, ys, box_t, swz, who, "y (tail)")) return rc;
-    if (int rc = encode_map(&map_y2, y_act ? y_act : y, 3, dims, ys, box_q, swz, who, "y_act")) return rc;
-    if (int rc = encode_map(&map_y2t, y_act ? y_act : y, 3, dims, ys, box_t, swz, who, "y_act (tail)")) return rc;
+    if (int rc = encode_map(&map_res, x, 3, dims, xs, box_r, swz, who, "x (residual)")) return rc;
+    if (int rc = encode_map(&map_y, y, 3, dims, ys, box_q, swz_y, who, "y")) return rc;
+    if (int rc = encode_map(&map_yt, y, 3, dims, ys, box_t, swz_y, who, "y (tail)")) return rc;
+    if (int rc = encode_map(&map_y2, y_act ? y_act : y, 3, dims, ys, box_q, swz_y, who, "y_act")) return rc;
+    if (int rc = encode_map(&map_y2t, y_act ? y_act : y, 3, dims, ys, box_t, swz_y, who, "y_act (tail)")) return rc;
   }
   {
-    // weights in the sib_conv1d_bf16 layout [1][1 chunk][k][c_out][c_in]: one K-major slab per tap
-    const cuuint64_t dims[3] = {(cuuint64_t)d->c, (cuuint64_t)d->c, (cuuint64_t)d->k};
-    const cuuint64_t ws[3] = {2, (cuuint64_t)d->c * 2, (cuuint64_t)d->c * d->c * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)d->c, (cuuint32_t)a.c_cta, (cuuint32_t)a.w_tg};
+    // weights in the sib_conv1d_bf16 layout [1][chunks][k][c_out][cc]: one K-major slab per (chunk, tap)
+    const cuuint64_t ccw = (cuuint64_t)(d->c / a.nch);
+    const cuuint64_t dims[3] = {ccw, (cuuint64_t)d->c, (cuuint64_t)d->k * a.nch};
+    const cuuint64_t ws[3] = {2, ccw * 2, (cuuint64_t)d->c * ccw * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)ccw, (cuuint32_t)a.c_cta, (cuuint32_t)a.w_tg};
     if (int rc = encode_map(&map_w1, w1, 3, dims, ws, box, swz, who, "w1")) return rc;
     if (int rc = encode_map(&map_w2, w2, 3, dims, ws, box, swz, who, "w2")) return rc;
   }
@@ -611,7 +761,8 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    const void* fns[2] = {(const void*)resunit_tc_kernel<false>, (const void*)resunit_tc_kernel<true>};
+    const void* fns[3] = {(const void*)resunit_tc_kernel<false>, (const void*)resunit_tc_kernel<true>,
+                          (const void*)resunit_tc_kernel<true, true>};
     for (const void* fn : fns) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) {
@@ -636,7 +787,10 @@ extern "C" int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const 
             d->batch, d->t, d->c, d->k, d->dilation, a.accumulate, a.has_y2, pl.pair, a.R, a.xr, a.nxs, a.slots, a.t1_bufs, a.la, pl.smem_bytes,
             pl.ctas_per_sm, a.total_tiles);
   const cudaError_t le =
-      pl.pair ? sib::launch_pdl_cluster(resunit_tc_kernel<true>, dim3(grid), dim3(NUM_THREADS), (size_t)pl.smem_bytes,
+      a.nch == 2 ? sib::launch_pdl_cluster(resunit_tc_kernel<true, true>, dim3(grid), dim3(NUM_THREADS_WIDE), (size_t)pl.smem_bytes,
+                                           static_cast<cudaStream_t>(stream), 2u, map_x, map_w1, map_w2, map_res, map_y, map_yt,
+                                           map_y2, map_y2t, args)
+      : pl.pair ? sib::launch_pdl_cluster(resunit_tc_kernel<true>, dim3(grid), dim3(NUM_THREADS), (size_t)pl.smem_bytes,
                                         static_cast<cudaStream_t>(stream), 2u, map_x, map_w1, map_w2, map_res, map_y, map_yt,
                                         map_y2, map_y2t, args)
               : sib::launch_pdl(resunit_tc_kernel<false>, dim3(grid), dim3(NUM_THREADS), (size_t)pl.smem_bytes,

@@ -166,6 +166,11 @@ RU_CASES = [
     (1, 300, 64, 11, 1, True, True, 1.0 / 3),    # odd tile count: the pair's second CTA runs a masked duplicate
     (3, 119, 64, 11, 3, True, False, 1.0),
     (8, 6000, 64, 11, 5, True, True, 1.0 / 3),   # 408 tiles: every persistent CTA pair loops over several tile pairs
+    (2, 1000, 128, 3, 1, False, False, 1.0),     # C = 128 (stage 2): wide CTA-pair variant, two 64-channel chunks per row
+    (1, 126, 128, 3, 5, False, False, 1.0),      # exactly one tile (R = 126), odd tile count -> masked duplicate in the pair
+    (3, 127, 128, 3, 3, False, False, 1.0),      # one row into the second tile
+    (8, 5000, 128, 3, 5, False, False, 1.0 / 3), # 320 tiles: every pair loops; output scale
+    (2, 300, 128, 1, 1, False, False, 1.0),      # k = 1
     (2, 400, 16, 3, 1, False, False, 1.0),       # I_da last stage
     (2, 401, 16, 11, 5, True, True, 1.0 / 3),
 ]
@@ -236,13 +241,16 @@ def test_new_operators_fail_loudly(sib):
     """Unsupported configurations of the fused operators raise SibError - nothing falls back to another path."""
     ops = sib.ops
     assert ops.resunit_supported(32, 11, 5) and ops.resunit_supported(64, 11, 5) and ops.resunit_supported(64, 3, 1, True, True)
-    assert not ops.resunit_supported(128, 3, 1)       # wider stages use the conv kernel
+    assert ops.resunit_supported(128, 3, 5)           # C = 128, k = 3: wide CTA-pair units
+    assert not ops.resunit_supported(128, 7, 1)       # ... but 448 KB of weights do not fit: the conv kernel runs k = 7 / 11
+    assert not ops.resunit_supported(128, 3, 1, True, False) and not ops.resunit_supported(128, 3, 1, False, True)
+    assert not ops.resunit_supported(256, 3, 1)       # wider stages use the conv kernel
     assert not ops.resunit_supported(64, 4, 1)        # even kernel sizes have no "same" padding
     x = torch.zeros(1, 64, 128, device="cuda", dtype=torch.bfloat16)
-    w = torch.zeros(1, 1, 3, 128, 128, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(1, 2, 7, 128, 64, device="cuda", dtype=torch.bfloat16)
     b = torch.zeros(128, device="cuda")
-    with pytest.raises(sib.SibError, match="unsupported"):
-        ops.resunit(x, w, b, w, b, torch.empty_like(x), 3, 1)
+    with pytest.raises(sib.SibError, match="k <= 3"):
+        ops.resunit(x, w, b, w, b, torch.empty_like(x), 7, 1)
     x32 = torch.zeros(1, 64, 32, device="cuda", dtype=torch.bfloat16)
     w32 = torch.zeros(1, 1, 3, 32, 32, device="cuda", dtype=torch.bfloat16)
     b32 = torch.zeros(32, device="cuda")
