@@ -255,7 +255,10 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint32_t xph = 0, a1ph = 0, tbph = 0;
     auto conv1 = [&]() {                       // next tile in order: x ring slot xs, accumulator a1
       mbar_wait(&act_done[xs], xph);
-      mbar_wait(&acc1_empty[a1], a1ph ^ 1);
+      // wide: epilogue 1 signals "intermediate tile full" and "accumulator drained" at the same instant, and this warp has
+      // always seen t1_full of the tile that last used this accumulator (conv2 of that tile precedes this point in program
+      // order) - so the second barrier, and the release fence its remote arrive costs every epilogue-1 warp, are dropped
+      if (!WIDE) mbar_wait(&acc1_empty[a1], a1ph ^ 1);
       tc_fence_after();
       umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)(a1 * p.C), make_desc_lo(x_base + (uint32_t)(xs * p.x_stage_bytes)), w1_lo,
                    a1_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
@@ -388,7 +391,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       __syncwarp();
       if (lane == 0) {
         arrive_mma(&t1_full[tb]);
-        arrive_mma(&acc1_empty[a]);
+        if (!WIDE) arrive_mma(&acc1_empty[a]);
       }
       if (++a == p.na1) { a = 0; aph ^= 1; }
       if (++tb == p.t1_bufs) { tb = 0; tbph ^= 1; }
