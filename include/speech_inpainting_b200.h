@@ -139,6 +139,11 @@ int sib_gather_frames_f32(const float* src, int batch, int t, int d, const int32
 int sib_cos_argmax_f32(const float* v, const float* cc, int m, int k, int d, int64_t* labels, sib_stream_t stream);
 /* a17: labels[m] = argmin_k ||f[m]-mu[k]||^2 (sklearn KMeans.predict, inpainting.py:204-205) */
 int sib_l2_argmin_f32(const float* f, const float* mu, int m, int k, int d, int64_t* labels, sib_stream_t stream);
+/* a17 at scale: argmin_k ||f - mu_k||^2 = argmax_k (f . mu_k - 0.5 ||mu_k||^2) - the form sklearn evaluates for float32
+ * features.  sib_row_sqnorm_f32 gives the bias (out[r] = scale * sum_c x[r,c]^2, scale = -0.5), sib_conv1d_f32 (a linear
+ * layer, w = mu^T) the scores [M, K], sib_row_argmax_f32 the labels (ties -> lowest k). */
+int sib_row_sqnorm_f32(const float* x, int rows, int d, float scale, float* out, sib_stream_t stream);
+int sib_row_argmax_f32(const float* s, int rows, int k, int64_t* labels, sib_stream_t stream);
 /* a10 head on the gathered frames (I_ea/model.py:75-78,88 Linear(H, 80) after LayerNorm): y[m,:] = x[m,:] @ w + bias for a
  * NARROW output (n <= 128), w [k][n] (= sib_conv1d_f32 layout of a linear layer); one CTA per row. */
 int sib_linear_skinny_f32(const float* x, const float* w, const float* bias, float* y, int m, int k, int n,

@@ -68,6 +68,8 @@ _SIGS = {
     "sib_cos_argmax_f32": ([_P, _P, _I, _I, _I, _P, _P], _I),
     "sib_l2_argmin_f32": ([_P, _P, _I, _I, _I, _P, _P], _I),
     "sib_linear_skinny_f32": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
+    "sib_row_sqnorm_f32": ([_P, _I, _I, _F, _P, _P], _I),
+    "sib_row_argmax_f32": ([_P, _I, _I, _P, _P], _I),
     "sib_paste_centroids_f32": ([_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P], _I),
     "sib_extend_mel_f32": ([_P, _P, _I, _I, _I, _I, _I, _P], _I),
     "sib_transpose_f32": ([_P, _P, _I, _I, _I, _P], _I),

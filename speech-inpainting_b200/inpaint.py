@@ -278,6 +278,8 @@ class BlindInpainter:
         self.emb_as_long = emb_as_long
         self.device = hubert._device
         self.mu = kmeans_centers.to(self.device, torch.float32).contiguous()  # [K, H]
+        with torch.cuda.device(self.device):
+            self._mu_packed, self._mu_bias = ops.kmeans_pack(self.mu)
         self.layer, self.normalize = layer, normalize
         self.hop, self.sr = code_hop_size, sampling_rate
 
@@ -297,7 +299,8 @@ class BlindInpainter:
     def units(self, feats):
         B, T, H = feats.shape
         labels = torch.empty(B * T, dtype=torch.int64, device=self.device)
-        ops.l2_argmin(feats.reshape(B * T, H), self.mu, labels)  # kmeans_model.predict (inpainting.py:204-205)
+        # kmeans_model.predict (inpainting.py:204-205): fp32 GEMM + row argmax (sklearn's float32 formulation)
+        ops.kmeans_assign(feats.reshape(B * T, H), self._mu_packed, self._mu_bias, labels)
         return labels.view(B, T)
 
     def __call__(self, *args, **kwargs):

@@ -470,6 +470,29 @@ def l2_argmin(f, mu, labels):
     _emit("sib_l2_argmin_f32", (_p(f), _p(mu), M, mu.shape[0], Dm, _p(labels)), keep=(f, mu, labels))
 
 
+def kmeans_pack(mu):
+    """Centres [K, D] -> (packed mu^T for the fp32 GEMM, bias -0.5 ||mu_k||^2) for `kmeans_assign`."""
+    _chk(mu, torch.float32, "mu")
+    mu = mu.contiguous()
+    K, Dm = mu.shape
+    bias = torch.empty(K, device=mu.device, dtype=torch.float32)
+    _emit("sib_row_sqnorm_f32", (_p(mu), K, Dm, -0.5, _p(bias)), keep=(mu, bias))
+    return pack_linear_weight(mu), bias
+
+
+def kmeans_assign(f, mu_packed, mu_bias, labels, scores=None):
+    """labels[m] = argmin_k ||f[m] - mu_k||^2 through one fp32 GEMM (scores = f mu^T - 0.5 ||mu||^2) and a row argmax:
+    sklearn's own float32 formulation of KMeans.predict (I_da/scripts/inpainting.py:204-205)."""
+    M, Dm = f.shape
+    K = mu_bias.shape[0]
+    _chk(f, torch.float32, "f"); _chk(labels, torch.int64, "labels")
+    if scores is None:
+        scores = torch.empty(M, K, device=f.device, dtype=torch.float32)
+    linear(f.contiguous(), mu_packed, mu_bias, scores)
+    _emit("sib_row_argmax_f32", (_p(scores), M, K, _p(labels)), keep=(scores, labels))
+    return labels
+
+
 def paste_centroids(mel, cc, center, labels, pos, length, off):
     B, Dm, T = mel.shape
     _chk(mel, torch.float32, "mel"); _chk(labels, torch.int64, "labels"); _chk(cc, torch.float32, "cc")

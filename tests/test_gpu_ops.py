@@ -227,6 +227,25 @@ def test_glue_gather_assign_paste(sib, golden_dir):
     lab = torch.empty(199, dtype=torch.int64, device="cuda")
     sib.ops.l2_argmin(f.cuda(), mu.cuda(), lab)
     assert torch.equal(glue_ref.kmeans_predict(f, mu), lab.cpu())
+    # ... and at scale through the fp32 GEMM + row argmax (sklearn's float32 form): same labels as sklearn's golden vectors
+    gk = np.load(f"{golden_dir}/kmeans_golden.npz")
+    for K, H, M in ((100, 768, 400), (500, 768, 600), (500, 1024, 300)):
+        g = torch.Generator().manual_seed(K + H)
+        mu = torch.randn(K, H, generator=g) * 0.5
+        idx = torch.randint(0, K, (M,), generator=g)
+        f = torch.cat([mu[idx[: M // 2]] + 0.3 * torch.randn(M // 2, H, generator=g), torch.randn(M - M // 2, H, generator=g) * 0.5])
+        packed, bias = sib.ops.kmeans_pack(mu.cuda())
+        lab = torch.empty(M, dtype=torch.int64, device="cuda")
+        sib.ops.kmeans_assign(f.cuda(), packed, bias, lab)
+        assert np.array_equal(lab.cpu().numpy(), gk[f"labels_{K}_{H}"])          # sklearn.cluster.KMeans.predict
+        lab2 = torch.empty(M, dtype=torch.int64, device="cuda")
+        sib.ops.l2_argmin(f.cuda(), mu.cuda(), lab2)
+        assert torch.equal(lab, lab2)
+    # ties resolve to the lowest index
+    sc = torch.zeros(3, 37, device="cuda"); sc[1, 5] = sc[1, 20] = 2.0; sc[2, 36] = 1.0
+    lab = torch.empty(3, dtype=torch.int64, device="cuda")
+    sib._load_lib().sib_row_argmax_f32(sc.data_ptr(), 3, 37, lab.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert lab.cpu().tolist() == [0, 5, 36]
 
 
 @pytest.mark.parametrize("T", [37, 100, 200])
