@@ -28,7 +28,7 @@ constexpr int ACT_WARPS = 6;                        // warps 2-3 and 12-15
 // wide (C = 128) builds: 18 warps - epilogue 1 gets EIGHT warps (4-7: columns 0-63, 12-15: columns 64-127), because with the
 // single intermediate buffer that fits, conv2(i) -> epilogue 1(i+1) -> conv2(i+1) is a serial chain and its length is
 // what paces the kernel; the activation warps are 2-3 only (bf16x2 arithmetic: two warps keep up with the 36 KB tiles)
-constexpr int NUM_THREADS_WIDE = 512;              // (18 warps cap the registers at 113: epilogue 2's prefetch spilled, 0.185 -> 0.276 ms)
+constexpr int NUM_THREADS_WIDE = 640;              // 20 warps: producer, MMA, 2 activation, 8 epilogue 1, 8 epilogue 2 (<= 102 registers)
 constexpr int ACT_WARPS_WIDE = 2;
 
 struct RuArgs {
@@ -141,7 +141,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc2_full[s], 1);
-      mbar_init(&acc2_empty[s], PAIR ? 8 : 4);
+      mbar_init(&acc2_empty[s], WIDE ? 16 : (PAIR ? 8 : 4));
     }
     mbar_init(w_full, 1);
     for (int s = 0; s < 12; ++s) mbar_init(&res_bar[s], 1);
@@ -396,17 +396,19 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (++a == p.na1) { a = 0; aph ^= 1; }
       if (++tb == p.t1_bufs) { tb = 0; tbph ^= 1; }
     }
-  } else if (WIDE && warp >= 8 && warp < 12) {
-    // ===================== epilogue 2, C = 128: four 32-channel groups per tile ==========
-    // residual rows by plain (read-only) loads from global x - one 64-byte slice of this lane's row per group, fetched a
-    // group ahead -, output through two 2 KB staging boxes per warp (32 rows x 32 channels, 64-byte swizzle) and TMA stores
+  } else if (WIDE && ((warp >= 8 && warp < 12) || warp >= 16)) {
+    // ===================== epilogue 2, C = 128: eight warps, two 32-channel groups each ==========
+    // (warps 8-11: channels 0-63, warps 16-19: channels 64-127 of the same lane quarter.)  Residual rows by plain
+    // read-only loads from global x - this lane's 128-byte half row, issued before the accumulator wait and bypassing L1 -,
+    // output through one 2 KB staging box per warp (32 rows x 32 channels, 64-byte swizzle) and TMA stores
     const int q = warp & 3;
+    const int half = warp >= 16 ? 1 : 0;
     const uint32_t swz = ((uint32_t)lane >> 1) & 3u;           // 64-byte swizzle: chunk ^= (row >> 1) & 3
     const int rows_q = q < 3 ? 32 : p.tail_rows;
     sib::pdl_wait();
-    uint8_t* my_box = sm_sa + q * 4096;                        // [2 slots][32 rows][64 B]
+    uint8_t* my_box = sm_sa + (q * 2 + half) * 2048;           // [32 rows][64 B]
+    const uint32_t box = smem_u32(my_box + lane * 64);
     const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(p.xg);
-    uint32_t slot = 0;
     TileCursor tc = cursor0();
     for (int i = 0; i < n_my; ++i, tc.next()) {
       const int t0 = tc.t0(), b = tc.bb();
@@ -414,45 +416,37 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       const int a = i & 1;
       const int row = t0 + q * 32 + lane;
       const bool row_ok = row < p.T;
-      const uint4* xrow = reinterpret_cast<const uint4*>(xg + (long long)b * p.xg_batch_stride + (long long)(row_ok ? row : 0) * p.xg_row_stride);
-      // residual slices (64 B of this lane's row per group) run TWO groups ahead of the arithmetic and bypass L1
-      uint4 xq[3][4];
+      const uint4* xrow = reinterpret_cast<const uint4*>(xg + (long long)b * p.xg_batch_stride +
+                                                         (long long)(row_ok ? row : 0) * p.xg_row_stride) + half * 8;
+      uint4 xq[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        xq[0][j] = row_ok ? ldg_stream(xrow + j) : make_uint4(0u, 0u, 0u, 0u);
-        xq[1][j] = row_ok ? ldg_stream(xrow + 4 + j) : make_uint4(0u, 0u, 0u, 0u);
-      }
+      for (int j = 0; j < 8; ++j) xq[j >> 2][j & 3] = row_ok ? ldg_stream(xrow + j) : make_uint4(0u, 0u, 0u, 0u);
       mbar_wait(&acc2_full[a], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((p.na1 + a) * p.C);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((p.na1 + a) * p.C + half * 64);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int gg = 0; gg < 2; ++gg) {
         uint32_t va[16], vb[16];
-        tmem_ld16_nowait(taddr + (uint32_t)(g * 32), va);
-        tmem_ld16_nowait(taddr + (uint32_t)(g * 32 + 16), vb);
-        if (g < 2) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) xq[(g + 2) % 3][j] = row_ok ? ldg_stream(xrow + (g + 2) * 4 + j) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        // the box about to be written was handed to the TMA two groups ago: its read-out must have finished
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        tmem_ld16_nowait(taddr + (uint32_t)(gg * 32), va);
+        tmem_ld16_nowait(taddr + (uint32_t)(gg * 32 + 16), vb);
+        // the box was handed to the TMA one group ago: its read-out must have finished before it is rewritten
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         tmem_ld_wait();
-        if (g == 3) {                                          // accumulator drained: hand it back to the MMA warp
+        if (gg == 1) {                                         // this warp's half of the accumulator is drained
           tc_fence_before();
           __syncwarp();
           if (lane == 0) arrive_mma(&acc2_empty[a]);
         } else {
           __syncwarp();
         }
-        const uint32_t box = smem_u32(my_box + slot * 2048 + lane * 64);
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const int col = g * 32 + 8 * h;
+          const int col = half * 64 + gg * 32 + 8 * h;
           const float4 ba = lds_const_f4(smem_u32(sm_bias + 128 + col));
           const float4 bb = lds_const_f4(smem_u32(sm_bias + 128 + col + 4));
           float f[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           float xf[8];
-          unpack8(xq[g % 3][h], xf);
+          unpack8(xq[gg][h], xf);
 #pragma unroll
           for (int u = 0; u < 8; ++u) f[u] += __uint_as_float(h < 2 ? va[8 * h + u] : vb[8 * (h - 2) + u]) + xf[u];
           if (p.out_scale != 1.f) {
@@ -464,10 +458,9 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (rows_q > 0 && valid) tma_store_3d(q < 3 ? &map_y : &map_yt, my_box + slot * 2048, g * 32, t0 + q * 32, b);
+          if (rows_q > 0 && valid) tma_store_3d(q < 3 ? &map_y : &map_yt, my_box, half * 64 + gg * 32, t0 + q * 32, b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        slot ^= 1u;
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
