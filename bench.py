@@ -299,18 +299,37 @@ def ncu_traffic(kernel_key, workload_key):
             for k in doc["kernels"]:
                 if kernel_key in k["kernel"]:
                     per_launch = (k["dram_read_bytes_per_step"] + k["dram_write_bytes_per_step"]) / k["launches_per_step"]
-                    return per_launch, f"{os.path.basename(f)}, captured on git {doc.get('git_head', 'unknown (round 1)')}"
+                    return per_launch, (f"{os.path.basename(f)}, captured on git {doc.get('git_head', 'unknown (round 1)')}"
+                                        f" / source digest {doc.get('source_digest', 'n/a')}")
         except Exception:
             continue
     return None, None
 
 
 def git_head():
+    """Git head when there is a work tree (the build container); the GPU boxes receive a snapshot without .git, so the line
+    always carries `source_digest()` as well."""
     try:
         return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True,
                               timeout=10).stdout.strip() or None
     except Exception:
         return None
+
+
+def source_digest():
+    """sha256 over the product sources (csrc, package .py, header, bench.py): identifies the tree a number or an ncu capture
+    was taken on, with or without git.  `python bench.py --print-digest` prints it."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    pkg = os.path.join(ROOT, "speech-inpainting_b200")
+    files = sorted(glob.glob(os.path.join(pkg, "csrc", "*.cu*")) + glob.glob(os.path.join(pkg, "*.py")) +
+                   glob.glob(os.path.join(ROOT, "include", "*.h")) + [os.path.join(ROOT, "bench.py")])
+    for f in files:
+        h.update(os.path.relpath(f, ROOT).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
 
 
 _REAL_STDOUT = None
@@ -349,7 +368,11 @@ def main():
     ap.add_argument("--cpu-sample-utts", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-launch timing table (JSON) to this path")
+    ap.add_argument("--print-digest", action="store_true", help="print the source digest of this tree and exit")
     args = ap.parse_args()
+    if args.print_digest:
+        _emit({"source_digest": source_digest(), "git_head": git_head()})
+        return
 
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -546,7 +569,8 @@ def main():
         roofline = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": ach / peak, "traffic": traffic,
                     "traffic_note": (f"DRAM bytes per launch, averaged over the family's launches of one step ({traffic_src}); "
-                                     f"this run: git {git_head()}" if traffic else "no ncu capture of this workload committed"),
+                                     f"this run: git {git_head()} / source digest {source_digest()}" if traffic
+                                     else "no ncu capture of this workload committed"),
                     "algorithmic_flops_per_launch": top["flops"] / max(top["launches"], 1),
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
                     if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
@@ -582,6 +606,7 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "algorithmic_tflop_per_step": fl_utt * total_utts / 1e12,
             "utterances_per_rank": utts_all, "micro_batches_per_rank_per_step": len(micro), "git_head": git_head(),
+            "source_digest": source_digest(),
         }
         if wl["scaling"] == "strong":   # the whole job's bytes: every utterance goes up and comes down exactly once
             per_utt_in = h2d / max(my_utts, 1)

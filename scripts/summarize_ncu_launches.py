@@ -2,7 +2,7 @@
 """Turn the ncu launch-list CSV of `bench.py` (timed region selected with --nvtx --nvtx-include "sib_timed/") into the
 committed summaries under profiles/: one row per launch, and per-kernel-family totals (time share, DRAM bytes, tensor-pipe
 activity) that bench.py reads for `roofline.traffic`.
-Usage: python scripts/summarize_ncu_launches.py gpurun_out/launches_vNN.csv vNN [steps] [round] [git_head] [workload]
+Usage: python scripts/summarize_ncu_launches.py gpurun_out/launches_vNN.csv vNN [steps] [round] [git_head] [workload] [source_digest]
 The git head of the tree the capture was taken on is stamped into the summary (bench.py quotes it in roofline.traffic_note)."""
 import collections
 import csv
@@ -31,6 +31,7 @@ def main():
     rnd = sys.argv[4] if len(sys.argv) > 4 else "r02"
     head = sys.argv[5] if len(sys.argv) > 5 else "unknown"
     wkl = sys.argv[6] if len(sys.argv) > 6 else "cfg2"
+    digest = sys.argv[7] if len(sys.argv) > 7 else "n/a"
     hdr, recs = None, collections.OrderedDict()
     for r in csv.reader(open(src)):
         if r and r[0] == "ID":
@@ -69,7 +70,7 @@ def main():
     json.dump({"source": "ncu --nvtx --nvtx-include sib_timed/ --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
                          "dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none "
                          f"python bench.py --workload {wkl} --steps {steps} --warmup 3 --no-cpu-baseline (B200, {rnd} {tag})",
-               "git_head": head, "workload": wkl, "steps": steps, "kernels": out},
+               "git_head": head, "source_digest": digest, "workload": wkl, "steps": steps, "kernels": out},
               open(f"profiles/{rnd}_ncu_step_{tag}_summary.json", "w"), indent=1)
     with open(f"profiles/{rnd}_ncu_launches_{tag}.csv", "w") as f:
         w = csv.writer(f)
