@@ -255,6 +255,8 @@ def profile_plans(sib, plans, detail=None):
             evs.append((name, args, e0, e1))
         torch.cuda.synchronize()
         for name, args, e0, e1 in evs:
+            if name == "sib_linear_ln_bf16":     # same kernel family (conv1d_bf16_tc_kernel), LayerNorm-folding epilogues
+                name = "sib_conv1d_bf16"
             a = agg.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0})
             a["ms"] += e0.elapsed_time(e1)
             a["launches"] += 1

@@ -234,6 +234,30 @@ int sib_resunit_bf16(const sib_resunit_desc* d, const void* x, const void* w1, c
 int sib_resunit_bf16_supported(int c, int k, int dilation, int accumulate, int has_y_act);
 int sib_conv1d_bf16_pre_act_supported(const sib_conv_desc* d, int has_residual, int has_y_act);
 
+/* LayerNorm folded into the neighbouring linear layers (HF:388-405 post-LN layers: x1 = LN(t1) feeds FFN-in AND is the
+ * residual of FFN-out): the normalised tensor is only stored RAW (t, bf16) together with partial row statistics
+ * stats[row][SIB_LN_SLOTS][2] = (sum, sum of squares) over slices of the row.
+ *   SIB_LN_APPLY:    y = act(LN(t) W + b) computed as r (t W' - mu s) + c with W' = diag(gamma) W (passed as w),
+ *                    s[n] = sum_k w'[k][n] (colsum, of the bf16-rounded w'), c = beta W + b (passed as bias); x = raw t.
+ *   SIB_LN_RESIDUAL: y = x W + b + LN(t) with the residual tile = raw t (gamma / beta / stats_in; stats_in null = the
+ *                    residual is already normalised); if stats_out is given, the partial statistics of the rows of y.
+ * A row's statistics are the sums over ALL slots (unused slots must stay zero: a buffer is always written by the same
+ * layer shape).  Linear layers only (one tap, one group, c_out % 64 == 0). */
+#define SIB_LN_SLOTS 32
+enum { SIB_LN_APPLY = 1, SIB_LN_RESIDUAL = 2 };
+typedef struct sib_ln_fold {
+  const float* stats_in;
+  const float* colsum;
+  const float* gamma;
+  const float* beta;
+  float* stats_out;
+  int32_t mode;
+  int32_t n_norm; /* length of the normalised rows (hidden size) */
+  float eps;
+} sib_ln_fold;
+int sib_linear_ln_bf16(const sib_conv_desc* d, const sib_ln_fold* ln, const void* x, const void* w, const float* bias,
+                       const void* residual, void* y, sib_stream_t stream);
+
 /* K-block geometry the kernel uses for c_in/groups: cc channels x tb taps per pipeline stage (cc*tb = 64). */
 int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb);
 

@@ -42,6 +42,15 @@ class ResUnitDesc(C.Structure):
     ]
 
 
+SIB_LN_SLOTS, SIB_LN_APPLY, SIB_LN_RESIDUAL = 32, 1, 2
+
+
+class LnFold(C.Structure):
+    """mirror of `sib_ln_fold`"""
+    _fields_ = [("stats_in", C.c_void_p), ("colsum", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("stats_out", C.c_void_p), ("mode", C.c_int32), ("n_norm", C.c_int32), ("eps", C.c_float)]
+
+
 class SibError(RuntimeError):
     pass
 
@@ -85,6 +94,7 @@ _SIGS = {
     "sib_abs_diff_mean_f32": ([_P, _P, _I, _L, _P, _P, _P], _I),
     "sib_abs_diff_workspace_bytes": ([_I], C.c_size_t),
     "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
+    "sib_linear_ln_bf16": ([C.POINTER(ConvDesc), C.POINTER(LnFold), _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16": ([C.POINTER(ResUnitDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16_supported": ([_I, _I, _I, _I, _I], _I),
     "sib_conv1d_bf16_pre_act_supported": ([C.POINTER(ConvDesc), _I, _I], _I),

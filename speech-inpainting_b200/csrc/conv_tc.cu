@@ -67,6 +67,13 @@ struct TcArgs {
   int a_sub_bytes, b_sub_bytes;  // bytes of one (tap) sub-tile of A / B inside a stage
   uint32_t desc_hi;              // SBO / version / swizzle bits of the smem matrix descriptor (bits 32..63)
   uint32_t idesc;
+  // LayerNorm folded into the neighbouring linear layers (EPI 2 / 3, see sib_linear_ln_bf16)
+  const float* ln_stats_in;      // [rows][LN_SLOTS][2] partial (sum, sum of squares) of the normalised tensor's rows, or null
+  const float* ln_colsum;        // EPI 2: s[n] = sum_k w'[k][n]
+  const float* ln_gamma;         // EPI 3: affine of the LayerNorm that produced the residual stream
+  const float* ln_beta;
+  float* ln_stats_out;           // EPI 3: partial statistics of the rows this launch writes, or null
+  float ln_inv_n, ln_eps;
   int pre_act;                   // halo mode: leaky-relu(pre_slope) applied in place to every landed A tile (warp 3)
   float pre_slope;
   int tap_row[SIB_MAX_TAPS];     // row coordinate delta per tap
@@ -126,8 +133,18 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 // instantiation on purpose - the short HuBERT GEMMs are sensitive to the epilogue's instruction schedule, code size and
 // register allocation (any edit to the shared lambda cost them 4-19 % in same-box A/Bs), so the plain layers keep the
 // original code untouched.  HOIST kernels always run one CTA per SM (no 85-register cap).
-template <int POST_ACT, bool PAIR, bool HOIST = false>
-__global__ void __launch_bounds__(PAIR ? NUM_THREADS_PAIR : NUM_THREADS, (PAIR || HOIST) ? 1 : 2)
+//
+// EPI selects the epilogue build: 0 plain, 1 = HOIST above, and the two halves of a LayerNorm folded away (r2):
+//   2 "apply":    this linear layer consumes LN(t) of a tensor t that is only stored RAW, with its row statistics:
+//                 LN(t) W + b = r (t W' - mu s) + c,  W' = diag(gamma) W, s = column sums of W', c = beta W + b (passed as
+//                 the bias); the MMAs run on raw t and W', the epilogue applies the two per-row scalars (mu, r).
+//   3 "residual": the residual input is LN(t) of such a raw tensor, rebuilt on the fly from the residual tile
+//                 ((t - mu) r gamma + beta); the rows this launch writes are the next raw tensor, and their partial
+//                 statistics (sum, sum of squares per row, per 32-column slice of every N tile) go to ln_stats_out.
+// Together they remove every LayerNorm launch from the transformer loop (HF:388-405).  Separate instantiations again.
+constexpr int LN_SLOTS = 32;     // partial-statistics slots per row: 2 per N tile (the two epilogue warps of a lane quarter)
+template <int POST_ACT, bool PAIR, int EPI = 0>
+__global__ void __launch_bounds__(PAIR ? NUM_THREADS_PAIR : NUM_THREADS, (PAIR || EPI != 0) ? 1 : 2)
 conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y2,
                       const __grid_constant__ CUtensorMap map_r, const __grid_constant__ TcArgs p) {
@@ -448,6 +465,23 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+      // folded LayerNorm: this thread's row of the normalised tensor (TMEM lane == tile row) -> mean and 1 / std from
+      // the partial sums its producer left; and the partial sums of the row this launch writes
+      float ln_mu = 0.f, ln_rs = 1.f, ln_sum = 0.f, ln_sq = 0.f;
+      const bool ln_row_ok = EPI >= 2 && (r0 + lane) < p.t_out;
+      const int64_t ln_row = (int64_t)b * p.t_out + r0 + lane;
+      if (EPI >= 2 && p.ln_stats_in && ln_row_ok) {
+        const float4* sp = reinterpret_cast<const float4*>(p.ln_stats_in + ln_row * (2 * LN_SLOTS));
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < LN_SLOTS / 2; ++j) {
+          const float4 v4 = __ldg(sp + j);
+          s1 += v4.x + v4.z;
+          s2 += v4.y + v4.w;
+        }
+        ln_mu = s1 * p.ln_inv_n;
+        ln_rs = rsqrtf(fmaxf(s2 * p.ln_inv_n - ln_mu * ln_mu, 0.f) + p.ln_eps);
+      }
 #pragma unroll 1
       for (int blk = 0; blk < p.nblk; ++blk) {
         uint8_t* box_y = stage_y + (slot * 4 + q) * box_bytes;
@@ -541,8 +575,64 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
           }
         };
+        // EPI 2: y = act(r (acc - mu s[n]) + c[n])
+        auto process16_ln_apply = [&](const uint32_t (&v)[16], const int c0) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = c0 + 8 * h;
+            const uint32_t off = (uint32_t)(lane * row_bytes) + ((((uint32_t)col >> 3) ^ swz) << 4);
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + ch0 + cb + col));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + ch0 + cb + col + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col + 4));
+            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float cv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              f[i] = act_t<POST_ACT>(fmaf(ln_rs, fmaf(-ln_mu, sv[i], __uint_as_float(v[8 * h + i])), cv[i]), p.post_slope);
+            sts128(sy + off, pack8(f));
+          }
+        };
+        // EPI 3: y = acc + bias + LN(residual row) (or the plain residual when there are no input statistics);
+        // the row's partial (sum, sum of squares) of y accumulate in registers over the blocks of the tile
+        auto process16_ln_res = [&](const uint32_t (&v)[16], const int c0) {
+          const uint32_t rowoff = (uint32_t)(lane * row_bytes);
+          const uint32_t off0 = rowoff + ((((uint32_t)c0 >> 3) ^ swz) << 4), off1 = rowoff + (((((uint32_t)c0 >> 3) + 1) ^ swz) << 4);
+          uint4 rr[2];
+          rr[0] = lds128(sr + off0);
+          rr[1] = lds128(sr + off1);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = c0 + 8 * h;
+            float f[8], r[8];
+            unpack8(rr[h], r);
+            if (p.ln_stats_in) {
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + ch0 + cb + col));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + ch0 + cb + col + 4));
+              const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + ch0 + cb + col));
+              const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + ch0 + cb + col + 4));
+              const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = fmaf((r[i] - ln_mu) * ln_rs, gv[i], ev[i]);
+            }
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col + 4));
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[i] = __uint_as_float(v[8 * h + i]) + bv[i] + r[i];
+              ln_sum += f[i];
+              ln_sq = fmaf(f[i], f[i], ln_sq);
+            }
+            sts128(sy + (h ? off1 : off0), pack8(f));
+          }
+        };
         auto process16 = [&](const uint32_t (&v)[16], const int c0) {
-          if constexpr (HOIST) process16_hoist(v, c0);
+          if constexpr (EPI == 1) process16_hoist(v, c0);
+          else if constexpr (EPI == 2) process16_ln_apply(v, c0);
+          else if constexpr (EPI == 3) process16_ln_res(v, c0);
           else process16_plain(v, c0);
         };
         if (p.cw == 64) {
@@ -586,6 +676,11 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         if (++slot == NB) slot = 0;
       }
+      if (EPI == 3 && p.ln_stats_out && ln_row_ok) {
+        // slot = 2 x (N tile) + (which warp of the lane quarter): every slot of a row is written by exactly one thread
+        const int nt = tile % p.tiles_n;
+        *reinterpret_cast<float2*>(p.ln_stats_out + (ln_row * LN_SLOTS + 2 * nt + half) * 2) = make_float2(ln_sum, ln_sq);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -618,7 +713,8 @@ extern "C" int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb) {
 }
 
 static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w, const float* bias,
-                            const void* residual, void* y, void* y_act, sib_stream_t stream, bool dry_run) {
+                            const void* residual, void* y, void* y_act, sib_stream_t stream, bool dry_run,
+                            const sib_ln_fold* ln = nullptr) {
   SIB_REQUIRE(d && x && w && y, "sib_conv1d_bf16: null argument");
   SIB_REQUIRE(d->batch > 0 && d->t_in > 0 && d->t_out > 0 && d->c_in > 0 && d->c_out > 0, "sib_conv1d_bf16: empty shape");
   SIB_REQUIRE(d->groups > 0 && d->c_in % d->groups == 0 && d->c_out % d->groups == 0,
@@ -697,6 +793,7 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
     double best = 0.0;
     for (int cand = bn_max; cand >= 16; cand -= 16) {
       if (cout_g % cand) continue;
+      if (ln && cand % 64) continue;     // the folded-LayerNorm epilogues work on 64-column blocks
       if (force_bn && cand == force_bn) { bn = cand; break; }
       const double c = tile_cost(cand);
       if (bn == 0 || c < best * 0.97) { bn = cand; best = c; }     // prefer the wider tile unless clearly slower
@@ -802,6 +899,30 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
   }
   a.pre_act = d->pre_act == SIB_ACT_LRELU ? 1 : 0;
   a.pre_slope = d->pre_slope;
+  int epi_ln = 0;
+  if (ln) {
+    SIB_REQUIRE(ln->mode == SIB_LN_APPLY || ln->mode == SIB_LN_RESIDUAL, "sib_linear_ln_bf16: unknown mode %d", ln->mode);
+    SIB_REQUIRE(d->n_taps == 1 && d->groups == 1 && d->stride == 1 && !d->accumulate && !y_act && d->out_scale == 1.f &&
+                    d->pre_act == SIB_ACT_NONE && cw == 64,
+                "sib_linear_ln_bf16: plain linear layers only (one tap, one group, c_out a multiple of 64, no second output)");
+    SIB_REQUIRE(ln->n_norm > 0 && ln->eps > 0.f, "sib_linear_ln_bf16: n_norm / eps");
+    SIB_REQUIRE(!ln->stats_out || a.tiles_n * 2 <= LN_SLOTS, "sib_linear_ln_bf16: %d N tiles need more than %d statistics slots",
+                a.tiles_n, LN_SLOTS);
+    if (ln->mode == SIB_LN_APPLY) {
+      SIB_REQUIRE(ln->stats_in && ln->colsum && bias && !residual && (d->post_act == SIB_ACT_NONE || d->post_act == SIB_ACT_GELU),
+                  "sib_linear_ln_bf16(apply): needs stats_in, colsum and the folded bias; no residual; activation none / gelu");
+      SIB_REQUIRE(al16(ln->stats_in) && al16(ln->colsum), "sib_linear_ln_bf16: stats_in / colsum must be 16-byte aligned");
+    } else {
+      SIB_REQUIRE(residual && bias && d->post_act == SIB_ACT_NONE && !d->res_after_act,
+                  "sib_linear_ln_bf16(residual): needs a residual and a bias, no activation");
+      SIB_REQUIRE(!ln->stats_in || (ln->gamma && ln->beta && al16(ln->stats_in) && al16(ln->gamma) && al16(ln->beta)),
+                  "sib_linear_ln_bf16(residual): stats_in comes with 16-byte aligned gamma / beta");
+      SIB_REQUIRE(!ln->stats_out || (reinterpret_cast<uintptr_t>(ln->stats_out) & 7) == 0, "sib_linear_ln_bf16: stats_out alignment");
+    }
+    a.ln_stats_in = ln->stats_in; a.ln_colsum = ln->colsum; a.ln_gamma = ln->gamma; a.ln_beta = ln->beta;
+    a.ln_stats_out = ln->stats_out; a.ln_inv_n = 1.f / (float)ln->n_norm; a.ln_eps = ln->eps;
+    epi_ln = ln->mode == SIB_LN_APPLY ? 2 : 3;
+  }
   if (a.pre_act && a.mode != 1) {
     sib::set_error("sib_conv1d_bf16: pre-activation needs the halo mode (stride 1, > 1 evenly spaced taps, tile fits); "
                    "have the producer write the activated tensor (y_act) for this layer");
@@ -876,13 +997,17 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    const void* fns[12] = {(const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, false>,
+    const void* fns[18] = {(const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, false>,
                            (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, false>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH, false>,
                            (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, true>,
                            (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH, true>,
                            // residual-before-activation layers (HiFi-GAN conv2 of a unit, ResBlock2 convs): no activation or leaky-relu
-                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, false, true>,
-                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, true, true>};
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false, 1>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, false, 1>,
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true, 1>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, true, 1>,
+                           // LayerNorm folded into the linear layers of the transformer loop
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false, 2>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, false, 2>,
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true, 2>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, true, 2>,
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false, 3>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true, 3>};
     for (const void* fn : fns) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) {
@@ -902,13 +1027,20 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
                                       (size_t)smem_bytes, cs, 2u, map_a, map_b, map_y, map_y2, map_r, a)                \
             : sib::launch_pdl(conv1d_bf16_tc_kernel<ACT, false, HOIST>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
                               map_a, map_b, map_y, map_y2, map_r, a)
-#define SIB_TC_LAUNCH(ACT) SIB_TC_LAUNCH_H(ACT, false)
+#define SIB_TC_LAUNCH(ACT) SIB_TC_LAUNCH_H(ACT, 0)
   static const bool hoist_on = !(getenv("SIB_TC_HOIST") && atoi(getenv("SIB_TC_HOIST")) == 0);   // A/B switch
   const bool hoist = hoist_on && a.has_res && !a.res_after_act && ctas_per_sm == 1 &&
                      (d->post_act == SIB_ACT_NONE || d->post_act == SIB_ACT_LRELU);
-  if (hoist) {
-    if (d->post_act == SIB_ACT_NONE) SIB_TC_LAUNCH_H(SIB_ACT_NONE, true);
-    else SIB_TC_LAUNCH_H(SIB_ACT_LRELU, true);
+  if (epi_ln == 2) {
+    SIB_REQUIRE(ctas_per_sm == 1, "sib_linear_ln_bf16: tile too narrow");
+    if (d->post_act == SIB_ACT_GELU) SIB_TC_LAUNCH_H(SIB_ACT_GELU, 2);
+    else SIB_TC_LAUNCH_H(SIB_ACT_NONE, 2);
+  } else if (epi_ln == 3) {
+    SIB_REQUIRE(ctas_per_sm == 1, "sib_linear_ln_bf16: tile too narrow");
+    SIB_TC_LAUNCH_H(SIB_ACT_NONE, 3);
+  } else if (hoist) {
+    if (d->post_act == SIB_ACT_NONE) SIB_TC_LAUNCH_H(SIB_ACT_NONE, 1);
+    else SIB_TC_LAUNCH_H(SIB_ACT_LRELU, 1);
   } else {
     switch (d->post_act) {
       case SIB_ACT_NONE: SIB_TC_LAUNCH(SIB_ACT_NONE); break;
@@ -932,6 +1064,12 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
 extern "C" int sib_conv1d_bf16(const sib_conv_desc* d, const void* x, const void* w, const float* bias,
                                const void* residual, void* y, void* y_act, sib_stream_t stream) {
   return conv1d_bf16_impl(d, x, w, bias, residual, y, y_act, stream, false);
+}
+
+extern "C" int sib_linear_ln_bf16(const sib_conv_desc* d, const sib_ln_fold* ln, const void* x, const void* w, const float* bias,
+                                  const void* residual, void* y, sib_stream_t stream) {
+  SIB_REQUIRE(ln, "sib_linear_ln_bf16: null sib_ln_fold");
+  return conv1d_bf16_impl(d, x, w, bias, residual, y, nullptr, stream, false, ln);
 }
 
 // 1 if sib_conv1d_bf16 would run this descriptor with its leaky-relu pre-activation (halo mode selected), else 0

@@ -178,6 +178,13 @@ class HubertModel(SibModule):
         # 11.15-11.33 ms per step against 10.97-11.04 for one (the persistent GEMMs own every SM, so the second chain only
         # adds smaller, less efficient tiles) - kept as an A/B switch, off by default
         self.transformer_chains = int(os.environ.get("SIB_HUBERT_CHAINS", "1")) if precision == "bf16" else 1
+        # bf16 arm, OFF by default: the LayerNorms of the transformer loop folded into the neighbouring linear layers
+        # (sib_linear_ln_bf16: no LayerNorm launch per layer, the normalised tensors are never materialised).  Measured on
+        # B200 at 32 x 4 s, three same-box alternations: 10.55-10.65 ms per step with the fold against 10.31-10.36 without -
+        # the GEMM epilogues are what paces the short HuBERT GEMMs, so moving the normalisation into them costs more than the
+        # 24 small LayerNorm launches it removes; it also makes a row's statistics depend on the N tiling the cost model picks
+        # for the batch size, which breaks the bit-exact shard invariance.  Kept as a tested option (SIB_HUBERT_FOLD_LN=1).
+        self.fold_layernorm = precision == "bf16" and os.environ.get("SIB_HUBERT_FOLD_LN", "0") != "0"
 
     # ---- state
     def _expected_keys(self):
@@ -221,6 +228,8 @@ class HubertModel(SibModule):
             P[f"l{l}.ff1.w"] = ops.pack_linear_weight(self._w(f + "intermediate_dense.weight"))
             P[f"l{l}.ff2.w"] = ops.pack_linear_weight(self._w(f + "output_dense.weight"))
         if self.precision == "bf16":
+            if self.fold_layernorm:
+                self._pack_folded(P)
             # tcgen05 operand layout (K-major bf16); conv0 / norms / biases stay fp32
             for k in [k for k in P if k.endswith(".w") and k != "conv0.w"]:
                 P[k] = ops.to_kmajor_bf16(P[k])
@@ -229,6 +238,34 @@ class HubertModel(SibModule):
         self._packed = P
         self._plans.clear()
         return P
+
+    def _pack_folded(self, P):
+        """Weights of the linear layers that consume a LayerNorm output, with that LayerNorm folded in (one-time):
+        LN(t) W + b = r (t W' - mu s) + c,  W' = diag(gamma) W,  s = column sums of the bf16-rounded W',  c = beta W + b.
+        post-LN (HF:388-405): QKV of layer l takes final_layer_norm of layer l-1, FFN-in takes layer_norm of layer l;
+        pre-LN  (HF:525-548): QKV takes layer_norm, FFN-in final_layer_norm of the same layer."""
+        cfg = self.config
+
+        def fold(wkey, bias, ln_name):
+            g, be = self._w(ln_name + ".weight"), self._w(ln_name + ".bias")
+            w = P[wkey]                                        # [1][1][K][N] fp32
+            wf = w * g.view(1, 1, -1, 1)
+            P[wkey + "f"] = wf                                 # K-major bf16 below (key ends in ".wf" -> handled explicitly)
+            P[wkey + "f.colsum"] = wf.to(torch.bfloat16).to(torch.float32).sum(dim=2).reshape(-1).contiguous()
+            P[wkey + "f.c"] = (be.view(1, -1) @ w[0, 0]).reshape(-1).add(bias).contiguous()
+
+        for l in range(cfg.num_hidden_layers):
+            b = f"encoder.layers.{l}."
+            f1b = self._w(b + "feed_forward.intermediate_dense.bias")
+            if cfg.do_stable_layer_norm:
+                fold(f"l{l}.qkv.w", P[f"l{l}.qkv.b"], b + "layer_norm")
+                fold(f"l{l}.ff1.w", f1b, b + "final_layer_norm")
+            else:
+                if l > 0:
+                    fold(f"l{l}.qkv.w", P[f"l{l}.qkv.b"], f"encoder.layers.{l - 1}.final_layer_norm")
+                fold(f"l{l}.ff1.w", f1b, b + "layer_norm")
+        for k in [k for k in P if k.endswith(".wf")]:
+            P[k] = ops.to_kmajor_bf16(P[k])
 
     # ---- plan
     def _build_plan(self, B: int, N: int, padded: bool, n_layers: int):
@@ -307,12 +344,17 @@ class HubertModel(SibModule):
             # Two independent half-batch chains through the transformer stack (every op is row- or utterance-wise): the
             # GEMMs of 32 x 199 frames are 1.0 - 4.1 waves of tiles, so a single chain leaves most SMs idle during each
             # kernel's last wave; the other chain's kernel fills them (ops.Plan.chain).  Same buffers, disjoint row ranges.
+            fold = bf16 and self.fold_layernorm and self.transformer_chains <= 1 and n_layers > 0
+            if fold:
+                h = self._record_layers_folded(P, h, qkv, att, ff, tmp, nrm, io.key_len, eps, n_layers)
             halves = [(0, B)]
-            if self.transformer_chains > 1 and B >= 2 * self.transformer_chains and not padded:
+            if fold:
+                halves = []
+            elif self.transformer_chains > 1 and B >= 2 * self.transformer_chains and not padded:
                 nc = self.transformer_chains
                 halves = [(B * c // nc, B * (c + 1) // nc) for c in range(nc)]
                 plan.fork()
-            for l in range(n_layers):   # layer-major order: the host feeds both streams alternately
+            for l in range(n_layers if halves else 0):   # layer-major order: the host feeds both streams alternately
                 for c, (b0, b1) in enumerate(halves):
                     with plan.chain(c):
                         self._record_layer(l, P, h[b0:b1], qkv[b0:b1], att[b0:b1], ff[b0:b1], nrm[b0:b1], tmp[b0:b1],
@@ -331,6 +373,61 @@ class HubertModel(SibModule):
         if self.use_cuda_graph:
             plan.capture()
         return io
+
+    def _record_layers_folded(self, P, h, qkv, att, ff, t1, t2, key_len, eps, n_layers):
+        """The transformer loop with every LayerNorm folded into its neighbours (`ops.linear_ln`): the normalised tensors are
+        never written.  post-LN: the stream alternates between two RAW tensors t1 (attention block output + residual) and t2
+        (FFN output + residual), each with the partial row statistics its producer leaves; LN(t) is applied on the fly -
+        as two per-row scalars in the epilogue of the linear layer that consumes it, and rebuilt from the residual tile where
+        it is the residual.  pre-LN: the stream h stays raw anyway; the producers only add the statistics.
+        Returns the tensor holding the loop's result (materialised by one last LayerNorm launch for post-LN)."""
+        cfg = self.config
+        B, T, H = h.shape
+        M = B * T
+        dev = h.device
+        st_a = torch.zeros(M, ops.LN_SLOTS, 2, device=dev, dtype=torch.float32)   # rows of t1 / of h after the attention block
+        st_b = torch.zeros(M, ops.LN_SLOTS, 2, device=dev, dtype=torch.float32)   # rows of t2 / of h after the FFN block
+        v2 = lambda t: t.view(M, -1)   # noqa: E731
+        prev = None                    # post-LN: (raw tensor, its statistics, gamma, beta) of the layer input
+        for l in range(n_layers):
+            b = f"encoder.layers.{l}."
+            ob, f2b = self._w(b + "attention.out_proj.bias"), self._w(b + "feed_forward.output_dense.bias")
+            ln1 = (self._w(b + "layer_norm.weight"), self._w(b + "layer_norm.bias"))
+            ln2 = (self._w(b + "final_layer_norm.weight"), self._w(b + "final_layer_norm.bias"))
+            if cfg.do_stable_layer_norm:   # HF:525-548
+                if l == 0:                 # nobody has produced the statistics of h yet: one real LayerNorm
+                    ops.layernorm(h, ln1[0], ln1[1], t1, eps)
+                    ops.linear(v2(t1), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], v2(qkv))
+                else:
+                    ops.linear_ln(v2(h), P[f"l{l}.qkv.wf"], P[f"l{l}.qkv.wf.c"], v2(qkv), mode="apply", n_norm=H, eps=eps,
+                                  stats_in=st_b, colsum=P[f"l{l}.qkv.wf.colsum"])
+                ops.attention(qkv, key_len, att, cfg.num_attention_heads)
+                ops.linear_ln(v2(att), P[f"l{l}.o.w"], ob, v2(h), mode="residual", n_norm=H, eps=eps, residual=v2(h), stats_out=st_a)
+                ops.linear_ln(v2(h), P[f"l{l}.ff1.wf"], P[f"l{l}.ff1.wf.c"], v2(ff), mode="apply", n_norm=H, eps=eps,
+                              stats_in=st_a, colsum=P[f"l{l}.ff1.wf.colsum"], post_act=ACT_GELU)
+                ops.linear_ln(v2(ff), P[f"l{l}.ff2.w"], f2b, v2(h), mode="residual", n_norm=H, eps=eps, residual=v2(h), stats_out=st_b)
+                continue
+            # post-LN, HF:388-405
+            if prev is None:
+                ops.linear(v2(h), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], v2(qkv))
+                res_kw = dict(residual=v2(h))
+            else:
+                pt, pst, pg, pb = prev
+                ops.linear_ln(v2(pt), P[f"l{l}.qkv.wf"], P[f"l{l}.qkv.wf.c"], v2(qkv), mode="apply", n_norm=H, eps=eps,
+                              stats_in=pst, colsum=P[f"l{l}.qkv.wf.colsum"])
+                res_kw = dict(residual=v2(pt), stats_in=pst, gamma=pg, beta=pb)
+            ops.attention(qkv, key_len, att, cfg.num_attention_heads)
+            ops.linear_ln(v2(att), P[f"l{l}.o.w"], ob, v2(t1), mode="residual", n_norm=H, eps=eps, stats_out=st_a, **res_kw)
+            ops.linear_ln(v2(t1), P[f"l{l}.ff1.wf"], P[f"l{l}.ff1.wf.c"], v2(ff), mode="apply", n_norm=H, eps=eps,
+                          stats_in=st_a, colsum=P[f"l{l}.ff1.wf.colsum"], post_act=ACT_GELU)
+            ops.linear_ln(v2(ff), P[f"l{l}.ff2.w"], f2b, v2(t2), mode="residual", n_norm=H, eps=eps, residual=v2(t1),
+                          stats_in=st_a, gamma=ln1[0], beta=ln1[1], stats_out=st_b)
+            prev = (t2, st_b, ln2[0], ln2[1])
+        if cfg.do_stable_layer_norm:
+            return h
+        pt, _, pg, pb = prev
+        ops.layernorm(pt, pg, pb, h, eps)          # the layer stack's output is the one LayerNorm that must exist in memory
+        return h
 
     def _record_layer(self, l, P, h, qkv, att, ff, nrm, tmp, key_len, eps):
         """Transformer layer l (HF:388-405 post-LN / HF:525-548 pre-LN) on a contiguous batch range of the plan's buffers."""

@@ -364,6 +364,36 @@ def linear(x2d, w, bias, y2d, *, residual=None, **kw):
            residual=None if residual is None else residual.unsqueeze(0), **kw)
 
 
+LN_SLOTS = _lib.SIB_LN_SLOTS
+
+
+def linear_ln(x2d, w, bias, y2d, *, mode, n_norm, eps=1e-5, stats_in=None, colsum=None, gamma=None, beta=None, stats_out=None,
+              residual=None, post_act=ACT_NONE):
+    """bf16 linear layer with a LayerNorm folded into it (`sib_linear_ln_bf16`).
+    mode "apply":    y = act(LN(t) W + b) from the RAW t (= x2d), W' = diag(gamma) W (= w), colsum of W', c = beta W + b (= bias)
+                     and the row statistics of t (`stats_in` [M, LN_SLOTS, 2]).
+    mode "residual": y = x W + b + LN(residual) (`stats_in` / gamma / beta; plain residual when stats_in is None), and the
+                     partial row statistics of y go to `stats_out`."""
+    M, K = x2d.shape
+    N = y2d.shape[1]
+    for t, nme in ((x2d, "x"), (w, "w"), (y2d, "y"), (residual, "residual")):
+        _chk(t, torch.bfloat16, nme)
+    for t, nme in ((bias, "bias"), (stats_in, "stats_in"), (colsum, "colsum"), (gamma, "gamma"), (beta, "beta"), (stats_out, "stats_out")):
+        _chk(t, torch.float32, nme)
+    for t in (stats_in, stats_out):
+        if t is not None and (tuple(t.shape) != (M, LN_SLOTS, 2) or not t.is_contiguous()):
+            raise SibError(f"linear_ln: statistics buffers must be dense [M, {LN_SLOTS}, 2] fp32 tensors")
+    d = make_desc(1, M, M, K, N, [0], x_row=x2d.stride(0), x_batch=M * x2d.stride(0), y_row=y2d.stride(0), y_batch=M * y2d.stride(0),
+                  r_row=None if residual is None else residual.stride(0),
+                  r_batch=None if residual is None else M * residual.stride(0), post_act=post_act)
+    ln = _lib.LnFold()
+    ln.stats_in, ln.colsum, ln.gamma, ln.beta, ln.stats_out = _p(stats_in), _p(colsum), _p(gamma), _p(beta), _p(stats_out)
+    ln.mode = _lib.SIB_LN_APPLY if mode == "apply" else _lib.SIB_LN_RESIDUAL
+    ln.n_norm, ln.eps = n_norm, eps
+    _emit("sib_linear_ln_bf16", (C.byref(d), C.byref(ln), _p(x2d), _p(w), _p(bias), _p(residual), _p(y2d)),
+          keep=(d, ln, x2d, w, bias, residual, y2d, stats_in, colsum, gamma, beta, stats_out))
+
+
 def linear_skinny(x2d, w, bias, y2d):
     """x2d [M,K] fp32 @ packed w [1][1][K][N] (+bias) -> y2d [M,N] for N <= 128: one CTA per row (few-hundred-row heads)."""
     M, K = x2d.shape

@@ -65,6 +65,30 @@ def test_hubert_bf16(sib, name, B, N):
         assert s > SNR_BOUND_DB
 
 
+@pytest.mark.parametrize("name,B,N", [("tiny_group", 2, 8000), ("tiny_layer", 2, 8000), ("base", 2, 32000)])
+def test_hubert_bf16_with_folded_layernorm(sib, name, B, N):
+    """The optional LayerNorm folding (`sib_linear_ln_bf16`: LN(t) W + b = r (t W' - mu s) + c in the epilogue of the consuming
+    linear layer, LN of the residual rebuilt from the raw residual tile, row statistics emitted by the producers) against the
+    same CPU oracle; post-LN (group) and pre-LN (layer) stacks."""
+    from oracle import hubert_ref
+    from oracle.params import HubertCfg, make_hubert_params
+    ocfg = {"tiny_group": HubertCfg.tiny(False), "tiny_layer": HubertCfg.tiny(True), "base": HubertCfg.base()}[name]
+    params = make_hubert_params(ocfg, 1234)
+    model = sib.HubertModel(sib.HubertConfig.from_any(ocfg), precision="bf16").to("cuda")
+    model.fold_layernorm = True
+    model.load_state_dict(params)
+    x = 0.1 * torch.randn(B, N, generator=torch.Generator().manual_seed(3))
+    ref = hubert_ref.hubert_forward(params, ocfg, x, None)
+    n0 = sib.ops.launch_count()
+    y = model(x.cuda()).last_hidden_state.cpu()
+    plan = model._plans.values()[0].plan
+    assert sum(1 for _, _, nme in plan.steps if nme == "sib_layernorm") <= 4           # none left inside the layer loop
+    assert sum(1 for _, _, nme in plan.steps if nme == "sib_linear_ln_bf16") >= 4 * ocfg.num_hidden_layers - 1
+    s = snr_db(ref, y)
+    print(f"\n[bf16 hubert {name}, folded LayerNorm] SNR {s:.1f} dB, max-abs {max_abs(ref, y):.4f}")
+    assert s > SNR_BOUND_DB
+
+
 def test_informed_inpainting_bf16_config1(sib):
     """config #1 shapes through the bf16 arm: labels vs fp32 oracle (agreement rate), waveform mel-L1."""
     from oracle import mel_ref
