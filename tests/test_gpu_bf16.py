@@ -82,7 +82,8 @@ def test_hubert_bf16_with_folded_layernorm(sib, name, B, N):
     n0 = sib.ops.launch_count()
     y = model(x.cuda()).last_hidden_state.cpu()
     plan = model._plans.values()[0].plan
-    assert sum(1 for _, _, nme in plan.steps if nme == "sib_layernorm") <= 4           # none left inside the layer loop
+    outside = 10 if ocfg.feat_extract_norm == "layer" else 3       # feature encoder / projection / encoder-level LayerNorms
+    assert sum(1 for _, _, nme in plan.steps if nme == "sib_layernorm") <= outside    # none left inside the layer loop
     assert sum(1 for _, _, nme in plan.steps if nme == "sib_linear_ln_bf16") >= 4 * ocfg.num_hidden_layers - 1
     s = snr_db(ref, y)
     print(f"\n[bf16 hubert {name}, folded LayerNorm] SNR {s:.1f} dB, max-abs {max_abs(ref, y):.4f}")
