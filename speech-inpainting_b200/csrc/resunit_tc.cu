@@ -268,27 +268,31 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                            a1_inc, w_inc, p.k, p.desc_hi, p.idesc, 1u);
       if (issuer) {
         commit_u<PAIR>(&acc1_full[a1]);
-        commit_u<PAIR>(&x_empty[xs]);
+        if (!WIDE) commit_u<PAIR>(&x_empty[xs]);   // wide: the slot goes on to hold the intermediate tile (freed by conv2)
       }
       if (++xs == p.nxs) { xs = 0; xph ^= 1; }
       if (++a1 == p.na1) { a1 = 0; a1ph ^= 1; }
     };
+    // wide: the intermediate tile of a tile is written IN PLACE over its x slot (conv1 has consumed it by then), so it is as
+    // deeply buffered as the x ring and conv2(i) -> epilogue 1(i+1) -> conv2(i+1) is no longer a serial chain through one
+    // shared buffer; conv2 frees the slot for the producer.
     auto conv2 = [&](int i) {
       const int a = i & 1;
       mbar_wait(&t1_full[tb], tbph);
       mbar_wait(&acc2_empty[a], (uint32_t)(((i >> 1) & 1) ^ 1));
       tc_fence_after();
-      umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)((p.na1 + a) * p.C), make_desc_lo(t1_base + (uint32_t)(tb * p.t1_bytes)), w2_lo,
+      const uint32_t t1_tile = WIDE ? x_base + (uint32_t)(tb * p.x_stage_bytes) : t1_base + (uint32_t)(tb * p.t1_bytes);
+      umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)((p.na1 + a) * p.C), make_desc_lo(t1_tile), w2_lo,
                    a2_inc, w_inc, p.k, p.desc_hi, p.idesc, 0u);
       if (WIDE)
         umma_taps_ks<PAIR>(p.ksteps, issuer, tmem_u + (uint32_t)((p.na1 + a) * p.C),
-                           make_desc_lo(t1_base + (uint32_t)(tb * p.t1_bytes + p.t1_chunk_bytes)), w2_lo + (uint32_t)p.k * w_inc,
+                           make_desc_lo(t1_tile + (uint32_t)p.x_chunk_bytes), w2_lo + (uint32_t)p.k * w_inc,
                            a2_inc, w_inc, p.k, p.desc_hi, p.idesc, 1u);
       if (issuer) {
         commit_u<PAIR>(&acc2_full[a]);
-        commit_u<PAIR>(&t1_empty[tb]);
+        commit_u<PAIR>(WIDE ? &x_empty[tb] : &t1_empty[tb]);
       }
-      if (++tb == p.t1_bufs) { tb = 0; tbph ^= 1; }
+      if (++tb == (WIDE ? p.nxs : p.t1_bufs)) { tb = 0; tbph ^= 1; }
     };
     // conv1 runs `la` tiles ahead: the commit -> epilogue 1 -> intermediate tile -> conv2 chain of one tile (~2-3k clocks
     // of barrier hand-offs) is then spread over la tiles instead of pacing every tile
@@ -351,10 +355,11 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     TileCursor tc = cursor0();
     for (int i = 0; i < n_my; ++i, tc.next()) {
       const int t0 = tc.t0();
-      const uint32_t row_ptr = smem_u32(sm_t1 + tb * p.t1_bytes + r * p.row_bytes);
+      const uint32_t row_ptr = smem_u32((WIDE ? sm_x + tb * p.x_stage_bytes : sm_t1 + tb * p.t1_bytes) + r * p.row_bytes);
       mbar_wait(&acc1_full[a], aph);
-      // conv2 of the tile that last used this intermediate buffer has read it
-      mbar_wait(&t1_empty[tb], tbph ^ 1);
+      // conv2 of the tile that last used this intermediate buffer has read it (wide: the tile's own x slot, which conv1
+      // - complete, or acc1_full would not have fired - was the last reader of)
+      if (!WIDE) mbar_wait(&t1_empty[tb], tbph ^ 1);
       tc_fence_after();
       const int tg = t0 - p.p2 + r;                            // global frame of this t1 row
       const bool inside = tg >= 0 && tg < p.T;
@@ -372,7 +377,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             f[u] = fmaxf(f[u], f[u] * p.slope_mid);          // leaky-relu, 0 < slope < 1
           }
           // (wide: columns 64.. live in the second chunk slab of the intermediate tile)
-          const uint32_t cofs = WIDE ? (uint32_t)(col >> 6) * (uint32_t)p.t1_chunk_bytes + (((((uint32_t)col & 63u) >> 3) ^ swz) << 4)
+          const uint32_t cofs = WIDE ? (uint32_t)(col >> 6) * (uint32_t)p.x_chunk_bytes + (((((uint32_t)col & 63u) >> 3) ^ swz) << 4)
                                      : ((((uint32_t)col >> 3) ^ swz) << 4);
           sts128(row_ptr + cofs, inside ? pack8(f) : make_uint4(0u, 0u, 0u, 0u));
         }
@@ -394,7 +399,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (!WIDE) arrive_mma(&acc1_empty[a]);
       }
       if (++a == p.na1) { a = 0; aph ^= 1; }
-      if (++tb == p.t1_bufs) { tb = 0; tbph ^= 1; }
+      if (++tb == (WIDE ? p.nxs : p.t1_bufs)) { tb = 0; tbph ^= 1; }
     }
   } else if (WIDE && ((warp >= 8 && warp < 12) || warp >= 16)) {
     // ===================== epilogue 2, C = 128: eight warps, two 32-channel groups each ==========
@@ -689,9 +694,9 @@ int plan_resunit_mode(int c, int k, int dil, int accumulate, int has_y2, int pai
   a.nxs = 0;
   // (three staging slots are supported by the kernel but measured 5-8 % slower than two: not offered)
   const int tries[9][3] = {{4, 2, 3}, {3, 2, 3}, {4, 2, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {3, 1, 1}, {2, 1, 2}, {2, 1, 1}};
-  if (wide) {                                        // the staging boxes are fixed: only the x ring may grow
-    if (need(3, 1, 1) <= one_cta) { a.nxs = 3; a.slots = 1; a.t1_bufs = 1; }
-    else if (need(2, 1, 1) <= one_cta) { a.nxs = 2; a.slots = 1; a.t1_bufs = 1; }
+  if (wide) {                                        // no separate intermediate buffer: it is written over the tile's x slot
+    if (need(3, 1, 0) <= one_cta) { a.nxs = 3; a.slots = 1; a.t1_bufs = 0; }
+    else if (need(2, 1, 0) <= one_cta) { a.nxs = 2; a.slots = 1; a.t1_bufs = 0; }
   } else
   for (int pass = pair ? 1 : 0; pass < 2 && a.nxs == 0; ++pass)
     for (const auto& tr : tries)
