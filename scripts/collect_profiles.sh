@@ -18,7 +18,8 @@ python scripts/aux_microbench.py > $OUT/aux_plain_$TAG.txt 2>&1 &&
 timeout 900 ncu --metrics $M_AUX --clock-control none --csv --log-file $OUT/aux_ncu_$TAG.csv \
     -k regex:'mel_kernel|znorm|layernorm|conv0_gn|conv1d_cout1|pack_int16|si_sdr|abs_diff|resample' \
     python scripts/aux_microbench.py > $OUT/ncu_aux.log 2>&1
-for CASE in s4k3d1 s3k7d3; do
+if [ "${2:-full}" != "lists" ]; then
+for CASE in s4k3d1 s3k7d3 s2k3d5; do
   python scripts/resunit_microbench.py --only $CASE --iters 1 > $OUT/plain_ru_$CASE.log 2>&1 &&
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:resunit -c 2 -o $OUT/prof_resunit_${CASE}_$TAG -f \
       python scripts/resunit_microbench.py --only $CASE --iters 1 > $OUT/ncu_ru_$CASE.log 2>&1
@@ -31,4 +32,5 @@ done
 python scripts/aux_microbench.py --only mel > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:mel_kernel -c 1 -o $OUT/prof_mel_$TAG -f \
     python scripts/aux_microbench.py > $OUT/ncu_mel.log 2>&1
+fi
 ls -la $OUT/*$TAG* | head -30
