@@ -17,7 +17,7 @@ from types import SimpleNamespace
 import torch
 
 from . import ops
-from .module import SibModule, _Node
+from .module import SibModule
 from .ops import ACT_GELU, ACT_NONE, Plan, SibError
 
 
