@@ -258,6 +258,34 @@ typedef struct sib_ln_fold {
 int sib_linear_ln_bf16(const sib_conv_desc* d, const sib_ln_fold* ln, const void* x, const void* w, const float* bias,
                        const void* residual, void* y, sib_stream_t stream);
 
+/* Tile-level dataflow between consecutive launches of the transformer loop (HF:388-405 / 525-548: out-proj -> LayerNorm ->
+ * FFN-in -> FFN-out -> LayerNorm -> next QKV are all ROW-WISE dependent).  A kernel boundary is a grid-wide barrier: a
+ * 75-tile GEMM on 74 SM pairs leaves 73 pairs idle for a whole tile time, and every boundary pays the drain of one
+ * kernel plus the pipeline fill of the next.  With a sib_flow the launch does not wait for the previous grid
+ * (programmatic dependent launch without griddepcontrol.wait): its CTAs start as SMs become free and read the rows of
+ * the 128-row block rb (row / 128) only once wait[rb] has reached the target; whoever writes a 32-row x n-column part
+ * of block rb adds n to signal[rb] after the stores have completed (release / acquire at gpu scope).  A full block is
+ * therefore worth 4 x N (N = row length of the producer's output); a LayerNorm producer adds N / 32 per VALID row, so
+ * the last block's target differs (wait_target_last).  Counters are zeroed by the caller before the chain starts
+ * (sib_fill_zero) and hold ceil(rows / 256) * 2 entries.  Arithmetic is untouched: results are bit-identical to the
+ * plain launches.  Every input of a launch that carries `wait` must be covered by the flags directly or transitively
+ * (weights aside); rows must be flat (batch == 1), linear layers only. */
+typedef struct sib_flow {
+  const int32_t* wait;   /* nullable: the launch then orders itself after the previous grid as usual */
+  int32_t* signal;       /* nullable */
+  int32_t wait_target, wait_target_last;
+} sib_flow;
+int sib_linear_flow_bf16(const sib_conv_desc* d, const sib_flow* flow, const void* x, const void* w, const float* bias,
+                         const void* residual, void* y, sib_stream_t stream);
+int sib_layernorm_flow_bf16(const void* x, const void* residual, const float* gamma, const float* beta, void* y,
+                            int64_t rows, int c, float eps, const sib_flow* flow, sib_stream_t stream);
+/* attention inside the chain: the counters run over the FLAT rows b * t + frame.  wait = the QKV projection's counters (an
+ * utterance is read once every row block it touches is complete); signal: 2 (= head_dim / 32) per stored row and head, i.e.
+ * a block is complete at valid_rows x (heads x head_dim) / 32 like a LayerNorm producer's.  head_dim 64. */
+int sib_attention_flow_bf16(const void* qkv, const int32_t* key_len, void* out, int batch, int t, int heads, int head_dim,
+                            const sib_flow* flow, sib_stream_t stream);
+int sib_fill_zero(void* p, int64_t bytes, sib_stream_t stream);
+
 /* K-block geometry the kernel uses for c_in/groups: cc channels x tb taps per pipeline stage (cc*tb = 64). */
 int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb);
 

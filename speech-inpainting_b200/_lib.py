@@ -51,6 +51,11 @@ class LnFold(C.Structure):
                 ("stats_out", C.c_void_p), ("mode", C.c_int32), ("n_norm", C.c_int32), ("eps", C.c_float)]
 
 
+class Flow(C.Structure):
+    """mirror of `sib_flow`"""
+    _fields_ = [("wait", C.c_void_p), ("signal", C.c_void_p), ("wait_target", C.c_int32), ("wait_target_last", C.c_int32)]
+
+
 class SibError(RuntimeError):
     pass
 
@@ -95,6 +100,10 @@ _SIGS = {
     "sib_abs_diff_workspace_bytes": ([_I], C.c_size_t),
     "sib_conv1d_bf16": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_linear_ln_bf16": ([C.POINTER(ConvDesc), C.POINTER(LnFold), _P, _P, _P, _P, _P, _P], _I),
+    "sib_linear_flow_bf16": ([C.POINTER(ConvDesc), C.POINTER(Flow), _P, _P, _P, _P, _P, _P], _I),
+    "sib_layernorm_flow_bf16": ([_P, _P, _P, _P, _P, _L, _I, _F, C.POINTER(Flow), _P], _I),
+    "sib_attention_flow_bf16": ([_P, _P, _P, _I, _I, _I, _I, C.POINTER(Flow), _P], _I),
+    "sib_fill_zero": ([_P, _L, _P], _I),
     "sib_resunit_bf16": ([C.POINTER(ResUnitDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "sib_resunit_bf16_supported": ([_I, _I, _I, _I, _I], _I),
     "sib_conv1d_bf16_pre_act_supported": ([C.POINTER(ConvDesc), _I, _I], _I),

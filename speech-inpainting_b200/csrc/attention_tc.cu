@@ -43,9 +43,17 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // the TMEM allocation and the tensor-map prefetch are paid once per CTA, and the producer warp runs ahead across items: the
 // next item's Q is fetched as soon as the last S MMAs of the current one have retired (q_empty), its first K / V block as
 // soon as a ring stage is free - both under the current item's softmax.  All barrier parities follow running counters.
+//
+// FLOW (sib_attention_flow_bf16, see sib_flow in the header): the kernel boundaries on both sides become per-128-row-block
+// counters over the FLAT rows b * T + t.  An item reads Q / K / V of utterance b once every row block that utterance touches
+// has been completed by the QKV projection (wait); after its output rows are stored it adds 2 per row (head_dim / 32) to the
+// counters of the one or two row blocks they lie in (signal), so a block is complete at rows x heads x 2 = rows x H / 32 -
+// the same accounting as a LayerNorm producer, which is what the out-projection's gate expects.
+template <bool FLOW>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out,
-                    const int32_t* __restrict__ key_len, int T, int heads, int tiles_q, int total_items) {
+                    const int32_t* __restrict__ key_len, int T, int heads, int tiles_q, int total_items, const sib_flow flow,
+                    int total_rows) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint64_t* q_full = bars + 0;
@@ -100,17 +108,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  sib::pdl_wait();                 // PDL: the prologue above overlapped the previous kernel's tail
+  if (!(FLOW && flow.wait)) sib::pdl_wait();   // PDL: the prologue above overlapped the previous kernel's tail
   sib::pdl_launch_dependents();
 
   if (warp == 4) {
     // ===================== TMA producer (whole warp in the loop, one elected lane issues) =====================
     const uint32_t issuer = elect_one_sync();
     uint32_t g = 0, it = 0;                     // running K/V block counter, running item counter
+    int gated_b = -1;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       int q0, h, b;
       decode(item, q0, h, b);
       const int nblk = (blocks_of(b) + KB - 1) / KB;
+      if (FLOW && flow.wait && b != gated_b) {
+        // every row block utterance b touches has all 3H columns of the projection (every lane polls: any may be the issuer)
+        const int last_rb = (total_rows - 1) >> 7;
+        for (int rb = (b * T) >> 7; rb <= (b * T + T - 1) >> 7; ++rb)
+          sib::flow_wait(flow.wait + rb, rb == last_rb ? flow.wait_target_last : flow.wait_target);
+        gated_b = b;
+      }
       mbar_wait(q_empty, (it & 1) ^ 1);         // the S MMAs of the previous item have read Q
       if (issuer) {
         mbar_expect_tx(q_full, TILE_BYTES);
@@ -255,6 +271,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
         dst[u] = pack8(f);
       }
     }
+    if (FLOW && flow.signal) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // the four softmax warps: this item's rows are stored
+      if (r == 0) {
+        const int row0 = b * T + q0, row1 = b * T + min(q0 + QT, T);   // flat rows [row0, row1)
+        const int rb0 = row0 >> 7, rb1 = (row1 - 1) >> 7;
+        const int split = min(row1, (rb0 + 1) << 7);
+        sib::flow_signal(flow.signal + rb0, 2 * (split - row0));
+        if (rb1 != rb0) sib::flow_signal(flow.signal + rb1, 2 * (row1 - split));
+      }
+    }
     }
     tc_fence_before();
   }
@@ -268,8 +294,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
 }  // namespace
 
 // bf16 arm of sib_attention (see attention_f32.cu for the dispatcher and the fp32 SIMT arm).
-int sib_attention_bf16_tc(const void* qkv, const int32_t* key_len, void* out, int batch, int t, int heads,
-                          cudaStream_t stream) {
+static int attention_bf16_tc_impl(const void* qkv, const int32_t* key_len, void* out, int batch, int t, int heads,
+                                  cudaStream_t stream, const sib_flow* flow) {
   const int H = heads * HD;
   CUtensorMap map;
   const cuuint64_t dims[3] = {(cuuint64_t)3 * H, (cuuint64_t)t, (cuuint64_t)batch};
@@ -280,7 +306,9 @@ int sib_attention_bf16_tc(const void* qkv, const int32_t* key_len, void* out, in
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute((const void*)attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute((const void*)attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       sib::set_error("sib_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return SIB_ERR_CUDA;
@@ -295,12 +323,32 @@ int sib_attention_bf16_tc(const void* qkv, const int32_t* key_len, void* out, in
   }
   const int slots = 2 * sib_tc::sm_count_of_current_device();        // two persistent CTAs per SM
   dim3 grid((unsigned)(items < slots ? items : slots));
-  const cudaError_t le = sib::launch_pdl(attention_tc_kernel, grid, dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, map,
-                                         (__nv_bfloat16*)out, key_len, t, heads, tiles_q, (int)items);
+  const sib_flow nf = {nullptr, nullptr, 0, 0};
+  const cudaError_t le =
+      flow ? sib::launch_pdl(attention_tc_kernel<true>, grid, dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, map,
+                             (__nv_bfloat16*)out, key_len, t, heads, tiles_q, (int)items, *flow, batch * t)
+           : sib::launch_pdl(attention_tc_kernel<false>, grid, dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, map,
+                             (__nv_bfloat16*)out, key_len, t, heads, tiles_q, (int)items, nf, batch * t);
   if (le != cudaSuccess) {
     sib::set_error("sib_attention: launch failed: %s", cudaGetErrorString(le));
     return SIB_ERR_CUDA;
   }
   SIB_CHECK_LAUNCH("sib_attention");
   return SIB_OK;
+}
+
+int sib_attention_bf16_tc(const void* qkv, const int32_t* key_len, void* out, int batch, int t, int heads,
+                          cudaStream_t stream) {
+  return attention_bf16_tc_impl(qkv, key_len, out, batch, t, heads, stream, nullptr);
+}
+
+extern "C" int sib_attention_flow_bf16(const void* qkv, const int32_t* key_len, void* out, int batch, int t, int heads,
+                                       int head_dim, const sib_flow* flow, sib_stream_t stream) {
+  SIB_REQUIRE(qkv && out && flow && batch > 0 && t > 0 && heads > 0, "sib_attention_flow_bf16: bad argument");
+  SIB_REQUIRE(head_dim == HD, "sib_attention_flow_bf16: head_dim must be %d", HD);
+  SIB_REQUIRE((int64_t)batch * t < (1ll << 31), "sib_attention_flow_bf16: too many rows");
+  SIB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "sib_attention_flow_bf16: qkv / out must be 16-byte aligned");
+  SIB_REQUIRE(!flow->wait || (flow->wait_target > 0 && flow->wait_target_last > 0), "sib_attention_flow_bf16: wait targets");
+  return attention_bf16_tc_impl(qkv, key_len, out, batch, t, heads, static_cast<cudaStream_t>(stream), flow);
 }

@@ -65,6 +65,48 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 // pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as this grid's CTAs retire.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ---- tile-level dataflow flags (sib_flow, see the header): counters in global memory, one per 128-row block.
+// flow_wait: the calling thread spins (acquire loads at gpu scope) until the counter has reached `target`, then fences
+// the async proxy so that TMA loads issued afterwards are ordered behind the acquire.  A producer that never arrives is
+// a bug of the launch chain, not a runtime condition: after 4 s the kernel traps (a loud launch failure, no hung GPU).
+// The spin loop lives out of line: inlined into the tcgen05 kernels it cost the short GEMMs 2-8 us per launch through
+// register allocation and scheduling of the surrounding loops even when it never ran (same-box microbenchmark of library
+// builds with and without the code, scripts/flow_microbench.py).
+static __device__ __noinline__ void flow_spin(const int32_t* ctr, int32_t target) {
+  int32_t v;
+  uint64_t t_start, t_now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+  do {
+    __nanosleep(64);
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+    if (t_now - t_start > 4000000000ull) __trap();
+  } while (v < target);
+}
+template <bool ASYNC_PROXY_READER = true>
+__device__ __forceinline__ void flow_wait(const int32_t* ctr, int32_t target) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+  if (v < target) flow_spin(ctr, target);
+  // TMA loads issued after this point read through the async proxy: order them behind the (generic-proxy) acquire
+  if (ASYNC_PROXY_READER) asm volatile("fence.proxy.async;" ::: "memory");
+}
+// flow_signal: the calling thread's earlier writes (and, through a preceding CTA / warp barrier, its peers') are
+// published before the counter moves.  Writes made through the async proxy (TMA stores) must have COMPLETED first
+// (cp.async.bulk.wait_group, not .read); their completion carries an implicit generic-async proxy fence.
+__device__ __forceinline__ void flow_signal(int32_t* ctr, int32_t amount) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ctr), "r"(amount) : "memory");
+}
+// the same for rows written by TMA stores of the calling thread: all of its bulk store groups except the `newer` most
+// recent ones must have completed (out of line for the same reason as flow_spin)
+static __device__ __noinline__ void flow_signal_stores(int32_t* ctr, int32_t amount, int newer) {
+  if (newer <= 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  else if (newer == 1) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+  else if (newer == 2) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
+  flow_signal(ctr, amount);
+}
+
 bool pdl_enabled();   // api.cu: false when SIB_NO_PDL is set or after sib_set_pdl(0)
 void set_pdl(int on);
 

@@ -76,6 +76,11 @@ struct TcArgs {
   float ln_inv_n, ln_eps;
   int pre_act;                   // halo mode: leaky-relu(pre_slope) applied in place to every landed A tile (warp 3)
   float pre_slope;
+  // tile-level dataflow (FLOW instantiations, sib_flow): per 128-row block counters
+  const int32_t* flow_wait;      // rows of block rb are loaded only once flow_wait[rb] >= target, or null
+  int32_t* flow_signal;          // += bn once a 32-row quarter of a tile has been stored, or null
+  int flow_target, flow_target_last, flow_last_rb;
+  int flow_bias_first;           // residual epilogue adds (acc + bias) + r like the plain build (see the launch code)
   int tap_row[SIB_MAX_TAPS];     // row coordinate delta per tap
   int tap_ch[SIB_MAX_TAPS];      // channel coordinate delta per tap (stride-s view)
 };
@@ -89,7 +94,10 @@ constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 16, MAX_NB = 6;
 
 // exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below
 // the bf16 rounding of the output): 1 rcp + 1 ex2 + 7 fma instead of erff's ~35 instructions - the FFN-in epilogue
-// (128 x 128 GELUs per tile) would otherwise outlast its mainloop.
+// (128 x 128 GELUs per tile) would otherwise outlast its mainloop.  (r2: a 7-instruction form, erf(x / sqrt 2) ~
+// tanh.approx(x (a1 + a3 x^2 + a5 x^4)) with fitted coefficients, max abs error 7.7e-5, was measured against this one
+// in same-box alternations: 10.68 / 10.73 ms per step against 10.61 / 10.64 - no gain, so the epilogue's GELU is not
+// what paces FFN-in any more; kept behind SIB_GELU_TANH3 for reference.)
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   // z = |x| / sqrt 2 never materialises: 0.3275911 z = 0.23164190 |x| and z^2 log2(e) = 0.72134752 x^2
   float t;
@@ -104,10 +112,25 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   // x * Phi(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2) on both sides of zero: three instructions, no select
   return fmaf(-0.5f, fabsf(x) * erfc_abs, fmaxf(x, 0.f));
 }
+#ifdef SIB_GELU_TANH3
+__device__ __forceinline__ float gelu_tanh3(float x) {
+  const float u = x * x;
+  float p = fmaf(u, -3.94178582e-4f, 3.73382982e-2f);
+  p = fmaf(p, u, 7.97047309e-1f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+#endif
 
 template <int POST_ACT>
 __device__ __forceinline__ float act_t(float v, float slope) {
+#ifdef SIB_GELU_TANH3
+  if (POST_ACT == SIB_ACT_GELU) return gelu_tanh3(v);
+#else
   if (POST_ACT == SIB_ACT_GELU) return gelu_erf_fast(v);
+#endif
   if (POST_ACT == SIB_ACT_LRELU) return v > 0.f ? v : v * slope;
   if (POST_ACT == SIB_ACT_TANH) return tanhf(v);
   return v;
@@ -142,9 +165,12 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 //                 ((t - mu) r gamma + beta); the rows this launch writes are the next raw tensor, and their partial
 //                 statistics (sum, sum of squares per row, per 32-column slice of every N tile) go to ln_stats_out.
 // Together they remove every LayerNorm launch from the transformer loop (HF:388-405).  Separate instantiations again.
+//
+// FLOW = true (linear layers of the transformer loop, sib_linear_flow_bf16): the kernel boundary towards the producer of
+// the A rows (and of the residual rows) is replaced by per-128-row-block counters; see sib_flow in the header.
 constexpr int LN_SLOTS = 32;     // partial-statistics slots per row: 2 per N tile (the two epilogue warps of a lane quarter)
-template <int POST_ACT, bool PAIR, int EPI = 0>
-__global__ void __launch_bounds__(PAIR ? NUM_THREADS_PAIR : NUM_THREADS, (PAIR || EPI != 0) ? 1 : 2)
+template <int POST_ACT, bool PAIR, int EPI = 0, bool FLOW = false>
+__global__ void __launch_bounds__(PAIR ? NUM_THREADS_PAIR : NUM_THREADS, (PAIR || EPI != 0 || FLOW) ? 1 : 2)
 conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y2,
                       const __grid_constant__ CUtensorMap map_r, const __grid_constant__ TcArgs p) {
@@ -210,9 +236,15 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent loop over (pair) tiles
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  // PDL: everything above overlapped the previous kernel's tail; from here on global memory is touched
-  sib::pdl_wait();
+  // PDL: everything above overlapped the previous kernel's tail; from here on global memory is touched.  A FLOW launch
+  // with wait counters does not wait for the previous grid: its loads are ordered block by block through the counters.
+  if (!(FLOW && p.flow_wait)) sib::pdl_wait();
   sib::pdl_launch_dependents();
+  auto flow_gate = [&](int t0) {            // rows [t0, t0 + 128) of the producer's output are complete
+    if (t0 >= p.t_out) return;              // (odd CTA of a last pair tile that lies past the end: nothing real to load)
+    const int rb = t0 >> 7;
+    sib::flow_wait(p.flow_wait + rb, rb == p.flow_last_rb ? p.flow_target_last : p.flow_target);
+  };
 
   // tile -> (n fastest, m, batch*group): CTAs that run concurrently share the same A rows in L2
   auto decode = [&](int tile, int& t0, int& n0, int& b, int& g) {
@@ -256,6 +288,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       } else {
         const int iters = p.n_chunks * p.n_tapblocks;
         int cc = 0, tb = 0;
+        if (FLOW && p.flow_wait) flow_gate(t0);      // every lane polls (the issuer is whichever lane was elected)
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&a_empty[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * p.stage_bytes;
@@ -439,6 +472,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       int t0, n0, b, g;
       decode(tile, t0, n0, b, g);
       const int ch = g * p.cout_g + n0 + blk * p.cw;
+      if (FLOW && EPI == 1 && p.flow_wait && blk == 0) flow_gate(t0);   // the residual rows come from the same chain of producers
       mbar_expect_tx(&my_res_bar[slot], pre_bytes);
       if (p.has_res) tma_load_3d(stage_r + (slot * 4 + q) * box_bytes, &map_r, &my_res_bar[slot], ch, t0 + q * 32, b);
       if (p.accumulate) tma_load_3d(stage_y + (slot * 4 + q) * box_bytes, &map_y, &my_res_bar[slot], ch, t0 + q * 32, b);
@@ -457,6 +491,7 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     int acc = 0, slot = 0;
     uint32_t acc_phase = 0, res_phase_bits = 0;
+    int sig_rb = -1;        // FLOW (leader lane): row block of the last finished tile, stores committed, not yet signalled
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
       int t0, n0, b, g;
       decode(tile, t0, n0, b, g);
@@ -551,13 +586,24 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const uint32_t off = h ? off1 : off0;
             float f[8], r[8];
             unpack8(rr[h], r);
+            if (FLOW && p.flow_bias_first) {
+              // same order of the fp32 additions as the plain build, so that a dataflow launch of a layer whose plain launch
+              // would not use this build (narrow tiles, two CTAs per SM) stays bit-identical to it
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]) + r[i];
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]) + r[i];
+            }
             if (p.bias) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + cb + col + 4));
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
               f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (FLOW && p.flow_bias_first) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += r[i];
             }
             if (p.accumulate) {                      // (2 of the 9 units of a stage: loaded in place)
               float o[8];
@@ -670,6 +716,17 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           else if (pending == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else if (pending == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+          if (FLOW && p.flow_signal) {
+            // The previous tile's 32 rows x bn columns are published from block min(2, nblk - 1) of this tile: every store
+            // group older than this tile's (blk + 1 of them) must have COMPLETED (wait_group without .read).  Two blocks of
+            // slack hide the write latency of the tile's last stores - waiting for them right away stalled this warp pair
+            // for ~1 us per tile, 12-16 % of the short GEMMs.
+            if (sig_rb >= 0 && blk == (p.nblk > 2 ? 2 : p.nblk - 1)) {
+              sib::flow_signal_stores(p.flow_signal + sig_rb, p.bn, blk + 1);
+              sig_rb = -1;
+            }
+            if (blk == p.nblk - 1) sig_rb = t0 >> 7;
+          }
           if (prefetch && pf_tile < p.total_tiles) issue_prefetch(pf_tile, pf_blk, pf_slot);
         }
         if (prefetch) pf_advance();
@@ -684,7 +741,10 @@ conv1d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (half == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (half == 0 && lane == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (FLOW && p.flow_signal && sig_rb >= 0) sib::flow_signal_stores(p.flow_signal + sig_rb, p.bn, 0);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   if (PAIR) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the pair's MMAs / multicast arrives touch it
@@ -714,7 +774,7 @@ extern "C" int sib_conv1d_bf16_kblock(int c_in_per_group, int* cc, int* tb) {
 
 static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w, const float* bias,
                             const void* residual, void* y, void* y_act, sib_stream_t stream, bool dry_run,
-                            const sib_ln_fold* ln = nullptr) {
+                            const sib_ln_fold* ln = nullptr, const sib_flow* flow = nullptr) {
   SIB_REQUIRE(d && x && w && y, "sib_conv1d_bf16: null argument");
   SIB_REQUIRE(d->batch > 0 && d->t_in > 0 && d->t_out > 0 && d->c_in > 0 && d->c_out > 0, "sib_conv1d_bf16: empty shape");
   SIB_REQUIRE(d->groups > 0 && d->c_in % d->groups == 0 && d->c_out % d->groups == 0,
@@ -858,7 +918,7 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
   const int slab_total = a.nb * (1 + a.need_r) * 4 * 32 * cw * 2;  // nb x (y [+ r]) boxes for 4 epilogue warp pairs
   // narrow layers (bn <= 32: 8 KB output tiles) are bound by the per-tile latency chain of one CTA, not by any
   // throughput: run two persistent CTAs per SM on half the shared memory each
-  const int ctas_per_sm = (bn <= 32 && !pair) ? 2 : 1;
+  const int ctas_per_sm = (bn <= 32 && !pair && !flow) ? 2 : 1;   // (the dataflow kernels are built for one CTA per SM)
   const int smem_budget = ctas_per_sm == 2 ? 112 * 1024 : 227 * 1024;
   const int avail = smem_budget - 2048 - slab_total - 1024;
 
@@ -922,6 +982,16 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
     a.ln_stats_in = ln->stats_in; a.ln_colsum = ln->colsum; a.ln_gamma = ln->gamma; a.ln_beta = ln->beta;
     a.ln_stats_out = ln->stats_out; a.ln_inv_n = 1.f / (float)ln->n_norm; a.ln_eps = ln->eps;
     epi_ln = ln->mode == SIB_LN_APPLY ? 2 : 3;
+  }
+  if (flow) {
+    SIB_REQUIRE(!ln && d->n_taps == 1 && d->groups == 1 && d->stride == 1 && d->batch == 1 && !d->accumulate && !y_act &&
+                    d->pre_act == SIB_ACT_NONE && !d->res_after_act && (d->post_act == SIB_ACT_NONE || d->post_act == SIB_ACT_GELU),
+                "sib_linear_flow_bf16: plain linear layers over flat rows only (batch 1, one tap, activation none / gelu)");
+    SIB_REQUIRE(!(residual && d->post_act != SIB_ACT_NONE), "sib_linear_flow_bf16: a residual input comes without activation");
+    SIB_REQUIRE(!flow->wait || (flow->wait_target > 0 && flow->wait_target_last > 0), "sib_linear_flow_bf16: wait targets");
+    a.flow_wait = flow->wait; a.flow_signal = flow->signal;
+    a.flow_target = flow->wait_target; a.flow_target_last = flow->wait_target_last;
+    a.flow_last_rb = (d->t_out - 1) >> 7;
   }
   if (a.pre_act && a.mode != 1) {
     sib::set_error("sib_conv1d_bf16: pre-activation needs the halo mode (stride 1, > 1 evenly spaced taps, tile fits); "
@@ -997,7 +1067,12 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    const void* fns[18] = {(const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, false>,
+    const void* fns[24] = {
+                           // tile-level dataflow (transformer loop)
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false, 0, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, false, 0, true>,
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true, 0, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, true, 0, true>,
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false, 1, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true, 1, true>,
+                           (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, false>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, false>,
                            (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, false>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH, false>,
                            (const void*)conv1d_bf16_tc_kernel<SIB_ACT_NONE, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_GELU, true>,
                            (const void*)conv1d_bf16_tc_kernel<SIB_ACT_LRELU, true>, (const void*)conv1d_bf16_tc_kernel<SIB_ACT_TANH, true>,
@@ -1022,16 +1097,27 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
   const int grid = (a.total_tiles < slots ? a.total_tiles : slots) * (pair ? 2 : 1);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   cudaError_t le = cudaSuccess;
-#define SIB_TC_LAUNCH_H(ACT, HOIST)                                                                                     \
-  le = pair ? sib::launch_pdl_cluster(conv1d_bf16_tc_kernel<ACT, true, HOIST>, dim3(grid), dim3(NUM_THREADS_PAIR),      \
+#define SIB_TC_LAUNCH_HF(ACT, HOIST, FLOW)                                                                              \
+  le = pair ? sib::launch_pdl_cluster(conv1d_bf16_tc_kernel<ACT, true, HOIST, FLOW>, dim3(grid), dim3(NUM_THREADS_PAIR), \
                                       (size_t)smem_bytes, cs, 2u, map_a, map_b, map_y, map_y2, map_r, a)                \
-            : sib::launch_pdl(conv1d_bf16_tc_kernel<ACT, false, HOIST>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
+            : sib::launch_pdl(conv1d_bf16_tc_kernel<ACT, false, HOIST, FLOW>, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, cs, \
                               map_a, map_b, map_y, map_y2, map_r, a)
+#define SIB_TC_LAUNCH_H(ACT, HOIST) SIB_TC_LAUNCH_HF(ACT, HOIST, false)
 #define SIB_TC_LAUNCH(ACT) SIB_TC_LAUNCH_H(ACT, 0)
   static const bool hoist_on = !(getenv("SIB_TC_HOIST") && atoi(getenv("SIB_TC_HOIST")) == 0);   // A/B switch
   const bool hoist = hoist_on && a.has_res && !a.res_after_act && ctas_per_sm == 1 &&
                      (d->post_act == SIB_ACT_NONE || d->post_act == SIB_ACT_LRELU);
-  if (epi_ln == 2) {
+  if (flow) {
+    SIB_REQUIRE(ctas_per_sm == 1, "sib_linear_flow_bf16: tile too narrow");
+    if (a.has_res) {
+      // (the residual prefetch is only gated in this build; the additions follow whichever build the plain launch would pick)
+      const bool plain_hoist = hoist_on && !(bn <= 32 && !pair);
+      a.flow_bias_first = plain_hoist ? 0 : 1;
+      SIB_TC_LAUNCH_HF(SIB_ACT_NONE, 1, true);
+    }
+    else if (d->post_act == SIB_ACT_GELU) SIB_TC_LAUNCH_HF(SIB_ACT_GELU, 0, true);
+    else SIB_TC_LAUNCH_HF(SIB_ACT_NONE, 0, true);
+  } else if (epi_ln == 2) {
     SIB_REQUIRE(ctas_per_sm == 1, "sib_linear_ln_bf16: tile too narrow");
     if (d->post_act == SIB_ACT_GELU) SIB_TC_LAUNCH_H(SIB_ACT_GELU, 2);
     else SIB_TC_LAUNCH_H(SIB_ACT_NONE, 2);
@@ -1053,6 +1139,7 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
   }
 #undef SIB_TC_LAUNCH
 #undef SIB_TC_LAUNCH_H
+#undef SIB_TC_LAUNCH_HF
   if (le != cudaSuccess) {
     sib::set_error("sib_conv1d_bf16: launch failed: %s", cudaGetErrorString(le));
     return SIB_ERR_CUDA;
@@ -1070,6 +1157,12 @@ extern "C" int sib_linear_ln_bf16(const sib_conv_desc* d, const sib_ln_fold* ln,
                                   const void* residual, void* y, sib_stream_t stream) {
   SIB_REQUIRE(ln, "sib_linear_ln_bf16: null sib_ln_fold");
   return conv1d_bf16_impl(d, x, w, bias, residual, y, nullptr, stream, false, ln);
+}
+
+extern "C" int sib_linear_flow_bf16(const sib_conv_desc* d, const sib_flow* flow, const void* x, const void* w, const float* bias,
+                                    const void* residual, void* y, sib_stream_t stream) {
+  SIB_REQUIRE(flow, "sib_linear_flow_bf16: null sib_flow");
+  return conv1d_bf16_impl(d, x, w, bias, residual, y, nullptr, stream, false, nullptr, flow);
 }
 
 // 1 if sib_conv1d_bf16 would run this descriptor with its leaky-relu pre-activation (halo mode selected), else 0

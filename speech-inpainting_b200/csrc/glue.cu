@@ -275,6 +275,18 @@ extern "C" int sib_cast_f32_to_bf16(const float* in, void* out, int64_t n, sib_s
   return SIB_OK;
 }
 
+// zeroes the dataflow counters (sib_flow) at the head of a launch chain; a memset node orders itself after everything
+// queued before it, so a previous replay of the same plan has drained its counters by then
+extern "C" int sib_fill_zero(void* p, int64_t bytes, sib_stream_t stream) {
+  SIB_REQUIRE(p && bytes > 0, "sib_fill_zero: bad argument");
+  cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    sib::set_error("sib_fill_zero: %s", cudaGetErrorString(e));
+    return SIB_ERR_CUDA;
+  }
+  return SIB_OK;
+}
+
 extern "C" int sib_cast_bf16_to_f32(const void* in, float* out, int64_t n, sib_stream_t stream) {
   SIB_REQUIRE(in && out && n > 0, "sib_cast_bf16_to_f32: bad argument");
   cast_bf16_f32_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)in, out, n);

@@ -57,18 +57,48 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TX* __restrict__ x
 
 // bf16 rows with C % 8 == 0: one warp per row, 16-byte loads / stores (lane owns chunks lane, lane+32, ... of 8 channels),
 // row in registers, two-pass variance in fp32.  3 vector loads per tensor per lane at C = 768 instead of 24 scalar ones.
-template <int NV>
+template <int NV, bool COHERENT>
+__device__ __forceinline__ void layernorm_bf16_row(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                   __nv_bfloat16* __restrict__ y, int64_t row, int C, float eps, int post_act,
+                                                   int lane);
+// FLOW (sib_layernorm_flow_bf16, see sib_flow in the header): instead of waiting for the previous grid, a row's warp polls
+// the counter of its 128-row block, reads the row with L2-coherent loads (it may have been written while this grid was
+// already running) and adds C / 32 to the outgoing counter once the row is stored.
+template <int NV, bool FLOW = false>
 __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x,
                                                                  const __nv_bfloat16* __restrict__ res,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta,
                                                                  __nv_bfloat16* __restrict__ y, int64_t rows, int C,
-                                                                 float eps, int post_act) {
-  sib::pdl_wait();                 // PDL-launched: may start while the producing GEMM is still draining
+                                                                 float eps, int post_act, const sib_flow flow) {
+  if (!(FLOW && flow.wait)) sib::pdl_wait();   // PDL-launched: may start while the producing GEMM is still draining
   sib::pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (FLOW) {
+    // warp-granular: a row's warp polls and publishes on its own (no CTA barrier in this single-wave, latency-bound kernel)
+    const int rb = (int)(row >> 7);
+    if (flow.wait) {
+      if (lane == 0) sib::flow_wait<false>(flow.wait + rb, rb == (int)((rows - 1) >> 7) ? flow.wait_target_last : flow.wait_target);
+      __syncwarp();
+    }
+    layernorm_bf16_row<NV, true>(x, res, gamma, beta, y, row, C, eps, post_act, lane);
+    if (flow.signal) {
+      __syncwarp();            // the lanes' stores are ordered before lane 0's release
+      if (lane == 0) sib::flow_signal(flow.signal + rb, C >> 5);
+    }
+    return;
+  }
+  layernorm_bf16_row<NV, false>(x, res, gamma, beta, y, row, C, eps, post_act, lane);
+}
+
+template <int NV, bool COHERENT>
+__device__ __forceinline__ void layernorm_bf16_row(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                   __nv_bfloat16* __restrict__ y, int64_t row, int C, float eps, int post_act,
+                                                   int lane) {
   const int nchunks = C >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
   const uint4* rr = res ? reinterpret_cast<const uint4*>(res + row * C) : nullptr;
@@ -78,7 +108,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bflo
   for (int i = 0; i < NV; ++i) {
     const int ch = lane + i * 32;
     if (ch < nchunks) {
-      const uint4 a = __ldg(xr + ch);
+      const uint4 a = COHERENT ? __ldcg(xr + ch) : __ldg(xr + ch);
       const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -86,7 +116,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const __nv_bflo
         v[i][2 * u] = t.x; v[i][2 * u + 1] = t.y;
       }
       if (rr) {
-        const uint4 b = __ldg(rr + ch);
+        const uint4 b = COHERENT ? __ldcg(rr + ch) : __ldg(rr + ch);
         const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -549,9 +579,10 @@ extern "C" int sib_layernorm(const void* x, int x_dtype, const void* residual, i
     __nv_bfloat16* yb = (__nv_bfloat16*)y;
     const int nv = (c / 8 + 31) / 32;
     cudaError_t le;
-    if (nv <= 2) le = sib::launch_pdl(layernorm_bf16_vec_kernel<2>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, post_act);
-    else if (nv <= 4) le = sib::launch_pdl(layernorm_bf16_vec_kernel<4>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, post_act);
-    else le = sib::launch_pdl(layernorm_bf16_vec_kernel<8>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, post_act);
+    const sib_flow nf = {nullptr, nullptr, 0, 0};
+    if (nv <= 2) le = sib::launch_pdl(layernorm_bf16_vec_kernel<2>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, post_act, nf);
+    else if (nv <= 4) le = sib::launch_pdl(layernorm_bf16_vec_kernel<4>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, post_act, nf);
+    else le = sib::launch_pdl(layernorm_bf16_vec_kernel<8>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, post_act, nf);
     if (le != cudaSuccess) {
       sib::set_error("sib_layernorm: launch failed: %s", cudaGetErrorString(le));
       return SIB_ERR_CUDA;
@@ -567,6 +598,33 @@ extern "C" int sib_layernorm(const void* x, int x_dtype, const void* residual, i
     default: SIB_REQUIRE(false, "sib_layernorm: unsupported dtype combination x=%d r=%d y=%d", x_dtype, r_dtype, y_dtype);
   }
   SIB_CHECK_LAUNCH("sib_layernorm");
+  return SIB_OK;
+}
+
+extern "C" int sib_layernorm_flow_bf16(const void* x, const void* residual, const float* gamma, const float* beta, void* y,
+                                       int64_t rows, int c, float eps, const sib_flow* flow, sib_stream_t stream) {
+  SIB_REQUIRE(x && gamma && beta && y && rows > 0 && flow, "sib_layernorm_flow_bf16: bad argument");
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+  SIB_REQUIRE(c % 32 == 0 && c <= 2048 && al16(x) && al16(y) && al16(gamma) && al16(beta) && (!residual || al16(residual)),
+              "sib_layernorm_flow_bf16: c=%d must be a multiple of 32, <= 2048, with 16-byte aligned operands", c);
+  SIB_REQUIRE(!flow->wait || (flow->wait_target > 0 && flow->wait_target_last > 0), "sib_layernorm_flow_bf16: wait targets");
+  const int warps = 8;    // 128 % warps == 0: a CTA's rows never straddle a 128-row block
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+  const __nv_bfloat16* rb = (const __nv_bfloat16*)residual;
+  __nv_bfloat16* yb = (__nv_bfloat16*)y;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nv = (c / 8 + 31) / 32;
+  const int act = SIB_ACT_NONE;
+  cudaError_t le;
+  if (nv <= 2) le = sib::launch_pdl(layernorm_bf16_vec_kernel<2, true>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, act, *flow);
+  else if (nv <= 4) le = sib::launch_pdl(layernorm_bf16_vec_kernel<4, true>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, act, *flow);
+  else le = sib::launch_pdl(layernorm_bf16_vec_kernel<8, true>, dim3(grid), dim3(warps * 32), 0, s, xb, rb, gamma, beta, yb, rows, c, eps, act, *flow);
+  if (le != cudaSuccess) {
+    sib::set_error("sib_layernorm_flow_bf16: launch failed: %s", cudaGetErrorString(le));
+    return SIB_ERR_CUDA;
+  }
+  SIB_CHECK_LAUNCH("sib_layernorm_flow_bf16");
   return SIB_OK;
 }
 

@@ -185,6 +185,14 @@ class HubertModel(SibModule):
         # 24 small LayerNorm launches it removes; it also makes a row's statistics depend on the N tiling the cost model picks
         # for the batch size, which breaks the bit-exact shard invariance.  Kept as a tested option (SIB_HUBERT_FOLD_LN=1).
         self.fold_layernorm = precision == "bf16" and os.environ.get("SIB_HUBERT_FOLD_LN", "0") != "0"
+        # bf16 arm, OFF by default: tile-level dataflow between the launches of the transformer loop (ops.FlowChain / sib_flow)
+        # instead of grid-wide kernel boundaries; bit-identical results.  1 = the GEMM / LayerNorm hand-offs, 2 = the attention
+        # kernel's two boundaries as well.  Measured on B200, same-box alternations of level 2 against 0: 32 x 4 s HuBERT-base
+        # 10.37-10.42 against 10.40-10.51 ms per step (-0.7 %), 64 x 4 s I_da 22.70-22.74 against 22.45-22.62 (+0.8 %),
+        # HuBERT-large 128 x 6 s 89.2-89.4 against 88.6-89.3 (neutral): the overlap it buys (6-8 us per half layer) is about
+        # what its release / acquire pairs cost, because programmatic dependent launch already hides most of every boundary
+        # and a late-starting CTA still owns a full static share of tiles.  SIB_HUBERT_FLOW=1|2 enables it.
+        self.flow = int(os.environ.get("SIB_HUBERT_FLOW", "0")) if precision == "bf16" else 0
 
     # ---- state
     def _expected_keys(self):
@@ -287,7 +295,12 @@ class HubertModel(SibModule):
         eps = cfg.layer_norm_eps
         io = SimpleNamespace(wave=torch.empty(B, N, **real_f32), key_len=torch.empty(B, dtype=torch.int32, device=dev) if padded else None)
         plan = Plan()
+        fold = bf16 and self.fold_layernorm and self.transformer_chains <= 1 and n_layers > 0
         with plan.record():
+            chain = None
+            if bf16 and self.flow and not fold and self.transformer_chains <= 1 and n_layers > 0:
+                chain = ops.FlowChain(B * T, 7 * n_layers, dev)
+                chain.reset()                  # first launch of the plan: the counters are zero before anything signals
             # ---- feature encoder (HF:203-213)
             t0 = lens[1]
             a = act_buf(B, t0, C)
@@ -338,13 +351,15 @@ class HubertModel(SibModule):
             h = h2
             # ---- transformer layers
             qkv = torch.empty(B, T, 3 * H, **f32)
+            # with the attention kernel inside the dataflow chain, the projection of layer l + 1 may start on early row blocks
+            # while a late utterance of layer l still reads its keys / values: the two layers' projections alternate buffers
+            qkv_alt = torch.empty(B, T, 3 * H, **f32) if chain is not None else qkv
             att = torch.empty(B, T, H, **f32)
             ff = torch.empty(B, T, cfg.intermediate_size, **f32)
             nrm = torch.empty(B, T, H, **f32)
             # Two independent half-batch chains through the transformer stack (every op is row- or utterance-wise): the
             # GEMMs of 32 x 199 frames are 1.0 - 4.1 waves of tiles, so a single chain leaves most SMs idle during each
             # kernel's last wave; the other chain's kernel fills them (ops.Plan.chain).  Same buffers, disjoint row ranges.
-            fold = bf16 and self.fold_layernorm and self.transformer_chains <= 1 and n_layers > 0
             if fold:
                 h = self._record_layers_folded(P, h, qkv, att, ff, tmp, nrm, io.key_len, eps, n_layers)
             halves = [(0, B)]
@@ -354,11 +369,15 @@ class HubertModel(SibModule):
                 nc = self.transformer_chains
                 halves = [(B * c // nc, B * (c + 1) // nc) for c in range(nc)]
                 plan.fork()
+            # Tile-level dataflow through the loop (ops.FlowChain / sib_flow): out-proj -> LN -> FFN-in -> FFN-out -> LN -> QKV
+            # hand their rows over per 128-row block, so the tail of one kernel overlaps the head of the next.
+            edge = None
             for l in range(n_layers if halves else 0):   # layer-major order: the host feeds both streams alternately
                 for c, (b0, b1) in enumerate(halves):
                     with plan.chain(c):
-                        self._record_layer(l, P, h[b0:b1], qkv[b0:b1], att[b0:b1], ff[b0:b1], nrm[b0:b1], tmp[b0:b1],
-                                           None if io.key_len is None else io.key_len[b0:b1], eps)
+                        edge = self._record_layer(l, P, h[b0:b1], (qkv if l % 2 == 0 else qkv_alt)[b0:b1], att[b0:b1], ff[b0:b1], nrm[b0:b1], tmp[b0:b1],
+                                                  None if io.key_len is None else io.key_len[b0:b1], eps, chain=chain, edge_in=edge,
+                                                  last=l == n_layers - 1)
             if len(halves) > 1:
                 plan.join()
             if cfg.do_stable_layer_norm and n_layers == cfg.num_hidden_layers:
@@ -429,8 +448,10 @@ class HubertModel(SibModule):
         ops.layernorm(pt, pg, pb, h, eps)          # the layer stack's output is the one LayerNorm that must exist in memory
         return h
 
-    def _record_layer(self, l, P, h, qkv, att, ff, nrm, tmp, key_len, eps):
-        """Transformer layer l (HF:388-405 post-LN / HF:525-548 pre-LN) on a contiguous batch range of the plan's buffers."""
+    def _record_layer(self, l, P, h, qkv, att, ff, nrm, tmp, key_len, eps, chain=None, edge_in=None, last=False):
+        """Transformer layer l (HF:388-405 post-LN / HF:525-548 pre-LN) on a contiguous batch range of the plan's buffers.
+        With a `chain` (ops.FlowChain) every hand-off except the two around the attention kernel is per 128-row block;
+        `edge_in` is the edge the previous layer's last launch signals, the return value this layer's."""
         cfg = self.config
         Bc, T, H = h.shape
         M = Bc * T
@@ -439,6 +460,34 @@ class HubertModel(SibModule):
         f1b = self._w(b + "feed_forward.intermediate_dense.bias")
         ln1 = (self._w(b + "layer_norm.weight"), self._w(b + "layer_norm.bias"))
         ln2 = (self._w(b + "final_layer_norm.weight"), self._w(b + "final_layer_norm.bias"))
+        if chain is not None:
+            I = ff.shape[-1]
+            v2 = lambda t: t.view(M, -1)   # noqa: E731
+            e1, e3 = chain.edge("linear", H), chain.edge("linear", I)
+            e2 = chain.edge("layernorm", H)
+            eq, eo = (chain.edge("linear", 3 * H), chain.edge("attention", H)) if int(self.flow) >= 2 else (None, None)
+            heads = cfg.num_attention_heads
+            if cfg.do_stable_layer_norm:  # HF:525-548; h is updated in place by the two residual GEMMs
+                ea = chain.edge("layernorm", H)
+                e4 = chain.edge("linear", H)
+                ops.layernorm(h, ln1[0], ln1[1], nrm, eps, wait=edge_in, signal=ea)
+                ops.linear(v2(nrm), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], v2(qkv), wait=ea, signal=eq)
+                ops.attention(qkv, key_len, att, heads, wait=eq, signal=eo)
+                ops.linear(v2(att), P[f"l{l}.o.w"], ob, v2(h), residual=v2(h), wait=eo, signal=e1)
+                ops.layernorm(h, ln2[0], ln2[1], nrm, eps, wait=e1, signal=e2)
+                ops.linear(v2(nrm), P[f"l{l}.ff1.w"], f1b, v2(ff), post_act=ACT_GELU, wait=e2, signal=e3)
+                # the loop's last launch hands over to a plain launch (grid-wide wait): no counter needed
+                ops.linear(v2(ff), P[f"l{l}.ff2.w"], f2b, v2(h), residual=v2(h), wait=e3, signal=None if last else e4)
+                return e4
+            e4, e5 = chain.edge("linear", H), chain.edge("layernorm", H)
+            ops.linear(v2(h), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], v2(qkv), wait=edge_in, signal=eq)
+            ops.attention(qkv, key_len, att, heads, wait=eq, signal=eo)
+            ops.linear(v2(att), P[f"l{l}.o.w"], ob, v2(tmp), wait=eo, signal=e1)
+            ops.layernorm(tmp, ln1[0], ln1[1], nrm, eps, residual=h, wait=e1, signal=e2)
+            ops.linear(v2(nrm), P[f"l{l}.ff1.w"], f1b, v2(ff), post_act=ACT_GELU, wait=e2, signal=e3)
+            ops.linear(v2(ff), P[f"l{l}.ff2.w"], f2b, v2(tmp), wait=e3, signal=e4)
+            ops.layernorm(tmp, ln2[0], ln2[1], h, eps, residual=nrm, wait=e4, signal=None if last else e5)
+            return e5
         if cfg.do_stable_layer_norm:  # HF:525-548
             ops.layernorm(h, ln1[0], ln1[1], nrm, eps)
             ops.linear(nrm.view(M, H), P[f"l{l}.qkv.w"], P[f"l{l}.qkv.b"], qkv.view(M, 3 * H))

@@ -358,10 +358,82 @@ def resunit(x, w1, b1, w2, b2, y, k, dilation, *, y_act=None, accumulate=False, 
           keep=(d, x, w1, b1, w2, b2, y, y_act))
 
 
-def linear(x2d, w, bias, y2d, *, residual=None, **kw):
-    """x2d [M,K] @ packed w [1][1][K][N] (+bias) -> y2d [M,N]."""
-    conv1d(x2d.unsqueeze(0), w, bias, y2d.unsqueeze(0), [0],
-           residual=None if residual is None else residual.unsqueeze(0), **kw)
+def linear(x2d, w, bias, y2d, *, residual=None, wait=None, signal=None, **kw):
+    """x2d [M,K] @ packed w [1][1][K][N] (+bias) -> y2d [M,N].
+    wait / signal: `FlowEdge`s of a `FlowChain` (bf16 only) - the launch then reads its rows block by block as their
+    producer finishes them instead of waiting for the previous grid, and / or publishes its own row blocks (`sib_flow`)."""
+    if wait is None and signal is None:
+        conv1d(x2d.unsqueeze(0), w, bias, y2d.unsqueeze(0), [0],
+               residual=None if residual is None else residual.unsqueeze(0), **kw)
+        return
+    M, K = x2d.shape
+    N = y2d.shape[1]
+    for t, nme in ((x2d, "x"), (w, "w"), (y2d, "y"), (residual, "residual")):
+        _chk(t, torch.bfloat16, nme)
+    _chk(bias, torch.float32, "bias")
+    d = make_desc(1, M, M, K, N, [0], x_row=x2d.stride(0), x_batch=M * x2d.stride(0), y_row=y2d.stride(0), y_batch=M * y2d.stride(0),
+                  r_row=None if residual is None else residual.stride(0),
+                  r_batch=None if residual is None else M * residual.stride(0), **kw)
+    fl = _flow_struct(M, wait, signal, N)
+    _emit("sib_linear_flow_bf16", (C.byref(d), C.byref(fl), _p(x2d), _p(w), _p(bias), _p(residual), _p(y2d)),
+          keep=(d, fl, x2d, w, bias, residual, y2d, wait, signal))
+
+
+class FlowEdge:
+    """One counter row of a `FlowChain`: written by exactly one producer launch, polled by its consumers."""
+
+    def __init__(self, counters, kind, n, rows):
+        self.counters, self.kind, self.n, self.rows = counters, kind, n, rows
+
+    def targets(self):
+        """(value of a complete 128-row block, value of the last block) - a linear layer stores whole 32-row quarters
+        (4 x n per block whatever the number of valid rows), a LayerNorm adds n / 32 per valid row."""
+        full = 4 * self.n
+        if self.kind == "linear":
+            return full, full
+        # "layernorm" / "attention": n / 32 per valid row
+        valid_last = self.rows - 128 * ((self.rows - 1) // 128)
+        return full, valid_last * (self.n // 32)
+
+
+class FlowChain:
+    """Dataflow counters for a chain of row-wise dependent launches over `rows` flat rows (`sib_flow`): one int32 per
+    128-row block and edge.  `reset()` is recorded at the head of the plan that uses the chain."""
+
+    def __init__(self, rows: int, n_edges: int, device):
+        self.rows = rows
+        self.n_rb = 2 * ((rows + 255) // 256)       # the odd CTA of a last pair tile signals its block even when it is empty
+        self.counters = torch.zeros(max(n_edges, 1), self.n_rb, dtype=torch.int32, device=device)
+        self._next = 0
+
+    def reset(self):
+        _emit("sib_fill_zero", (_p(self.counters), self.counters.numel() * 4), keep=(self.counters,))
+
+    def edge(self, kind: str, n: int) -> FlowEdge:
+        if kind not in ("linear", "layernorm", "attention"):
+            raise SibError(f"FlowChain.edge: unknown producer kind {kind!r}")
+        if kind != "linear" and n % 32:
+            raise SibError("FlowChain.edge: a row-wise producer needs a row length that is a multiple of 32")
+        if self._next >= self.counters.shape[0]:
+            raise SibError("FlowChain: more edges requested than allocated")
+        e = FlowEdge(self.counters[self._next], kind, n, self.rows)
+        self._next += 1
+        return e
+
+
+def _flow_struct(rows, wait, signal, n_out):
+    fl = _lib.Flow()
+    for e in (wait, signal):
+        if e is not None and e.rows != rows:
+            raise SibError(f"flow edge over {e.rows} rows used by a launch over {rows} rows")
+    if wait is not None:
+        fl.wait = _p(wait.counters)
+        fl.wait_target, fl.wait_target_last = wait.targets()
+    if signal is not None:
+        if signal.n != n_out:
+            raise SibError(f"flow edge declared for rows of {signal.n} values, the launch writes rows of {n_out}")
+        fl.signal = _p(signal.counters)
+    return fl
 
 
 LN_SLOTS = _lib.SIB_LN_SLOTS
@@ -437,19 +509,36 @@ def conv0_gn_stats(wave, w, bias, c, k, stride, t0, eps, mean, rstd):
           keep=(wave, w, bias, mean, rstd))
 
 
-def layernorm(x, gamma, beta, y, eps=1e-5, residual=None, post_act=ACT_NONE):
+def layernorm(x, gamma, beta, y, eps=1e-5, residual=None, post_act=ACT_NONE, wait=None, signal=None):
     c = x.shape[-1]
     rows = x.numel() // c
     _chk(x, None, "x"); _chk(y, None, "y"); _chk(gamma, torch.float32, "gamma")
     if not (x.is_contiguous() and y.is_contiguous() and (residual is None or residual.is_contiguous())):
         raise SibError("layernorm: tensors must be contiguous")
+    if wait is not None or signal is not None:
+        for t, nme in ((x, "x"), (y, "y"), (residual, "residual")):
+            _chk(t, torch.bfloat16, nme)
+        if post_act != ACT_NONE:
+            raise SibError("layernorm: the dataflow variant has no activation")
+        fl = _flow_struct(rows, wait, signal, c)
+        _emit("sib_layernorm_flow_bf16", (_p(x), _p(residual), _p(gamma), _p(beta), _p(y), rows, c, eps, C.byref(fl)),
+              keep=(x, residual, gamma, beta, y, fl, wait, signal))
+        return
     _emit("sib_layernorm", (_p(x), _dt(x), _p(residual), _dt(residual), _p(gamma), _p(beta), _p(y), _dt(y), rows, c, eps,
                             post_act), keep=(x, residual, gamma, beta, y))
 
 
-def attention(qkv, key_len, out, heads):
+def attention(qkv, key_len, out, heads, wait=None, signal=None):
     B, T, H3 = qkv.shape
     _chk(qkv, None, "qkv"); _chk(out, qkv.dtype, "out"); _chk(key_len, torch.int32, "key_len")
+    if wait is not None or signal is not None:
+        _chk(qkv, torch.bfloat16, "qkv")
+        if not (qkv.is_contiguous() and out.is_contiguous()):
+            raise SibError("attention: the dataflow variant needs dense [B, T, 3H] / [B, T, H] tensors (flat rows)")
+        fl = _flow_struct(B * T, wait, signal, H3 // 3)
+        _emit("sib_attention_flow_bf16", (_p(qkv), _p(key_len), _p(out), B, T, heads, H3 // 3 // heads, C.byref(fl)),
+              keep=(qkv, key_len, out, fl, wait, signal))
+        return
     _emit("sib_attention", (_p(qkv), _dt(qkv), _p(key_len), _p(out), B, T, heads, H3 // 3 // heads), keep=(qkv, key_len, out))
 
 

@@ -90,6 +90,81 @@ def test_hubert_bf16_with_folded_layernorm(sib, name, B, N):
     assert s > SNR_BOUND_DB
 
 
+@pytest.mark.parametrize("name,B,N", [("tiny_group", 3, 8000), ("tiny_layer", 3, 8000), ("base", 5, 32000), ("base", 32, 64000),
+                                      ("large", 3, 24000)])
+def test_hubert_bf16_dataflow_is_bit_identical(sib, name, B, N):
+    """Tile-level dataflow through the transformer loop (`sib_flow`: per-128-row-block counters instead of grid-wide kernel
+    boundaries between out-proj / LayerNorm / FFN-in / FFN-out / LayerNorm / QKV) changes WHEN rows are read, never the
+    arithmetic: the output must equal the plain launch chain's bit for bit - post-LN and pre-LN stacks, row counts with a
+    partial last block, padded batches, and a repeated replay of the same plan (counters reset at the head of every run)."""
+    from oracle.params import HubertCfg, make_hubert_params
+    ocfg = {"tiny_group": HubertCfg.tiny(False), "tiny_layer": HubertCfg.tiny(True), "base": HubertCfg.base(),
+            "large": HubertCfg.large()}[name]
+    params = make_hubert_params(ocfg, 1234)
+    x = 0.1 * torch.randn(B, N, generator=torch.Generator().manual_seed(5))
+    am = torch.ones(B, N, dtype=torch.long)
+    am[1, N - 2000:] = 0
+    outs = {}
+    L = ocfg.num_hidden_layers
+    want = {0: 0, 1: 6 * L - (0 if ocfg.do_stable_layer_norm else 1), 2: 7 * L}   # level 2: every launch of the loop
+    for flow in (0, 1, 2):
+        model = sib.HubertModel(sib.HubertConfig.from_any(ocfg), precision="bf16").to("cuda")
+        model.flow = flow
+        model.load_state_dict(params)
+        res = []
+        for mask in (None, am, None):
+            res.append(model(x.cuda(), None if mask is None else mask.cuda()).last_hidden_state.cpu())
+        plan = list(model._plans.values())[0].plan
+        n_flow = sum(1 for _, _, nme in plan.steps if nme in ("sib_linear_flow_bf16", "sib_layernorm_flow_bf16", "sib_attention_flow_bf16"))
+        assert n_flow == want[flow]
+        assert torch.equal(res[0], res[2])
+        outs[flow] = res
+    for level in (1, 2):
+        for a, b in zip(outs[0], outs[level]):
+            assert torch.isfinite(a).all()
+            assert torch.equal(a, b)
+
+
+def test_linear_flow_chain_against_plain_launches(sib):
+    """Three chained linear layers + a LayerNorm through `sib_linear_flow_bf16` / `sib_layernorm_flow_bf16` on 6368 rows
+    (49 full blocks + 96 rows; CTA pairs) and on 300 rows against the same launches without counters."""
+    ops = sib.ops
+    g = torch.Generator().manual_seed(9)
+    for M in (6368, 300, 128):
+        H, I = 768, 3072
+        x = torch.randn(M, H, generator=g).to("cuda", torch.bfloat16)
+        w1 = ops.to_kmajor_bf16(ops.pack_linear_weight((0.03 * torch.randn(I, H, generator=g)).cuda()))
+        w2 = ops.to_kmajor_bf16(ops.pack_linear_weight((0.03 * torch.randn(H, I, generator=g)).cuda()))
+        b1, b2 = (0.1 * torch.randn(I, generator=g)).cuda(), (0.1 * torch.randn(H, generator=g)).cuda()
+        gam, bet = (1 + 0.1 * torch.randn(H, generator=g)).cuda(), (0.1 * torch.randn(H, generator=g)).cuda()
+        res = {}
+        for flow in (False, True):
+            h1 = torch.empty(M, I, device="cuda", dtype=torch.bfloat16)
+            h2 = torch.empty(M, H, device="cuda", dtype=torch.bfloat16)
+            n1 = torch.empty(M, H, device="cuda", dtype=torch.bfloat16)
+            h3 = torch.empty(M, I, device="cuda", dtype=torch.bfloat16)
+            if flow:
+                ch = ops.FlowChain(M, 3, "cuda")
+                for _ in range(3):      # replayed: the counters are reset at the head of every run
+                    ch._next = 0
+                    ch.reset()
+                    e1, e2, e3 = ch.edge("linear", I), ch.edge("linear", H), ch.edge("layernorm", H)
+                    ops.linear(x, w1, b1, h1, post_act=ops.ACT_GELU, signal=e1)
+                    ops.linear(h1, w2, b2, h2, residual=x, wait=e1, signal=e2)
+                    ops.layernorm(h2, gam, bet, n1, 1e-5, residual=x, wait=e2, signal=e3)
+                    ops.linear(n1, w1, b1, h3, wait=e3)
+            else:
+                ops.linear(x, w1, b1, h1, post_act=ops.ACT_GELU)
+                ops.linear(h1, w2, b2, h2, residual=x)
+                ops.layernorm(h2, gam, bet, n1, 1e-5, residual=x)
+                ops.linear(n1, w1, b1, h3)
+            torch.cuda.synchronize()
+            res[flow] = (h1.cpu(), h2.cpu(), n1.cpu(), h3.cpu())
+        for a, b in zip(res[False], res[True]):
+            assert torch.isfinite(a.float()).all()
+            assert torch.equal(a, b)
+
+
 def test_informed_inpainting_bf16_config1(sib):
     """config #1 shapes through the bf16 arm: labels vs fp32 oracle (agreement rate), waveform mel-L1."""
     from oracle import mel_ref
