@@ -461,6 +461,15 @@ class HubertModel(SibModule):
         ln1 = (self._w(b + "layer_norm.weight"), self._w(b + "layer_norm.bias"))
         ln2 = (self._w(b + "final_layer_norm.weight"), self._w(b + "final_layer_norm.bias"))
         if chain is not None:
+            # Buffer reuse under dataflow (no grid-wide barrier any more), checked per 128-row block m:
+            #  * every linear layer / LayerNorm of the loop reads and writes block m only, and its wait on block m of its producer
+            #    implies (transitively, release / acquire is cumulative) that all earlier launches have finished block m - so
+            #    tmp / nrm / ff / h are overwritten only after their last reader of that block is done; the in-place residual
+            #    updates of the pre-LN stack read and write the same tile;
+            #  * the attention kernel reads whole utterances: it waits for every block an utterance touches, and the out-projection
+            #    waits for the attention rows of its block, i.e. for all launches of the previous layers on the blocks of the
+            #    utterances in it.  The one buffer that is NOT safe is qkv: a late utterance of layer l may still read keys in a
+            #    block that layer l + 1's projection (gated only on its own block) may overwrite - the caller alternates two buffers.
             I = ff.shape[-1]
             v2 = lambda t: t.view(M, -1)   # noqa: E731
             e1, e3 = chain.edge("linear", H), chain.edge("linear", I)
