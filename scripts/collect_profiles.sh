@@ -29,6 +29,9 @@ for CASE in s2k3c2n ffn1g; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv1d_bf16 -c 2 -o $OUT/prof_conv_${CASE}_$TAG -f \
       python scripts/tc_microbench.py --only $CASE --iters 1 > $OUT/ncu_tc_$CASE.log 2>&1
 done
+python scripts/attn_microbench.py --only base_4s --iters 1 > $OUT/plain_attn.log 2>&1 &&
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc -c 1 -o $OUT/prof_attn_$TAG -f \
+    python scripts/attn_microbench.py --only base_4s --iters 1 > $OUT/ncu_attn.log 2>&1
 python scripts/aux_microbench.py --only mel > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:mel_kernel -c 1 -o $OUT/prof_mel_$TAG -f \
     python scripts/aux_microbench.py > $OUT/ncu_mel.log 2>&1
