@@ -16,9 +16,12 @@ FAMILIES = ["conv1d_bf16_tc_kernel", "resunit_tc_kernel", "attention_tc_kernel",
 
 
 def family(name):
-    m = re.search(r"(conv1d_bf16_tc_kernel|resunit_tc_kernel)<[^>]*?(\d)>", name)
+    # template arguments: conv1d_bf16_tc_kernel<POST_ACT, PAIR, EPI, FLOW>, resunit_tc_kernel<PAIR, WIDE>
+    m = re.search(r"(conv1d_bf16_tc_kernel|resunit_tc_kernel)<([^>]*)>", name)
     if m:
-        return m.group(1), ("pair, cta_group::2" if m.group(2) == "1" else "single CTA")
+        args = [a.strip().split(")")[-1] for a in m.group(2).split(",")]
+        pair = args[1] if m.group(1) == "conv1d_bf16_tc_kernel" and len(args) > 1 else args[0]
+        return m.group(1), ("pair, cta_group::2" if pair == "1" else "single CTA")
     for k in FAMILIES:
         if k in name:
             return k, None
