@@ -292,7 +292,12 @@ def ncu_traffic(kernel_key, workload_key):
     ncu capture of this same command and workload (profiles/r*_ncu_step_*_summary.json); (None, None) if there is none.
     The summary carries the git head of the tree it was captured on, which goes into `roofline.traffic_note`."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_step_*_summary.json")), key=os.path.getmtime)
+    import re
+
+    def order(f):   # (round, capture version) from r02_ncu_step_cfg2_v4_summary.json; a checkout gives every file the same mtime
+        m = re.search(r"r(\d+)_ncu_step_.*?v(\d+)_summary", os.path.basename(f))
+        return (int(m.group(1)), int(m.group(2))) if m else (0, 0)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_step_*_summary.json")), key=lambda f: (order(f), os.path.getmtime(f)))
     for f in reversed(files):
         try:
             doc = json.load(open(f))
