@@ -918,7 +918,22 @@ static int conv1d_bf16_impl(const sib_conv_desc* d, const void* x, const void* w
   const int slab_total = a.nb * (1 + a.need_r) * 4 * 32 * cw * 2;  // nb x (y [+ r]) boxes for 4 epilogue warp pairs
   // narrow layers (bn <= 32: 8 KB output tiles) are bound by the per-tile latency chain of one CTA, not by any
   // throughput: run two persistent CTAs per SM on half the shared memory each
-  const int ctas_per_sm = (bn <= 32 && !pair && !flow) ? 2 : 1;   // (the dataflow kernels are built for one CTA per SM)
+  int ctas_per_sm = (bn <= 32 && !pair && !flow) ? 2 : 1;   // (the dataflow kernels are built for one CTA per SM)
+  // r2: the same holds for 64-wide tiles whose weights stay resident next to two halo stages in HALF the shared memory (k = 3
+  // layers at C = 64: `ups.3`, the I_da stages): one 16 KB output block per tile leaves the epilogue's per-block latency
+  // (TMEM load, fence, barrier, store issue) as the pace of a single CTA - C = 64, k = 3, 32 x 44032: 0.105 -> 0.077 ms,
+  // 3.4 -> 4.7 TB/s.  Layers with a residual input keep one CTA per SM (their epilogue build has no 85-register variant).
+  static const bool two_cta_64 = !(getenv("SIB_TC_2CTA_64") && atoi(getenv("SIB_TC_2CTA_64")) == 0);   // A/B switch
+  if (two_cta_64 && ctas_per_sm == 1 && bn <= 64 && !pair && !flow && !ln && halo && d->groups == 1 && cout_g == bn &&
+      !residual && !d->accumulate) {
+    const int avail2 = 112 * 1024 - 2048 - slab_total - 1024;
+    const int a_stage2 = (rows_h * row_bytes + 1023) / 1024 * 1024;
+    int tg2 = 16384 / a.b_tap_bytes;
+    if (tg2 < 1) tg2 = 1;
+    if (tg2 > d->n_taps) tg2 = d->n_taps;
+    const int slabs2 = a.n_chunks * d->n_taps, rloads2 = (slabs2 + tg2 - 1) / tg2, rtg2 = (slabs2 + rloads2 - 1) / rloads2;
+    if (rloads2 * rtg2 * a.b_tap_bytes + 2 * a_stage2 <= avail2) ctas_per_sm = 2;
+  }
   const int smem_budget = ctas_per_sm == 2 ? 112 * 1024 : 227 * 1024;
   const int avail = smem_budget - 2048 - slab_total - 1024;
 
