@@ -214,27 +214,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
       const int nk16 = (nk + 15) & ~15;
       mbar_wait(s_full, g & 1);
       tc_fence_after();
+      // only the last 16-column group of a block can hold keys past the utterance's end: the full groups run without the
+      // per-element compare / select (two of the ~7 instructions per score; the softmax warps are 60 % ALU-busy, ncu)
+      const int nfull = nk & ~15;
       float mx = -INFINITY;
-      for (int c0 = 0; c0 < nk16; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_s + (uint32_t)c0, v);
+      int c1 = 0;
+      for (; c1 + 32 <= nfull; c1 += 32) {            // two TMEM loads in flight per wait
+        uint32_t va[16], vb[16];
+        tmem_ld16_nowait(t_s + (uint32_t)c1, va);
+        tmem_ld16_nowait(t_s + (uint32_t)(c1 + 16), vb);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c0 + i < nk) ? __uint_as_float(v[i]) : -INFINITY);
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+      }
+      for (; c1 < nfull; c1 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_s + (uint32_t)c1, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      if (nfull < nk16) {
+        uint32_t v[16];
+        tmem_ld16(t_s + (uint32_t)nfull, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (nfull + i < nk) ? __uint_as_float(v[i]) : -INFINITY);
       }
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2((m_run - m_new) * c);   // exp2(-inf) = 0 on the first block
       const float mc = m_new * c;
       mbar_wait(p_empty, (g & 1) ^ 1);                      // the P V MMAs of the previous block have read P
       float sum = 0.f;
-      for (int c0 = 0; c0 < nk16; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_s + (uint32_t)c0, v);
-        float p[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          p[i] = (c0 + i < nk) ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
-          sum += p[i];
-        }
+      auto emit_p = [&](const float (&p)[16], int c0) {
         const uint32_t chunk = prow + (uint32_t)((c0 >> 6) * TILE_BYTES);
         const uint32_t u = (uint32_t)((c0 & 63) >> 3);
         float lo[8], hi[8];
@@ -242,6 +252,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* 
         for (int i = 0; i < 8; ++i) { lo[i] = p[i]; hi[i] = p[8 + i]; }
         sts128(chunk + ((u ^ swz) << 4), pack8(lo));
         sts128(chunk + (((u + 1) ^ swz) << 4), pack8(hi));
+      };
+      for (int c0 = 0; c0 < nfull; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_s + (uint32_t)c0, v);
+        float p[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          p[i] = fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc));
+          sum += p[i];
+        }
+        emit_p(p, c0);
+      }
+      if (nfull < nk16) {
+        uint32_t v[16];
+        tmem_ld16(t_s + (uint32_t)nfull, v);
+        float p[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          p[i] = (nfull + i < nk) ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          sum += p[i];
+        }
+        emit_p(p, nfull);
       }
       l_run = l_run * alpha + sum;
       m_run = m_new;
