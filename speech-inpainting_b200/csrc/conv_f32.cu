@@ -230,12 +230,12 @@ __global__ void __launch_bounds__(256) conv1d_cout1_kernel(const TX* __restrict_
 // (16-byte loads), forms its K partial products <x_row, w_j> against broadcast float4 weight loads and parks them in
 // shared memory; output t then sums K neighbouring partials.  Every activation byte is read once per CTA instead of
 // K times and the per-output shared-memory traffic drops from K*C scalar weight loads to K*C/4 vector ones.
-constexpr int CO1_TILE = 256, CO1_MAXK = 8;
-__global__ void __launch_bounds__(CO1_TILE) conv1d_cout1_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x,
-                                                                         const float* __restrict__ w,
-                                                                         const float* __restrict__ bias,
-                                                                         float* __restrict__ y, int T, int C, int K, int pad,
-                                                                         float pre_slope, int post_act) {
+constexpr int CO1_ROWS = 2, CO1_THREADS = 256, CO1_TILE = CO1_ROWS * CO1_THREADS, CO1_MAXK = 8;
+__global__ void __launch_bounds__(CO1_THREADS) conv1d_cout1_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                            const float* __restrict__ w,
+                                                                            const float* __restrict__ bias,
+                                                                            float* __restrict__ y, int T, int C, int K, int pad,
+                                                                            float pre_slope, int post_act) {
   extern __shared__ float sm[];
   float* ws = sm;                                  // [K][C]
   float* part = sm + K * C;                        // [K][CO1_TILE + CO1_MAXK]
@@ -243,52 +243,69 @@ __global__ void __launch_bounds__(CO1_TILE) conv1d_cout1_bf16_rows_kernel(const 
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
   const int b = blockIdx.y;
-  // a CTA produces CO1_TILE - (K - 1) outputs from exactly CO1_TILE input rows: one row per thread, no second loop trip
-  // in which six threads of warp 0 would redo a whole row's work while 250 wait at the barrier
+  // a CTA produces CO1_TILE - (K - 1) outputs from exactly CO1_TILE input rows.  r2: a thread owns CO1_ROWS rows (r, r + 256,
+  // ...) and uses every broadcast weight load for all of them - the kernel was bound by the load / store unit (ncu: LSU
+  // wavefronts 88 %, 56 weight loads of 16 bytes per row), not by HBM: 81 -> 70.6 us with two rows, 73.6 with four
   const int tile_out = CO1_TILE - (K - 1);
   const int t0 = blockIdx.x * tile_out;
   const __nv_bfloat16* xb = x + (int64_t)b * T * C;
-  const int rows = CO1_TILE;
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-    const int ti = t0 - pad + r;
-    float p[CO1_MAXK];
+  {
+    const int r = threadIdx.x;
+    float p[CO1_ROWS][CO1_MAXK];
+    const uint4* xr[CO1_ROWS];
+    bool in[CO1_ROWS];
 #pragma unroll
-    for (int j = 0; j < CO1_MAXK; ++j) p[j] = 0.f;
-    if (ti >= 0 && ti < T) {
-      const uint4* xr = reinterpret_cast<const uint4*>(xb + (int64_t)ti * C);
-      for (int c8 = 0; c8 < (C >> 3); ++c8) {
-        const uint4 raw = __ldg(xr + c8);
+    for (int q = 0; q < CO1_ROWS; ++q) {
+      const int ti = t0 - pad + r + q * CO1_THREADS;
+      in[q] = ti >= 0 && ti < T;
+      xr[q] = reinterpret_cast<const uint4*>(xb + (int64_t)(in[q] ? ti : 0) * C);
+#pragma unroll
+      for (int j = 0; j < CO1_MAXK; ++j) p[q][j] = 0.f;
+    }
+    for (int c8 = 0; c8 < (C >> 3); ++c8) {
+      float f[CO1_ROWS][8];
+#pragma unroll
+      for (int q = 0; q < CO1_ROWS; ++q) {
+        const uint4 raw = in[q] ? __ldg(xr[q] + c8) : make_uint4(0u, 0u, 0u, 0u);
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-        float f[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 v = __bfloat1622float2(h2[i]);
-          f[2 * i] = v.x > 0.f ? v.x : v.x * pre_slope;
-          f[2 * i + 1] = v.y > 0.f ? v.y : v.y * pre_slope;
+          f[q][2 * i] = v.x > 0.f ? v.x : v.x * pre_slope;
+          f[q][2 * i + 1] = v.y > 0.f ? v.y : v.y * pre_slope;
         }
+      }
 #pragma unroll
-        for (int j = 0; j < CO1_MAXK; ++j) {
-          if (j < K) {
-            const float4 wa = *reinterpret_cast<const float4*>(ws + j * C + c8 * 8);
-            const float4 wb = *reinterpret_cast<const float4*>(ws + j * C + c8 * 8 + 4);
-            p[j] = fmaf(f[0], wa.x, p[j]); p[j] = fmaf(f[1], wa.y, p[j]); p[j] = fmaf(f[2], wa.z, p[j]); p[j] = fmaf(f[3], wa.w, p[j]);
-            p[j] = fmaf(f[4], wb.x, p[j]); p[j] = fmaf(f[5], wb.y, p[j]); p[j] = fmaf(f[6], wb.z, p[j]); p[j] = fmaf(f[7], wb.w, p[j]);
+      for (int j = 0; j < CO1_MAXK; ++j) {
+        if (j < K) {
+          const float4 wa = *reinterpret_cast<const float4*>(ws + j * C + c8 * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(ws + j * C + c8 * 8 + 4);
+#pragma unroll
+          for (int q = 0; q < CO1_ROWS; ++q) {
+            float a = p[q][j];
+            a = fmaf(f[q][0], wa.x, a); a = fmaf(f[q][1], wa.y, a); a = fmaf(f[q][2], wa.z, a); a = fmaf(f[q][3], wa.w, a);
+            a = fmaf(f[q][4], wb.x, a); a = fmaf(f[q][5], wb.y, a); a = fmaf(f[q][6], wb.z, a); a = fmaf(f[q][7], wb.w, a);
+            p[q][j] = a;
           }
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < CO1_MAXK; ++j)
-      if (j < K) part[j * PW + r] = p[j];
+    for (int q = 0; q < CO1_ROWS; ++q)
+#pragma unroll
+      for (int j = 0; j < CO1_MAXK; ++j)
+        if (j < K) part[j * PW + r + q * CO1_THREADS] = p[q][j];
   }
   __syncthreads();
-  const int t = t0 + threadIdx.x;
-  if ((int)threadIdx.x >= tile_out || t >= T) return;
-  float acc = bias ? bias[0] : 0.f;
+  for (int o = threadIdx.x; o < tile_out; o += CO1_THREADS) {
+    const int t = t0 + o;
+    if (t >= T) break;
+    float acc = bias ? bias[0] : 0.f;
 #pragma unroll
-  for (int j = 0; j < CO1_MAXK; ++j)
-    if (j < K) acc += part[j * PW + threadIdx.x + j];   // input row t + j - pad sits at local index threadIdx.x + j
-  y[(int64_t)b * T + t] = sib::apply_act(acc, post_act, 0.f);
+    for (int j = 0; j < CO1_MAXK; ++j)
+      if (j < K) acc += part[j * PW + o + j];   // input row t + j - pad sits at local index o + j
+    y[(int64_t)b * T + t] = sib::apply_act(acc, post_act, 0.f);
+  }
 }
 
 }  // namespace
@@ -333,7 +350,7 @@ extern "C" int sib_conv1d_cout1(const void* x, int x_dtype, const float* w, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x_dtype == SIB_BF16 && c % 8 == 0 && k <= CO1_MAXK) {
     const size_t smem2 = ((size_t)k * c + (size_t)k * (CO1_TILE + CO1_MAXK)) * sizeof(float);
-    conv1d_cout1_bf16_rows_kernel<<<dim3(sib::ceil_div(t, CO1_TILE - (k - 1)), batch), CO1_TILE, smem2, s>>>(
+    conv1d_cout1_bf16_rows_kernel<<<dim3(sib::ceil_div(t, CO1_TILE - (k - 1)), batch), CO1_THREADS, smem2, s>>>(
         (const __nv_bfloat16*)x, w, bias, y, t, c, k, pad, pre_slope, post_act);
   } else if (x_dtype == SIB_BF16)
     conv1d_cout1_kernel<<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, w, bias, y, t, c, k, pad, pre_slope, post_act);
