@@ -49,6 +49,8 @@ struct RuArgs {
   float slope_in, slope_mid, out_scale, act2_slope;
   int accumulate, has_y2;
   int early_w;                                           // resident weights fetched before the PDL dependency wait
+  int e2w;                                               // epilogue-2 warps of the C <= 64 builds: 4, or 8 (warps 12-15 join: two
+                                                         // column halves per TMEM lane quarter; the activation stage keeps warps 2-3)
   // C = 128 ("wide", CTA pairs only): a row is TWO 64-channel chunks, every operand tile is two 128-byte-swizzled slabs
   int nch;                                               // channel chunks per row: 1, or 2 when C = 128
   int x_chunk_bytes, t1_chunk_bytes;                     // one chunk slab of an x stage / of the intermediate tile
@@ -131,7 +133,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int s = 0; s < 4; ++s) {
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
-      mbar_init(&act_done[s], (PAIR ? 2 : 1) * (WIDE ? ACT_WARPS_WIDE : ACT_WARPS));
+      mbar_init(&act_done[s], (PAIR ? 2 : 1) * (WIDE ? ACT_WARPS_WIDE : (p.e2w == 8 ? 2 : ACT_WARPS)));
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&acc1_full[s], 1);
@@ -141,7 +143,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc2_full[s], 1);
-      mbar_init(&acc2_empty[s], WIDE ? 16 : (PAIR ? 8 : 4));
+      mbar_init(&acc2_empty[s], WIDE ? 16 : (PAIR ? 2 : 1) * p.e2w);
     }
     mbar_init(w_full, 1);
     for (int s = 0; s < 12; ++s) mbar_init(&res_bar[s], 1);
@@ -301,12 +303,12 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (i + p.la < n_my) conv1();
       conv2(i);
     }
-  } else if (warp == 2 || warp == 3 || (!WIDE && warp >= 12)) {
+  } else if (warp == 2 || warp == 3 || (!WIDE && p.e2w == 4 && warp >= 12)) {
     // ===================== activation: leaky-relu in place on the freshly landed x tile =====================
     // (six warps: with two, this stage paced the whole kernel on the short k = 3 tiles - the MMA warp sat on act_done)
     // bf16x2 arithmetic as in sib_conv1d_bf16: slope * x = x * hi + x * lo with hi + lo = slope to ~2^-17 (no slope bias
     // from rounding 0.1 to bf16), then max(x, slope * x): 12 instead of 28 ALU instructions per 16-byte chunk
-    constexpr int AW = WIDE ? ACT_WARPS_WIDE : ACT_WARPS;
+    const int AW = WIDE ? ACT_WARPS_WIDE : (p.e2w == 8 ? 2 : ACT_WARPS);
     const int tid = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
     const int n16 = ((WIDE ? p.x_chunk_bytes : 0) + p.xr * p.row_bytes) >> 4;   // wide: chunk 0's slab (with its pad) + chunk 1
     const __nv_bfloat16 s_hi = __float2bfloat16_rn(p.slope_in);
@@ -477,9 +479,16 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp >= 8 && (warp < 12 || (!WIDE && p.e2w == 8))) {
     // ===================== epilogue 2: conv2 accumulator + bias + x (+ running sum) -> y (and lrelu(y)) ==========
+    // e2w == 8 (r2): warps (8 + q, 12 + q) share TMEM lane quarter q and take the two column halves of the tile's rows - this
+    // stage paced the k = 3 units (7 % of its samples in waits against 40-57 % for the others); warp 8 + q drives the TMA
+    // traffic of the quarter's staging box, a 64-thread named barrier orders the partner's writes before the store
     const int q = warp & 3;
+    const int half = warp >= 12 ? 1 : 0;
+    const bool two = p.e2w == 8;
+    const int c_begin = two ? half * (p.C >> 1) : 0, c_end = two ? c_begin + (p.C >> 1) : p.C;
+    const bool leader = half == 0 && lane == 0;
     const int chunks_per_row = p.row_bytes >> 4;
     const int swz_shift = p.row_bytes == 128 ? 0 : (p.row_bytes == 64 ? 1 : 2);
     const uint32_t swz = ((uint32_t)lane >> swz_shift) & (uint32_t)(chunks_per_row - 1);
@@ -496,7 +505,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         tma_load_3d(sm_sb + slot * p.stage_box_bytes + q * box_bytes, &map_y, &my_res[slot], 0, t0 + q * 32, b);
     };
     TileCursor tc = cursor0(), tn = cursor0();                 // this tile / the next one (prefetch target)
-    if (lane == 0 && n_my > 0) prefetch(tn, 0);
+    if (leader && n_my > 0) prefetch(tn, 0);
     tn.next();
     int slot = 0;
     uint32_t res_phase_bits = 0;
@@ -505,7 +514,7 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       const bool valid = tc.valid();
       const int a = i & 1;
       const int next_slot = slot + 1 == p.slots ? 0 : slot + 1;
-      if (lane == 0 && p.slots >= 2) {
+      if (leader && p.slots >= 2) {
         // the slot of tile i+1 was last stored from slots-1 tiles ago: with three slots the store of the previous tile
         // may still be draining while the next residual is already being fetched
         if (p.slots == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -577,19 +586,20 @@ resunit_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           }
         }
       };
-      for (int c0 = 0; c0 < p.C; c0 += 32) {                   // two TMEM loads in flight per wait
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {           // two TMEM loads in flight per wait
         uint32_t va[16], vb[16];
         tmem_ld16_nowait(taddr + (uint32_t)c0, va);
-        if (c0 + 16 < p.C) tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), vb);
+        if (c0 + 16 < c_end) tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), vb);
         tmem_ld_wait();
         emit16(va, c0);
-        if (c0 + 16 < p.C) emit16(vb, c0 + 16);
+        if (c0 + 16 < c_end) emit16(vb, c0 + 16);
       }
       tc_fence_before();
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        arrive_mma(&acc2_empty[a]);
+      if (lane == 0) arrive_mma(&acc2_empty[a]);
+      if (two) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // both column halves of the box are written
+      if (leader) {
         if (rows_q > 0 && valid) {
           const uint8_t* src_a = sm_sa + slot * p.stage_box_bytes + q * box_bytes;
           const uint8_t* src_b = sm_sb + slot * p.stage_box_bytes + q * box_bytes;
@@ -721,6 +731,12 @@ int plan_resunit_mode(int c, int k, int dil, int accumulate, int has_y2, int pai
     while (pw < cols) pw <<= 1;
     a.tmem_cols = pw;
   }
+  static const int force_e2w = getenv("SIB_RU_EPI2_WARPS") ? atoi(getenv("SIB_RU_EPI2_WARPS")) : 0;   // A/B switch: 4 or 8
+  // measured per configuration (standalone, same box, 4 -> 8 warps): C = 64 k = 3 0.121 -> 0.106 ms, C = 32 k = 11 0.226 -> 0.217;
+  // C = 32 k = 3 / 7 and C = 64 k = 7 within +-3 %; the C = 64 k = 11 pair units 0.240 -> 0.273 (their 23 KB tiles need the six
+  // activation warps) - so eight only where it pays
+  const bool e2w8 = !wide && ((c == 64 && !pair && k <= 3) || (c == 32 && k >= 11));
+  a.e2w = force_e2w == 4 ? 4 : (force_e2w == 8 && !wide && c >= 32 ? 8 : (e2w8 ? 8 : 4));
   out->ctas_per_sm = (!pair && out->smem_bytes <= 115 * 1024 - 1024) ? 2 : 1;
   return SIB_OK;
 }
