@@ -101,20 +101,34 @@ def test_c_abi_library_exports_every_declared_symbol(sib):
     assert lib.sib_abi_version() == 2
 
 
-def test_conv_desc_layout_matches_header(sib, tmp_path):
-    """struct layout agreement between include/*.h (compiled with gcc) and the ctypes mirror."""
-    from speech_inpainting_b200._lib import ConvDesc
-    fields = [f[0] for f in ConvDesc._fields_]
+@pytest.mark.parametrize("cname,pyname", [("sib_conv_desc", "ConvDesc"), ("sib_resunit_desc", "ResUnitDesc"), ("sib_ln_fold", "LnFold"),
+                                          ("sib_flow", "Flow")])
+def test_struct_layouts_match_header(sib, tmp_path, cname, pyname):
+    """struct layout agreement between include/*.h (compiled with gcc) and every ctypes mirror."""
+    from speech_inpainting_b200 import _lib
+    mirror = getattr(_lib, pyname)
+    fields = [f[0] for f in mirror._fields_]
     src = tmp_path / "layout.c"
-    lines = "\n".join(f'  printf("{f} %zu\\n", offsetof(sib_conv_desc, {f}));' for f in fields)
+    lines = "\n".join(f'  printf("{f} %zu\\n", offsetof({cname}, {f}));' for f in fields)
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "speech_inpainting_b200.h"\nint main(void) {\n'
-                   f'  printf("sizeof %zu\\n", sizeof(sib_conv_desc));\n{lines}\n  return 0;\n}}\n')
+                   f'  printf("sizeof %zu\\n", sizeof({cname}));\n{lines}\n  return 0;\n}}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
-    assert int(out["sizeof"]) == ctypes.sizeof(ConvDesc)
+    assert int(out["sizeof"]) == ctypes.sizeof(mirror)
     for f in fields:
-        assert int(out[f]) == getattr(ConvDesc, f).offset, f
+        assert int(out[f]) == getattr(mirror, f).offset, f
+
+
+def test_flow_edge_targets():
+    """Dataflow counters (`sib_flow`): what a complete 128-row block is worth per producer kind.  A linear layer stores whole
+    32-row quarters of every tile (4 x n per block, valid rows or not); LayerNorm and attention add n / 32 per VALID row,
+    so only their last block's target depends on the row count."""
+    from speech_inpainting_b200.ops import FlowEdge
+    assert FlowEdge(None, "linear", 768, 6368).targets() == (3072, 3072)
+    assert FlowEdge(None, "layernorm", 768, 6368).targets() == (3072, 96 * 24)          # 6368 = 49 x 128 + 96
+    assert FlowEdge(None, "attention", 1024, 256).targets() == (4096, 128 * 32)        # a full last block
+    assert FlowEdge(None, "layernorm", 128, 72).targets() == (512, 72 * 4)
 
 
 def test_no_product_import_of_oracle():
